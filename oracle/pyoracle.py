@@ -1,0 +1,215 @@
+"""ctypes loaders for the CPU oracle -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this.  The product package (mlvfs_b200/) never does.
+
+  load_oracle()  -> oracle/liboracle.so          (our C restatement, oracle/*.c)
+  load_ref()     -> oracle/_ref/libmlvfs_ref.so  (the unmodified reference compiled by oracle/Makefile;
+                                                  None when it was never built)
+"""
+import contextlib
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libmlvfs_ref.so")
+REFERENCE_SRC = "/root/reference/mlvfs"
+
+
+class Pixel(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int)]
+
+
+class RandState(C.Structure):
+    _fields_ = [("r", C.c_uint32 * 34), ("f", C.c_int), ("b", C.c_int), ("primed", C.c_int)]
+
+
+def build(ref=True, quiet=True):
+    """Compile liboracle.so and, where the reference sources exist, oracle/_ref."""
+    out = subprocess.DEVNULL if quiet else None
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"], stdout=out)
+    if ref and os.path.isdir(REFERENCE_SRC):
+        subprocess.check_call(["make", "-s", "-C", HERE, "-j8", "ref"], stdout=out)
+
+
+_oracle = None
+_ref = None
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def load_oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        lib = C.CDLL(ORACLE_SO)
+        lib.orc_raw2ev.restype = C.POINTER(C.c_int)
+        lib.orc_raw2evf.restype = C.POINTER(C.c_double)
+        lib.orc_ev2raw.restype = C.POINTER(C.c_int)
+        lib.orc_unpack.restype = C.c_size_t
+        lib.orc_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_size_t, C.c_int]
+        lib.orc_badpix_detect.restype = C.c_size_t
+        lib.orc_badpix_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_size_t]
+        lib.orc_badpix_apply.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                         C.c_int, C.c_int, C.c_int]
+        lib.orc_focuspix_apply.argtypes = lib.orc_badpix_apply.argtypes
+        lib.orc_chroma_smooth_u16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.orc_chroma_smooth_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p]
+        lib.orc_stripes_compute.restype = C.c_int
+        lib.orc_stripes_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+        lib.orc_stripes_apply.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.orc_rand_seed.argtypes = [C.c_void_p, C.c_uint]
+        lib.orc_rand_next.argtypes = [C.c_void_p]
+        _oracle = lib
+    return _oracle
+
+
+def load_ref():
+    """The compiled reference, or None if oracle/_ref was not built (no /root/reference at build time)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            if os.path.isdir(REFERENCE_SRC):
+                build(ref=True)
+            else:
+                return None
+        lib = C.CDLL(REF_SO)
+        lib.ref_process_frame.restype = C.c_size_t
+        lib.ref_process_frame.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.ref_sizeof_frame_headers.restype = C.c_size_t
+        lib.ref_offsetof_frame_headers.restype = C.c_size_t
+        lib.dng_get_image_data.restype = C.c_size_t
+        lib.dng_get_image_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_size_t]
+        lib.get_raw2ev.restype = C.POINTER(C.c_int)
+        lib.get_ev2raw.restype = C.POINTER(C.c_int)
+        lib.get_raw2evf.restype = C.POINTER(C.c_double)
+        lib.stripes_new_correction.restype = C.c_void_p
+        lib.stripes_get_correction.restype = C.c_void_p
+        lib.ref_init()
+        _ref = lib
+    return _ref
+
+
+@contextlib.contextmanager
+def quiet_stdout():
+    """The reference printf()s per frame; silence fd 1 around calls into it."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+# ---- numpy-friendly wrappers around the restatement -------------------------------------------
+
+def unpack(words, npix, bpp=14, offset=0, nbytes=None):
+    lib = load_oracle()
+    words = np.ascontiguousarray(words, dtype=np.uint16)
+    nbytes = npix * 2 if nbytes is None else nbytes
+    out = np.zeros(nbytes // 2, dtype=np.uint16)
+    first_word = (max(0, offset) // 2) * bpp // 16
+    lib.orc_unpack(C.c_void_p(words.ctypes.data + 2 * first_word), _p(out), offset, nbytes, bpp)
+    return out
+
+
+def chroma_smooth(img, black, method):
+    lib = load_oracle()
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    lib.orc_chroma_smooth_u16(_p(out), w, h, black, method)
+    return out
+
+
+def badpix_detect(img, black, aggressive, crop=(0, 0)):
+    lib = load_oracle()
+    img = np.ascontiguousarray(img, dtype=np.uint16)
+    h, w = img.shape
+    cap = 1 << 16
+    while True:
+        arr = (Pixel * cap)()
+        n = lib.orc_badpix_detect(_p(img), w, h, black, int(aggressive), crop[0], crop[1], arr, cap)
+        if n <= cap:
+            break
+        cap = int(n)
+    return np.frombuffer(arr, dtype=np.int32, count=2 * n).reshape(n, 2).copy()
+
+
+def badpix_apply(img, black, plist, crop=(0, 0), dual_iso=0):
+    lib = load_oracle()
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    pl = np.ascontiguousarray(plist, dtype=np.int32)
+    lib.orc_badpix_apply(_p(out), w, h, black, _p(pl), len(pl), crop[0], crop[1], dual_iso)
+    return out
+
+
+def focuspix_apply(img, black, pmap, crop=(0, 0), dual_iso=0):
+    lib = load_oracle()
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    pl = np.ascontiguousarray(pmap, dtype=np.int32)
+    lib.orc_focuspix_apply(_p(out), w, h, black, _p(pl), len(pl), crop[0], crop[1], dual_iso)
+    return out
+
+
+def stripes_compute(img, black, white, frame_size, rng=None):
+    lib = load_oracle()
+    img = np.ascontiguousarray(img, dtype=np.uint16)
+    h, w = img.shape
+    if rng is None:
+        rng = RandState()
+        lib.orc_rand_seed(C.byref(rng), 1)
+    coef = np.zeros(8, dtype=np.int32)
+    needed = lib.orc_stripes_compute(_p(img), w, h, black, white, frame_size, C.byref(rng), _p(coef))
+    return needed, coef
+
+
+def stripes_apply(img, black, white, needed, coef):
+    lib = load_oracle()
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    coef = np.ascontiguousarray(coef, dtype=np.int32)
+    lib.orc_stripes_apply(_p(out), out.size, w, black, white, int(needed), _p(coef))
+    return out
+
+
+def single_iso_chain(frames, black, white, frame_size, *, chroma_smooth_method=0, fix_bad_pixels=0,
+                     fix_stripes=0, state=None):
+    """process_frame's single-ISO stage order (main.c:966-997) over a list of unpacked frames.
+
+    Per-clip state (bad-pixel list, stripe coefficients) comes from the first frame processed,
+    exactly as in the reference.  Returns (list of frames, state).
+    """
+    state = state if state is not None else {}
+    outs = []
+    for fr in frames:
+        img = np.ascontiguousarray(fr, dtype=np.uint16).copy()
+        if fix_bad_pixels:
+            if "badpix" not in state:
+                state["badpix"] = badpix_detect(img, black, fix_bad_pixels == 2)
+            img = badpix_apply(img, black, state["badpix"])
+        if chroma_smooth_method:
+            img = chroma_smooth(img, black, chroma_smooth_method)
+        if fix_stripes:
+            if "stripes" not in state:
+                state["stripes"] = stripes_compute(img, black, white, frame_size)
+            needed, coef = state["stripes"]
+            img = stripes_apply(img, black, white, needed, coef)
+        outs.append(img)
+    return outs, state
