@@ -1,0 +1,362 @@
+// abi.cu -- the mlvb_* entry points of include/mlvfs_b200.h: context lifecycle, the slot ring that
+// pipelines host frames (pinned H2D -> kernels -> pinned D2H on one stream per slot), and the
+// device-resident batch form.  The reference-named drop-in symbols live in dropin.cu.
+#include <stdlib.h>
+#include <string.h>
+
+#include "context.cuh"
+
+namespace {
+
+int round_up(size_t v, size_t a, size_t *out) { *out = (v + a - 1) / a * a; return 0; }
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes)
+{
+    size_t pb, fb;
+    round_up(packed_bytes + 16, 256, &pb);
+    round_up(frame_bytes, 256, &fb);
+    if (pb > s.packed_cap) {
+        if (s.d_packed) cudaFree(s.d_packed);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        s.d_packed = nullptr; s.h_in = nullptr; s.packed_cap = s.h_in_cap = 0;
+        MLVB_CUDA_OK(cudaMalloc(&s.d_packed, pb));
+        MLVB_CUDA_OK(cudaHostAlloc(&s.h_in, pb, cudaHostAllocDefault));
+        s.packed_cap = s.h_in_cap = pb;
+    }
+    if (fb > s.frame_cap) {
+        if (s.d_a) cudaFree(s.d_a);
+        if (s.d_b) cudaFree(s.d_b);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        s.d_a = s.d_b = nullptr; s.h_out = nullptr; s.frame_cap = s.h_out_cap = 0;
+        MLVB_CUDA_OK(cudaMalloc(&s.d_a, fb));
+        MLVB_CUDA_OK(cudaMalloc(&s.d_b, fb));
+        MLVB_CUDA_OK(cudaHostAlloc(&s.h_out, fb, cudaHostAllocDefault));
+        s.frame_cap = s.h_out_cap = fb;
+    }
+    return MLVB_OK;
+}
+
+Slot *acquire_slot(mlvb_context *ctx)
+{
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    for (;;) {
+        for (auto &c : ctx->slots)
+            if (!c.busy) { c.busy = true; c.ticket = ctx->next_ticket++; return &c; }
+        ctx->cv.wait(lk);
+    }
+}
+
+void release_slot(mlvb_context *ctx, Slot *s)
+{
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        s->busy = false;
+        s->ticket = -1;
+    }
+    ctx->cv.notify_one();
+}
+
+namespace {
+
+// Decode the VIDF payload into unpacked 16-bit frames at d_frames (main.c:569-706 dispatch).
+int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, const void *d_payload,
+                   size_t payload_stride, size_t payload_bytes, uint16_t *d_frames, size_t frame_stride, int nframes,
+                   cudaStream_t st)
+{
+    const int vc = hdr->file_hdr.videoClass;
+    if (vc & MLVB_VIDEO_CLASS_FLAG_LZMA) return MLVB_ERR_UNSUPPORTED;      // legacy codec stays on the CPU side
+    if (vc & MLVB_VIDEO_CLASS_FLAG_LJ92) return MLVB_ERR_UNSUPPORTED;      // TODO(lj92): device decoder
+    if (payload_bytes < mlvb_packed_bytes((uint32_t)g.npix, g.bpp)) return MLVB_ERR_ARG;
+    StageTimer t(ctx, ST_UNPACK, st);
+    int rc = launch_unpack(d_payload, payload_stride, payload_bytes, d_frames, frame_stride, (uint32_t)g.npix, g.bpp,
+                           nframes, st);
+    if (rc == MLVB_OK) ctx->launches += 1;
+    return rc;
+}
+
+// Everything process_frame does between get_image_data and the final header (main.c:942-997),
+// on device buffers.  Finished frames end up in d_out.
+int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options &opts, const char *mlv_filename,
+                 const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_work, uint16_t *d_out,
+                 size_t frame_stride, int nframes, cudaStream_t st, mlvb_frame_result *res)
+{
+    const FrameGeom g = geom_from_headers(hdr);
+    if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
+    res->is_dual_iso = 0;
+    res->black_level = g.black;
+    res->white_level = g.white;
+    res->exposure_bias[0] = hdr->rawi_hdr.raw_info.exposure_bias[0];
+    res->exposure_bias[1] = hdr->rawi_hdr.raw_info.exposure_bias[1];
+
+    const bool cs = (opts.chroma_smooth == 2 || opts.chroma_smooth == 3 || opts.chroma_smooth == 5) && opts.dual_iso != 2 &&
+                    g.black <= MLVB_MAX_BLACK;
+    // without an out-of-place stage the chain can run directly in d_out
+    uint16_t *d_a = cs ? d_work : d_out;
+    int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, st);
+    if (rc) return rc;
+    if (opts.fix_pattern_noise || opts.dual_iso || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: next stages
+    // main.c:975: the outer chroma smoothing is skipped whenever dual_iso == 2
+    return run_single_iso_chain(ctx, hdr, g, opts, mlv_filename, d_a, d_out, frame_stride, nframes, opts.dual_iso == 2, st);
+}
+
+std::mutex g_default_mu;
+mlvb_context *g_default_ctx = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+int mlvb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mlvb_context_create(int device, int nslots, mlvb_context **out)
+{
+    if (!out) return MLVB_ERR_ARG;
+    *out = nullptr;
+    if (mlvb_device_count() <= device) {
+        fprintf(stderr, "libmlvfs_b200: CUDA device %d not available -- this library has no CPU path\n", device);
+        return MLVB_ERR_CUDA;
+    }
+    MLVB_CUDA_OK(cudaSetDevice(device));
+    mlvb_context *ctx = new mlvb_context();
+    ctx->device = device;
+    const size_t n1 = (16384 + MLVB_MAX_BLACK) * sizeof(int), n3 = 24 * MLVB_EV_RES * sizeof(int);
+    const size_t n2 = 14 * MLVB_EV_RES * sizeof(uint16_t);
+    std::vector<uint16_t> pos(14 * MLVB_EV_RES);
+    const int *ev2raw = host_ev2raw_base();
+    for (int e = 0; e < 14 * MLVB_EV_RES; e++) pos[e] = (uint16_t)ev2raw[e + 10 * MLVB_EV_RES];
+    MLVB_CUDA_OK(cudaMalloc(&ctx->d_raw2ev_base, n1));
+    MLVB_CUDA_OK(cudaMalloc(&ctx->d_ev2raw_pos, n2));
+    MLVB_CUDA_OK(cudaMalloc(&ctx->d_ev2raw_full, n3));
+    MLVB_CUDA_OK(cudaMemcpy(ctx->d_raw2ev_base, host_raw2ev_base(), n1, cudaMemcpyHostToDevice));
+    MLVB_CUDA_OK(cudaMemcpy(ctx->d_ev2raw_pos, pos.data(), n2, cudaMemcpyHostToDevice));
+    MLVB_CUDA_OK(cudaMemcpy(ctx->d_ev2raw_full, ev2raw, n3, cudaMemcpyHostToDevice));
+    ctx->luts.raw2ev_base = ctx->d_raw2ev_base;
+    ctx->luts.ev2raw_pos = ctx->d_ev2raw_pos;
+    ctx->luts.ev2raw_full = ctx->d_ev2raw_full + 10 * MLVB_EV_RES;
+    if (nslots <= 0) nslots = 4;
+    ctx->slots.resize(nslots);
+    for (auto &s : ctx->slots) {
+        MLVB_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        MLVB_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    MLVB_CUDA_OK(cudaStreamCreateWithFlags(&ctx->batch_stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return MLVB_OK;
+}
+
+void mlvb_context_destroy(mlvb_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &s : ctx->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.d_packed) cudaFree(s.d_packed);
+        if (s.d_a) cudaFree(s.d_a);
+        if (s.d_b) cudaFree(s.d_b);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+    }
+    if (ctx->batch_stream) cudaStreamDestroy(ctx->batch_stream);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_stat) cudaFree(ctx->d_stat);
+    mlvb_reset_clip_state(ctx);
+    cudaFree(ctx->d_raw2ev_base);
+    cudaFree(ctx->d_ev2raw_pos);
+    cudaFree(ctx->d_ev2raw_full);
+    delete ctx;
+}
+
+mlvb_context *mlvb_default_context(void)
+{
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        const char *dev = getenv("MLVB_DEVICE");
+        if (mlvb_context_create(dev ? atoi(dev) : 0, 0, &g_default_ctx) != MLVB_OK) g_default_ctx = nullptr;
+    }
+    return g_default_ctx;
+}
+
+void *mlvb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void mlvb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void mlvb_reset_clip_state(mlvb_context *ctx)
+{
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->clip_mu);
+    ctx->stripes.clear();
+    for (auto &m : ctx->bad_maps) m = BadPixelMap();
+    ctx->bad_map_cursor = 0;
+    ctx->focus_maps.clear();
+}
+
+void mlvb_seed_dither(mlvb_context *ctx, unsigned seed)
+{
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->clip_mu);
+    ctx->dither_rng.seed(seed);
+}
+
+int mlvb_get_stripes(mlvb_context *ctx, const char *mlv_filename, int *needed, int coef[8])
+{
+    if (!ctx) return MLVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->clip_mu);
+    auto it = ctx->stripes.find(mlv_filename ? mlv_filename : "");
+    if (it == ctx->stripes.end() || !it->second.computed) return MLVB_ERR_ARG;
+    if (needed) *needed = it->second.coef.needed;
+    if (coef) memcpy(coef, it->second.coef.coef, sizeof(int) * 8);
+    return 8;
+}
+
+int mlvb_get_bad_pixels(mlvb_context *ctx, uint64_t file_guid, int aggressive, int *xy, int cap)
+{
+    if (!ctx) return MLVB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->clip_mu);
+    for (auto &m : ctx->bad_maps)
+        if (m.valid && m.file_guid == file_guid && m.aggressive == aggressive && m.list) {
+            const int n = (int)m.list->host.size();
+            for (int i = 0; i < n && i < cap; i++) { xy[2 * i] = m.list->host[i].x; xy[2 * i + 1] = m.list->host[i].y; }
+            return n;
+        }
+    return MLVB_ERR_ARG;
+}
+
+void mlvb_profile_begin(mlvb_context *ctx)
+{
+    if (!ctx) return;
+    for (auto &sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    ctx->spans.clear();
+    ctx->profiling = true;
+}
+
+int mlvb_profile_end(mlvb_context *ctx, float *ms_per_stage, int *spans_per_stage, int nstages)
+{
+    if (!ctx) return MLVB_ERR_ARG;
+    ctx->profiling = false;
+    for (int i = 0; i < nstages; i++) { ms_per_stage[i] = 0.f; spans_per_stage[i] = 0; }
+    int rc = MLVB_OK;
+    for (auto &sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.b) != cudaSuccess || cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) rc = MLVB_ERR_CUDA;
+        else if (sp.stage < nstages) { ms_per_stage[sp.stage] += ms; spans_per_stage[sp.stage]++; }
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    return rc;
+}
+
+uint64_t mlvb_launch_count(mlvb_context *ctx) { return ctx ? (uint64_t)ctx->launches : 0; }
+
+// ------------------------------------------------------------------ host-buffer pipeline
+
+mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
+                        const mlvb_options *opts, const char *mlv_filename, uint16_t *dst)
+{
+    if (!ctx || !hdr || !payload || !opts || !dst) return MLVB_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MLVB_ERR_CUDA;
+    const FrameGeom g = geom_from_headers(hdr);
+    const size_t frame_bytes = g.npix * 2;
+
+    Slot *s = acquire_slot(ctx);
+    auto fail = [&](int rc) -> mlvb_ticket { release_slot(ctx, s); return rc; };
+    int rc = slot_reserve(*s, payload_bytes, frame_bytes);
+    if (rc) return fail(rc);
+
+    // H2D: straight from the caller's buffer when it is pinned, else through the slot's pinned stage
+    const void *src = payload;
+    if (!is_pinned(payload)) { memcpy(s->h_in, payload, payload_bytes); src = s->h_in; }
+    if (cudaMemcpyAsync(s->d_packed, src, payload_bytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess)
+        return fail(MLVB_ERR_CUDA);
+
+    s->result = mlvb_frame_result();
+    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->stream,
+                      &s->result);
+    if (rc) { cudaStreamSynchronize(s->stream); return fail(rc); }
+
+    s->out_bytes = frame_bytes;
+    const bool dst_pinned = is_pinned(dst);
+    s->user_dst = dst_pinned ? nullptr : dst;
+    if (cudaMemcpyAsync(dst_pinned ? (void *)dst : (void *)s->h_out, s->d_b, frame_bytes, cudaMemcpyDeviceToHost,
+                        s->stream) != cudaSuccess ||
+        cudaEventRecord(s->done, s->stream) != cudaSuccess) {
+        cudaStreamSynchronize(s->stream);
+        return fail(MLVB_ERR_CUDA);
+    }
+    return s->ticket;
+}
+
+int mlvb_wait(mlvb_context *ctx, mlvb_ticket ticket, mlvb_frame_result *res)
+{
+    if (!ctx || ticket < 0) return MLVB_ERR_ARG;
+    Slot *s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (auto &c : ctx->slots) if (c.busy && c.ticket == ticket) { s = &c; break; }
+    }
+    if (!s) return MLVB_ERR_ARG;
+    int rc = MLVB_OK;
+    if (cudaEventSynchronize(s->done) != cudaSuccess) {
+        fprintf(stderr, "libmlvfs_b200: frame failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        rc = MLVB_ERR_CUDA;
+    } else if (s->user_dst) {
+        memcpy(s->user_dst, s->h_out, s->out_bytes);
+    }
+    s->result.status = rc;
+    if (res) *res = s->result;
+    release_slot(ctx, s);
+    return rc;
+}
+
+int mlvb_process_frame(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
+                       const mlvb_options *opts, const char *mlv_filename, uint16_t *dst, mlvb_frame_result *res)
+{
+    const mlvb_ticket t = mlvb_submit(ctx, hdr, payload, payload_bytes, opts, mlv_filename, dst);
+    if (t < 0) {
+        if (res) { *res = mlvb_frame_result(); res->status = (int)t; }
+        return (int)t;
+    }
+    return mlvb_wait(ctx, t, res);
+}
+
+// ------------------------------------------------------------------ device-resident batch
+
+int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options *opts,
+                              const char *mlv_filename, const void *d_payload, size_t payload_stride,
+                              size_t payload_bytes, uint16_t *d_out, size_t out_stride_px, int nframes,
+                              void *cuda_stream)
+{
+    if (!ctx || !hdr || !opts || !d_payload || !d_out || nframes <= 0) return MLVB_ERR_ARG;
+    MLVB_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->batch_stream;
+    const FrameGeom g = geom_from_headers(hdr);
+    if (out_stride_px < g.npix) return MLVB_ERR_ARG;
+    // one work frame per output frame, same stride as the output
+    int rc = ctx->ensure_scratch((size_t)nframes * out_stride_px * sizeof(uint16_t));
+    if (rc) return rc;
+    mlvb_frame_result res;
+    return run_pipeline(ctx, hdr, *opts, mlv_filename, d_payload, payload_stride, payload_bytes, (uint16_t *)ctx->d_scratch,
+                        d_out, out_stride_px, nframes, st, &res);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// context.cuh -- host-side state behind the C ABI: one mlvb_context per GPU holding the EV tables,
+// a ring of frame slots (stream + device buffers + pinned staging), a scratch arena for batches and
+// the per-clip state the reference keeps in file-static lists.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mlvfs_b200.h"
+#include "kernels.cuh"
+
+// glibc-compatible rand() (TYPE_3 additive feedback generator), the dither source of stripes.c:129-130.
+struct GlibcRand {
+    uint32_t r[34];
+    int f = 3, b = 0;
+    GlibcRand() { seed(1); }
+    void seed(unsigned s);
+    int next();
+};
+
+// A pixel list with its level schedule, resident on the device (bad-pixel map, focus-pixel map).
+struct PixelList {
+    std::vector<PixelXY> host;             // original (reference) order
+    PixelXY *d_by_level = nullptr;         // sorted by level, stable
+    unsigned *d_level_start = nullptr;
+    std::vector<unsigned> level_start;     // nlevels + 1 entries
+    unsigned nlevels = 0;
+    ~PixelList();
+    int upload();                          // builds the level schedule from `host`
+};
+
+struct BadPixelMap {                       // reference cs.c:186-193 + the 8-slot ring cs.c:215-217
+    uint64_t file_guid = 0;
+    int aggressive = 0;
+    bool valid = false;
+    std::shared_ptr<PixelList> list;
+};
+
+struct FocusPixelMap {                     // reference cs.c:176-184
+    uint32_t camera = 0;
+    int rawi_width = 0, rawi_height = 0;
+    std::shared_ptr<PixelList> list;       // null or empty: no map file for this camera/size
+};
+
+struct StripesState {                      // reference stripes.h:30-36, keyed by MLV path (stripes.c:29-38)
+    bool computed = false;
+    StripeCoef coef{};
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *d_packed = nullptr;  size_t packed_cap = 0;
+    uint16_t *d_a = nullptr, *d_b = nullptr;  size_t frame_cap = 0;     // bytes each
+    uint8_t *h_in = nullptr;   size_t h_in_cap = 0;                    // pinned staging
+    uint16_t *h_out = nullptr; size_t h_out_cap = 0;
+    // in-flight bookkeeping
+    bool busy = false;
+    int64_t ticket = -1;
+    uint16_t *user_dst = nullptr;          // non-null: copy h_out -> user_dst in wait()
+    size_t out_bytes = 0;
+    mlvb_frame_result result{};
+};
+
+struct mlvb_context {
+    int device = 0;
+    EvLuts luts{};
+    int *d_raw2ev_base = nullptr;
+    uint16_t *d_ev2raw_pos = nullptr;
+    int *d_ev2raw_full = nullptr;
+
+    std::mutex mu;                         // slots + tickets
+    std::condition_variable cv;
+    std::vector<Slot> slots;
+    int64_t next_ticket = 0;
+
+    std::mutex clip_mu;                    // per-clip state (creation is once-only, under this lock)
+    std::map<std::string, StripesState> stripes;
+    BadPixelMap bad_maps[8];
+    int bad_map_cursor = 0;
+    std::vector<FocusPixelMap> focus_maps;
+    GlibcRand dither_rng;
+
+    // scratch for the device-batch entry point and the per-clip statistics passes
+    cudaStream_t batch_stream = nullptr;
+    void *d_scratch = nullptr;  size_t scratch_cap = 0;
+    void *d_stat = nullptr;     size_t stat_cap = 0;
+
+    std::atomic<uint64_t> launches{0};
+
+    // optional per-stage device timing (mlvb_profile_begin / mlvb_profile_end), bench.py's roofline leg
+    bool profiling = false;
+    struct StageSpan { int stage; cudaEvent_t a, b; };
+    std::vector<StageSpan> spans;
+
+    int ensure_scratch(size_t bytes);
+    int ensure_stat(size_t bytes);
+};
+
+// stage ids reported by mlvb_profile_end
+enum { ST_UNPACK = 0, ST_PIXFIX = 1, ST_CHROMA = 2, ST_STRIPES = 3, ST_PATTERN = 4, ST_DUALISO = 5, ST_LJ92 = 6, ST_COUNT = 8 };
+
+// RAII span: records a cudaEvent pair around a stage when profiling is on
+struct StageTimer {
+    mlvb_context *ctx; cudaStream_t st; cudaEvent_t b = nullptr;
+    StageTimer(mlvb_context *c, int stage, cudaStream_t s) : ctx(c), st(s)
+    {
+        if (!c->profiling) return;
+        cudaEvent_t a;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        c->spans.push_back({stage, a, b});
+    }
+    ~StageTimer() { if (b) cudaEventRecord(b, st); }
+};
+
+// host EV tables (built once per process with libm, uploaded per context)
+const int *host_raw2ev_base();
+const double *host_raw2evf_base();
+const int *host_ev2raw_base();             // 24*EV entries, index 0 <-> e = -10 EV
+
+struct FrameGeom {
+    int w, h, bpp, black, white, crop_x, crop_y, frame_size;
+    size_t npix;
+};
+FrameGeom geom_from_headers(const struct frame_headers *hdr);
+
+// the single-ISO correction chain on device buffers (process_frame order, main.c:966-997).
+// d_a holds the unpacked frames on entry; the finished frames are written to d_out (may alias d_a
+// only when no chroma smoothing is requested).  Creates per-clip state from frame 0 when missing.
+int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g,
+                         const mlvb_options &opts, const char *mlv_filename, uint16_t *d_a, uint16_t *d_out,
+                         size_t frame_stride, int nframes, int skip_chroma, cudaStream_t st);
+
+// per-clip state accessors (call with ctx->clip_mu held)
+int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, int aggressive,
+                      const uint16_t *d_img, cudaStream_t st, std::shared_ptr<PixelList> *out);
+int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, std::shared_ptr<PixelList> *out);
+int compute_stripes(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, cudaStream_t st, StripeCoef *out);
+
+// slot lease for the synchronous drop-in entry points (dropin.cu)
+Slot *acquire_slot(mlvb_context *ctx);
+void release_slot(mlvb_context *ctx, Slot *s);
+int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes);

@@ -1,0 +1,278 @@
+// dropin.cu -- the reference-named symbols of include/mlvfs_b200.h section (1).
+//
+// Same signatures, argument meaning and error behaviour as the reference objects they replace
+// (dng.o, cs.o, stripes.o, and main.c's LUT accessors / get_image_data), but the pixel work runs on
+// the GPU: each call leases a frame slot of the default context, copies the host buffer in, runs the
+// kernels, copies the result back and returns.  They exist so that the FUSE / GIF / Pismo front-ends
+// link unchanged; the fast path is mlvb_process_frame / mlvb_submit (abi.cu), which keeps a frame on
+// the device across all stages.
+#include <errno.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "context.cuh"
+
+namespace {
+
+struct Lease {
+    mlvb_context *ctx;
+    Slot *s;
+    explicit Lease(mlvb_context *c) : ctx(c), s(c ? acquire_slot(c) : nullptr) { if (c) cudaSetDevice(c->device); }
+    ~Lease() { if (s) release_slot(ctx, s); }
+};
+
+bool sync_ok(cudaStream_t st, const char *what)
+{
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { fprintf(stderr, "libmlvfs_b200: %s failed: %s\n", what, cudaGetErrorString(e)); return false; }
+    return true;
+}
+
+// in-place frame op: H2D image -> fn(d_a, d_b) -> D2H from whichever buffer fn reports
+template <typename Fn>
+bool with_frame_on_device(const char *what, uint16_t *image, size_t npix, Fn fn)
+{
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: %s: no CUDA context (no CPU path)\n", what); return false; }
+    Lease L(ctx);
+    if (slot_reserve(*L.s, 16, npix * 2) != MLVB_OK) return false;
+    cudaStream_t st = L.s->stream;
+    if (cudaMemcpyAsync(L.s->d_a, image, npix * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    uint16_t *result = nullptr;
+    if (fn(ctx, L.s->d_a, L.s->d_b, st, &result) != MLVB_OK) { cudaStreamSynchronize(st); return false; }
+    if (result && cudaMemcpyAsync(image, result, npix * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess) return false;
+    return sync_ok(st, what);
+}
+
+std::mutex g_corr_mu;
+struct stripes_correction *g_corrections = nullptr;   // stripes.c:29 list head
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- LUT accessors (main.c:128-196)
+
+double *get_raw2evf(int black)
+{
+    if (black > MLVB_MAX_BLACK) { fprintf(stderr, "Black level too large for processing\n"); return NULL; }
+    return const_cast<double *>(host_raw2evf_base()) + (MLVB_MAX_BLACK - black);
+}
+
+int *get_raw2ev(int black)
+{
+    if (black > MLVB_MAX_BLACK) { fprintf(stderr, "Black level too large for processing\n"); return NULL; }
+    return const_cast<int *>(host_raw2ev_base()) + (MLVB_MAX_BLACK - black);
+}
+
+int *get_ev2raw(void) { return const_cast<int *>(host_ev2raw_base()) + 10 * MLVB_EV_RES; }
+
+// ---------------------------------------------------------------- dng.c:813-891
+
+size_t dng_get_image_size(struct frame_headers *frame_headers)
+{
+    return (size_t)frame_headers->rawi_hdr.xRes * frame_headers->rawi_hdr.yRes * 2;
+}
+
+size_t dng_get_image_data(struct frame_headers *frame_headers, uint16_t *packed_bits, uint8_t *output_buffer,
+                          off_t offset, size_t max_size)
+{
+    const int bpp = frame_headers->rawi_hdr.raw_info.bits_per_pixel;
+    if (bpp < 1 || bpp > 16 || !packed_bits || !output_buffer) return 0;
+    const uint32_t first_px = (uint32_t)(offset > 0 ? offset : 0) / 2;            // dng.c:815
+    const size_t skip = offset < 0 ? (size_t)(-offset) : 0;
+    if (max_size < skip) return 0;
+    const uint32_t npix = (uint32_t)((max_size - skip) / 2);                      // dng.c:817,825
+    if (npix == 0) return max_size;
+    uint8_t *dst = output_buffer + skip + offset % 2;                             // dng.c:823
+    const uint64_t first_word = (uint64_t)first_px * bpp / 16;                    // packed_bits[0] is this word
+    const uint64_t end_word = ((uint64_t)(first_px + npix) * bpp + 15) / 16;
+    const size_t in_bytes = (size_t)(end_word - first_word) * 2;
+
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: dng_get_image_data: no CUDA context (no CPU path)\n"); return 0; }
+    Lease L(ctx);
+    if (slot_reserve(*L.s, in_bytes, (size_t)npix * 2) != MLVB_OK) return 0;
+    cudaStream_t st = L.s->stream;
+    if (cudaMemcpyAsync(L.s->d_packed, packed_bits, in_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return 0;
+    int rc;
+    if (first_px == 0)
+        rc = launch_unpack(L.s->d_packed, 0, in_bytes, L.s->d_a, 0, npix, bpp, 1, st);
+    else
+        rc = launch_unpack_range((const uint16_t *)L.s->d_packed, L.s->d_a, first_px, npix, bpp, st);
+    ctx->launches += 1;
+    if (rc != MLVB_OK) return 0;
+    if (cudaMemcpyAsync(dst, L.s->d_a, (size_t)npix * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 0;
+    return sync_ok(st, "dng_get_image_data") ? max_size : 0;
+}
+
+// ---------------------------------------------------------------- main.c:569-706
+
+size_t get_image_data(struct frame_headers *frame_headers, FILE *file, uint8_t *output_buffer, off_t offset,
+                      size_t max_size)
+{
+    const int vc = frame_headers->file_hdr.videoClass;
+    const int bpp = frame_headers->rawi_hdr.raw_info.bits_per_pixel;
+    const uint64_t data_pos = frame_headers->position + frame_headers->vidf_hdr.frameSpace + sizeof(mlv_vidf_hdr_t);
+    if (vc & (MLVB_VIDEO_CLASS_FLAG_LZMA | MLVB_VIDEO_CLASS_FLAG_LJ92)) {
+        fprintf(stderr, "libmlvfs_b200: get_image_data: compressed payloads go through mlvb_process_frame\n");
+        return 0;
+    }
+    const uint64_t first_px = (uint64_t)(offset > 0 ? offset : 0) / 2;            // main.c:575-579
+    const uint64_t first_word = first_px * bpp / 16;
+    const size_t out_bytes = max_size - (offset < 0 ? (size_t)(-offset) : 0);
+    const uint64_t words = ((first_px + out_bytes / 2) * bpp + 15) / 16 - first_word;
+    uint16_t *packed = (uint16_t *)calloc(words + 2, 2);
+    if (!packed) return 0;
+    size_t result = 0;
+    if (fseeko(file, (off_t)(data_pos + first_word * 2), SEEK_SET) == 0) {
+        size_t got = fread(packed, 2, words, file);
+        if (ferror(file)) fprintf(stderr, "libmlvfs_b200: fread error: %s\n", strerror(errno));
+        else if (got > 0) result = dng_get_image_data(frame_headers, packed, output_buffer, offset, max_size);
+    }
+    free(packed);
+    return result;
+}
+
+// ---------------------------------------------------------------- cs.c
+
+void chroma_smooth(struct frame_headers *frame_headers, uint16_t *image_data, int method)
+{
+    const FrameGeom g = geom_from_headers(frame_headers);
+    if (g.black > MLVB_MAX_BLACK) { fprintf(stderr, "Black level too large for processing\n"); return; }   // cs.c:58
+    if (method != 2 && method != 3 && method != 5) { fprintf(stderr, "Unsupported chroma smooth method\n"); return; }
+    with_frame_on_device("chroma_smooth", image_data, g.npix,
+                         [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *d_b, cudaStream_t st, uint16_t **res) {
+                             *res = d_b;
+                             ctx->launches += 1;
+                             return launch_chroma_smooth_u16(d_a, d_b, g.w, g.h, g.npix, 1, g.black, method, ctx->luts,
+                                                             nullptr, g.white, st);
+                         });
+}
+
+void fix_bad_pixels(struct frame_headers *frame_headers, uint16_t *image_data, int aggressive, int dual_iso)
+{
+    const FrameGeom g = geom_from_headers(frame_headers);
+    if (g.black > MLVB_MAX_BLACK) { fprintf(stderr, "Black level too large for processing\n"); return; }   // cs.c:231
+    with_frame_on_device("fix_bad_pixels", image_data, g.npix,
+                         [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *, cudaStream_t st, uint16_t **res) {
+                             std::shared_ptr<PixelList> bad;
+                             {
+                                 std::lock_guard<std::mutex> lk(ctx->clip_mu);
+                                 int rc = get_bad_pixel_map(ctx, frame_headers, g, aggressive != 0, d_a, st, &bad);
+                                 if (rc) return rc;
+                             }
+                             *res = d_a;
+                             if (!bad || !bad->nlevels) { *res = nullptr; return (int)MLVB_OK; }
+                             ctx->launches += 1 + (bad->nlevels > 1);
+                             return launch_pixel_fix(d_a, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, dual_iso != 0, 0,
+                                                     bad->d_by_level, bad->d_level_start, bad->level_start.data(),
+                                                     bad->nlevels, ctx->luts, st);
+                         });
+}
+
+void fix_focus_pixels(struct frame_headers *frame_headers, uint16_t *image_data, int dual_iso)
+{
+    const FrameGeom g = geom_from_headers(frame_headers);
+    mlvb_context *ctx0 = mlvb_default_context();
+    if (!ctx0) { fprintf(stderr, "libmlvfs_b200: fix_focus_pixels: no CUDA context (no CPU path)\n"); return; }
+    std::shared_ptr<PixelList> focus;
+    {
+        std::lock_guard<std::mutex> lk(ctx0->clip_mu);
+        if (get_focus_pixel_map(ctx0, frame_headers, &focus) != MLVB_OK) return;
+    }
+    if (!focus || !focus->nlevels) return;                                         // no map: nothing to do (cs.c:444)
+    if (g.black > MLVB_MAX_BLACK) { fprintf(stderr, "raw2ev LUT error\n"); return; }   // cs.c:456-460
+    with_frame_on_device("fix_focus_pixels", image_data, g.npix,
+                         [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *, cudaStream_t st, uint16_t **res) {
+                             *res = d_a;
+                             ctx->launches += 1 + (focus->nlevels > 1);
+                             return launch_pixel_fix(d_a, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, dual_iso != 0, 1,
+                                                     focus->d_by_level, focus->d_level_start, focus->level_start.data(),
+                                                     focus->nlevels, ctx->luts, st);
+                         });
+}
+
+// cs.c:404-419 frees the focus maps AND the bad-pixel ring
+void free_focus_pixel_maps(void)
+{
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lk(ctx->clip_mu);
+    ctx->focus_maps.clear();
+    for (auto &m : ctx->bad_maps) m = BadPixelMap();
+    ctx->bad_map_cursor = 0;
+}
+
+// ---------------------------------------------------------------- stripes.c
+
+struct stripes_correction *stripes_get_correction(const char *mlv_filename)
+{
+    std::lock_guard<std::mutex> lk(g_corr_mu);
+    for (struct stripes_correction *c = g_corrections; c; c = c->next)
+        if (!strcmp(c->mlv_filename, mlv_filename)) return c;
+    return NULL;
+}
+
+struct stripes_correction *stripes_new_correction(const char *mlv_filename)
+{
+    struct stripes_correction *c = (struct stripes_correction *)calloc(1, sizeof(*c));
+    if (!c) return NULL;
+    c->mlv_filename = strdup(mlv_filename);
+    if (!c->mlv_filename) { free(c); return NULL; }
+    for (int i = 0; i < 8; i++) c->coeffficients[i] = 65536;
+    std::lock_guard<std::mutex> lk(g_corr_mu);
+    struct stripes_correction **tail = &g_corrections;
+    while (*tail) tail = &(*tail)->next;
+    *tail = c;
+    return c;
+}
+
+void stripes_free_corrections(void)
+{
+    std::lock_guard<std::mutex> lk(g_corr_mu);
+    while (g_corrections) {
+        struct stripes_correction *n = g_corrections->next;
+        free(g_corrections->mlv_filename);
+        free(g_corrections);
+        g_corrections = n;
+    }
+}
+
+void stripes_compute_correction(struct frame_headers *frame_headers, struct stripes_correction *correction,
+                                uint16_t *image_data, off_t offset, size_t size)
+{
+    (void)offset; (void)size;                                   // the reference ignores both (stripes.c:143-160)
+    if (!correction) return;
+    const FrameGeom g = geom_from_headers(frame_headers);
+    StripeCoef sc{};
+    bool ok = with_frame_on_device("stripes_compute_correction", image_data, g.npix,
+                                   [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *, cudaStream_t st, uint16_t **res) {
+                                       *res = nullptr;
+                                       std::lock_guard<std::mutex> lk(ctx->clip_mu);
+                                       return compute_stripes(ctx, g, d_a, st, &sc);
+                                   });
+    if (!ok) return;
+    correction->correction_needed = sc.needed;
+    for (int i = 0; i < 8; i++) correction->coeffficients[i] = sc.coef[i];
+}
+
+void stripes_apply_correction(struct frame_headers *frame_headers, struct stripes_correction *correction,
+                              uint16_t *image_data, off_t offset, size_t size)
+{
+    if (!correction || !correction->correction_needed) return;           // stripes.c:252
+    if (frame_headers->rawi_hdr.xRes % 8 != 0) return;                    // stripes.c:253
+    const FrameGeom g = geom_from_headers(frame_headers);
+    StripeCoef sc{};
+    sc.needed = 1;
+    const size_t start = (size_t)offset % 8;                              // stripes.c:257: coefficient phase
+    for (int i = 0; i < 8; i++) sc.coef[i] = correction->coeffficients[(i + start) % 8];
+    with_frame_on_device("stripes_apply_correction", image_data, size,
+                         [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *, cudaStream_t st, uint16_t **res) {
+                             *res = d_a;
+                             ctx->launches += 1;
+                             return launch_stripes_apply(d_a, 8, size, size, 1, g.black, g.white, &sc, st);
+                         });
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// pixfix.cu -- bad-pixel detection and bad/focus-pixel interpolation.
+//
+// Replaces reference cs.c:87-168 (interpolate_horizontal / _vertical / _pixel), cs.c:257-306 (the
+// detection pass of fix_bad_pixels), cs.c:314-330 and cs.c:462-501 (the two apply loops).
+//
+// The reference applies its list sequentially IN PLACE, so an entry can read pixels that an
+// earlier entry already rewrote.  We keep that exact semantics with a level
+// schedule: level(m) = 1 + max level of the earlier entries inside m's +-3 cross stencil (0 if none).
+// Because the stencil is symmetric, every later entry in m's stencil has a strictly higher level, so
+// running levels in order, in place, reads exactly what the sequential loop would have read.
+// Level 0 (virtually everything on real sensors) runs grid-wide; deeper levels run in one CTA that
+// walks the levels with a barrier in between.
+#include "kernels.cuh"
+#include "scan.cuh"
+
+namespace {
+
+struct FixLut {
+    const int *raw2ev;           // indexed by raw value
+    const uint16_t *ev2raw;      // e in [0, 14 EV)
+    int black;
+};
+
+__device__ __forceinline__ int ev_of(const FixLut &L, const uint16_t *im, long long i) { return __ldg(L.raw2ev + im[i]); }
+
+__device__ __forceinline__ int ev_grad(const FixLut &L, const uint16_t *im, long long i, long long o1, long long o2)
+{
+    return wabs(wsub(ev_of(L, im, i + o1), ev_of(L, im, i + o2)));
+}
+
+// cs.c:87-109 (step 1) / cs.c:111-133 (step w)
+__device__ void interp_line(uint16_t *im, long long i, long long step, const FixLut &L)
+{
+    const int d1 = ev_grad(L, im, i, 3 * step, step);
+    const int d2 = ev_grad(L, im, i, -step, -3 * step);
+    const int sum = wadd(d1, d2);
+    if (sum == 0) { im[i] = im[i + 2 * step]; return; }
+    const int c1 = ((sum - d1) << 8) / sum;
+    const int c2 = ((sum - d2) << 8) / sum;
+    const int ev = (wmul(ev_of(L, im, i + 2 * step), c1) >> 8) + (wmul(ev_of(L, im, i - 2 * step), c2) >> 8);
+    im[i] = (uint16_t)(__ldg(L.ev2raw + clamp_ev(ev)) + L.black);
+}
+
+// cs.c:135-168
+__device__ void interp_cross(uint16_t *im, long long i, long long w, const FixLut &L)
+{
+    const int dv1 = ev_grad(L, im, i, 3 * w, w);
+    const int dv2 = ev_grad(L, im, i, -w, -3 * w);
+    const int dh1 = ev_grad(L, im, i, 3, 1);
+    const int dh2 = ev_grad(L, im, i, -1, -3);
+    const int sum = wadd(wadd(dh1, dh2), wadd(dv1, dv2));
+    if (sum == 0) { im[i] = im[i + 2]; return; }
+    const int den = wmul(3, sum);
+    const int cv1 = ((sum - dv1) << 8) / den;
+    const int cv2 = ((sum - dv2) << 8) / den;
+    const int ch1 = ((sum - dh1) << 8) / den;
+    const int ch2 = ((sum - dh2) << 8) / den;
+    const int ev = (wmul(ev_of(L, im, i + 2 * w), cv1) >> 8) + (wmul(ev_of(L, im, i - 2 * w), cv2) >> 8) +
+                   (wmul(ev_of(L, im, i + 2), ch1) >> 8) + (wmul(ev_of(L, im, i - 2), ch2) >> 8);
+    im[i] = (uint16_t)(__ldg(L.ev2raw + clamp_ev(ev)) + L.black);
+}
+
+// One list entry.  edge_rules = 0: bad-pixel semantics (cs.c:314-330, border entries ignored);
+// edge_rules = 1: focus-pixel semantics (cs.c:462-501, border entries use 1-D / copy fallbacks).
+__device__ void fix_entry(uint16_t *im, int w, int h, int x, int y, int dual_iso, int edge_rules, const FixLut &L)
+{
+    const long long i = (long long)x + (long long)y * w;
+    if (x > 2 && x < w - 3 && y > 2 && y < h - 3) {
+        if (dual_iso) interp_line(im, i, 1, L);
+        else interp_cross(im, i, w, L);
+    } else if (edge_rules && i > 0 && i < (long long)w * h) {
+        const bool hedge = (x >= w - 3 && x < w) || (x >= 0 && x <= 3);
+        const bool vedge = (y >= h - 3 && y < h) || (y >= 0 && y <= 3);
+        if (hedge && !vedge && !dual_iso) interp_line(im, i, w, L);
+        else if (vedge && !hedge) interp_line(im, i, 1, L);
+        else if (x >= 0 && x <= 3) im[i] = im[i + 2];
+        else if (x >= w - 3 && x < w) im[i] = im[i - 2];
+    }
+}
+
+struct FixArgs {
+    uint16_t *img;
+    size_t frame_stride;
+    int w, h, crop_x, crop_y, dual_iso, edge_rules;
+    const PixelXY *list;         // sorted by level, list order preserved inside a level
+    FixLut lut;
+};
+
+__global__ void fix_level0_kernel(const FixArgs A, unsigned count)
+{
+    const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= count) return;
+    const PixelXY p = A.list[m];
+    fix_entry(A.img + (size_t)blockIdx.y * A.frame_stride, A.w, A.h, p.x - A.crop_x, p.y - A.crop_y, A.dual_iso,
+              A.edge_rules, A.lut);
+}
+
+// levels 1..nlevels-1: one CTA per frame, barrier between levels (global writes of a CTA are visible
+// to the whole CTA after __syncthreads)
+__global__ void fix_deep_levels_kernel(const FixArgs A, const unsigned *__restrict__ level_start, unsigned nlevels)
+{
+    uint16_t *im = A.img + (size_t)blockIdx.y * A.frame_stride;
+    for (unsigned l = 1; l < nlevels; l++) {
+        const unsigned lo = level_start[l], hi = level_start[l + 1];
+        for (unsigned m = lo + threadIdx.x; m < hi; m += blockDim.x) {
+            const PixelXY p = A.list[m];
+            fix_entry(im, A.w, A.h, p.x - A.crop_x, p.y - A.crop_y, A.dual_iso, A.edge_rules, A.lut);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- detection (cs.c:257-306) ----
+
+constexpr int DET_THREADS = 256;
+constexpr int DET_PX = 8;       // consecutive pixels per thread (one flag byte)
+
+__device__ __forceinline__ bool is_bad(const uint16_t *im, int w, int x, int y, const int *raw2ev, int black,
+                                       int aggressive)
+{
+    const int p = im[x + (size_t)y * w];
+    // three largest (with multiplicity) of the eight same-colour neighbours at +-2
+    int m1 = -1, m2 = -1, m3 = -1;
+#pragma unroll
+    for (int dy = -2; dy <= 2; dy += 2)
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx += 2) {
+            if (dx == 0 && dy == 0) continue;
+            const int q = im[(x + dx) + (size_t)(y + dy) * w];
+            if (q >= m1) { m3 = m2; m2 = m1; m1 = q; }
+            else if (q >= m2) { m3 = m2; m2 = q; }
+            else if (q > m3) m3 = q;
+        }
+    const int dark_min = black - 96, dark_max = black + 96;          // dark_noise 12 * 8 (cs.c:257-259)
+    if (p < dark_min) return true;
+    const int ep = __ldg(raw2ev + p);
+    if (wsub(ep, __ldg(raw2ev + m2)) > 2 * MLVB_EV_RES && p > dark_max) return true;
+    if (aggressive && (wsub(ep, __ldg(raw2ev + m2)) > MLVB_EV_RES || wsub(ep, __ldg(raw2ev + m3)) > MLVB_EV_RES) &&
+        p > dark_max)
+        return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(DET_THREADS)
+badpix_flag_kernel(const uint16_t *__restrict__ im, int w, int h, const int *__restrict__ raw2ev, int black,
+                   int aggressive, uint8_t *__restrict__ flags, unsigned long long *__restrict__ cta_counts)
+{
+    const size_t npix = (size_t)w * h;
+    const size_t t = (size_t)blockIdx.x * DET_THREADS + threadIdx.x;
+    unsigned bits = 0;
+#pragma unroll
+    for (int k = 0; k < DET_PX; k++) {
+        const size_t i = t * DET_PX + k;
+        if (i < npix) {
+            const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+            if (x >= 6 && x < w - 6 && y >= 6 && y < h - 6 && is_bad(im, w, x, y, raw2ev, black, aggressive)) bits |= 1u << k;
+        }
+    }
+    if (t * DET_PX < npix) flags[t] = (uint8_t)bits;
+    unsigned total;
+    block_exclusive_scan(__popc(bits), total);
+    if (threadIdx.x == 0) cta_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(DET_THREADS)
+badpix_scatter_kernel(const uint8_t *__restrict__ flags, int w, size_t npix, int crop_x, int crop_y,
+                      const unsigned long long *__restrict__ cta_offsets, PixelXY *__restrict__ list)
+{
+    const size_t t = (size_t)blockIdx.x * DET_THREADS + threadIdx.x;
+    const unsigned bits = (t * DET_PX < npix) ? flags[t] : 0u;
+    unsigned total;
+    unsigned pos = block_exclusive_scan(__popc(bits), total);
+    if (!bits) return;
+    size_t o = cta_offsets[blockIdx.x] + pos;
+    for (int k = 0; k < DET_PX; k++)
+        if (bits & (1u << k)) {
+            const size_t i = t * DET_PX + k;
+            const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+            list[o++] = PixelXY{x + crop_x, y + crop_y};
+        }
+}
+
+}  // namespace
+
+int badpix_detect_scratch_bytes(int w, int h, size_t *flag_bytes, size_t *count_bytes)
+{
+    const size_t npix = (size_t)w * h;
+    const size_t nthreads = (npix + DET_PX - 1) / DET_PX;
+    const size_t nctas = (nthreads + DET_THREADS - 1) / DET_THREADS;
+    *flag_bytes = (nthreads + 255) & ~(size_t)255;
+    *count_bytes = (nctas + 1) * sizeof(unsigned long long);
+    return (int)nctas;
+}
+
+// Phase 1: flags + per-CTA counts + scan.  d_counts[nctas] receives the total (read it back, allocate
+// the list, then call phase 2).
+int launch_badpix_detect_count(const uint16_t *d_img, int w, int h, int black, int aggressive, const EvLuts &luts,
+                               uint8_t *d_flags, unsigned long long *d_counts, cudaStream_t st)
+{
+    if (black > MLVB_MAX_BLACK) return MLVB_ERR_ARG;
+    size_t fb, cb;
+    const int nctas = badpix_detect_scratch_bytes(w, h, &fb, &cb);
+    badpix_flag_kernel<<<nctas, DET_THREADS, 0, st>>>(d_img, w, h, luts.raw2ev_base + (MLVB_MAX_BLACK - black), black,
+                                                      aggressive, d_flags, d_counts);
+    scan_counts_kernel<<<1, 1024, 0, st>>>(d_counts, (unsigned)nctas, d_counts + nctas);
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
+
+int launch_badpix_detect_scatter(const uint8_t *d_flags, const unsigned long long *d_offsets, int w, int h, int crop_x,
+                                 int crop_y, PixelXY *d_list, cudaStream_t st)
+{
+    size_t fb, cb;
+    const int nctas = badpix_detect_scratch_bytes(w, h, &fb, &cb);
+    badpix_scatter_kernel<<<nctas, DET_THREADS, 0, st>>>(d_flags, w, (size_t)w * h, crop_x, crop_y, d_offsets, d_list);
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
+
+int launch_pixel_fix(uint16_t *d_img, int w, int h, size_t frame_stride, int nframes, int black, int crop_x, int crop_y,
+                     int dual_iso, int edge_rules, const PixelXY *d_list_by_level, const unsigned *d_level_start,
+                     const unsigned *h_level_start, unsigned nlevels, const EvLuts &luts, cudaStream_t st)
+{
+    if (nlevels == 0 || h_level_start[nlevels] == 0) return MLVB_OK;
+    if (black > MLVB_MAX_BLACK) return MLVB_ERR_ARG;
+    FixArgs A;
+    A.img = d_img; A.frame_stride = frame_stride; A.w = w; A.h = h; A.crop_x = crop_x; A.crop_y = crop_y;
+    A.dual_iso = dual_iso; A.edge_rules = edge_rules; A.list = d_list_by_level;
+    A.lut.raw2ev = luts.raw2ev_base + (MLVB_MAX_BLACK - black);
+    A.lut.ev2raw = luts.ev2raw_pos;
+    A.lut.black = black;
+    const unsigned n0 = h_level_start[1];
+    if (n0) fix_level0_kernel<<<dim3(ceil_div(n0, 128), nframes), 128, 0, st>>>(A, n0);
+    if (nlevels > 1) fix_deep_levels_kernel<<<dim3(1, nframes), 1024, 0, st>>>(A, d_level_start, nlevels);
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
