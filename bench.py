@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
@@ -88,10 +88,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.002)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -359,7 +359,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--frames-per-step", type=int, default=256)
     ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -55,7 +55,7 @@ def test_unpack_subrange_offsets(fresh_ctx, oracle):
     hdr = _hdr(w, h)
     img = synth.make_frame(w, h, 1)
     words = np.concatenate([synth.pack_bits(img), np.zeros(2, np.uint16)])
-    for offset, size in [(0, 4096), (2, 1000), (4096, 8192), (w * h * 2 - 512, 512), (131072 // 2, 65536 // 4)]:
+    for offset, size in [(0, 4096), (2, 1000), (4096, 8192), (w * h * 2 - 512, 512), (32768, 16384)]:
         first_word = (offset // 2) * 14 // 16
         want = oracle.unpack(words, w * h, 14, offset=offset, nbytes=size)
         n, raw = M.dng_get_image_data(hdr, words[first_word:], offset=offset, max_size=size)
