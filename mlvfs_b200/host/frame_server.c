@@ -1,0 +1,131 @@
+/*
+ * frame_server.c -- command-line driver of the host frame-request path, without FUSE:
+ *   mlvb_frames <mlv_dir> <clip.MLV> [--cs3x3 --bad-pix --stripes ...] [--prefetch=N] [--readers=T]
+ *               [--frames=K] [--dump=out.raw]
+ * Requests every frame of the clip the way the FUSE read handler does (main.c:1460):
+ * get_or_create_image_buffer(path, &process_frame, &was_created), touches the data, releases it.
+ * Prints frames/s and an FNV-1a hash per run (and optionally dumps the frames) so tests can compare
+ * against the oracle.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "frame_builder.h"
+#include "mlv_index.h"
+
+static char g_clip[1024];
+static int g_nframes, g_next = 0;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static uint64_t *g_hash;
+static FILE *g_dump;
+static int g_failed = 0;
+
+static uint64_t fnv1a(const void *p, size_t n)
+{
+    const uint8_t *b = p;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static void *reader(void *arg)
+{
+    (void)arg;
+    char base[1024];
+    snprintf(base, sizeof(base), "%s", g_clip);
+    char *dot = strrchr(base, '.');
+    if (dot) *dot = 0;
+    for (;;) {
+        pthread_mutex_lock(&g_mu);
+        int i = g_next < g_nframes ? g_next++ : -1;
+        pthread_mutex_unlock(&g_mu);
+        if (i < 0) return NULL;
+        char path[2200];
+        snprintf(path, sizeof(path), "/%s/%s_%06d.dng", g_clip, base, i);
+        int created = 0;
+        struct image_buffer *ib = get_or_create_image_buffer(path, &process_frame, &created);
+        if (!ib || !ib->data) { __sync_fetch_and_add(&g_failed, 1); continue; }
+        g_hash[i] = fnv1a(ib->data, ib->size);
+        if (g_dump) {
+            pthread_mutex_lock(&g_mu);
+            fseeko(g_dump, (off_t)i * (off_t)ib->size, SEEK_SET);
+            fwrite(ib->data, 1, ib->size, g_dump);
+            pthread_mutex_unlock(&g_mu);
+        }
+        release_image_buffer_by_path(path);
+    }
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 3) {
+        fprintf(stderr, "usage: %s <mlv_dir> <clip.MLV> [options]\n", argv[0]);
+        return 2;
+    }
+    struct frame_builder_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.mlv_path = argv[1];
+    snprintf(g_clip, sizeof(g_clip), "%s", argv[2]);
+    int prefetch = 0, readers = 1, limit = -1;
+    const char *dump = NULL;
+    for (int i = 3; i < argc; i++) {                       /* option names of main.c:1853-1882 */
+        const char *a = argv[i];
+        if (!strcmp(a, "--cs2x2")) cfg.options.chroma_smooth = 2;
+        else if (!strcmp(a, "--cs3x3")) cfg.options.chroma_smooth = 3;
+        else if (!strcmp(a, "--cs5x5")) cfg.options.chroma_smooth = 5;
+        else if (!strcmp(a, "--bad-pix")) cfg.options.fix_bad_pixels = 1;
+        else if (!strcmp(a, "--really-bad-pix")) cfg.options.fix_bad_pixels = 2;
+        else if (!strcmp(a, "--fix-pattern-noise")) cfg.options.fix_pattern_noise = 1;
+        else if (!strcmp(a, "--stripes")) cfg.options.fix_stripes = 1;
+        else if (!strncmp(a, "--deflicker=", 12)) cfg.options.deflicker = atoi(a + 12);
+        else if (!strcmp(a, "--dual-iso-preview")) cfg.options.dual_iso = 1;
+        else if (!strcmp(a, "--dual-iso")) cfg.options.dual_iso = 2;
+        else if (!strcmp(a, "--amaze-edge")) cfg.options.hdr_interpolation_method = 0;
+        else if (!strcmp(a, "--mean23")) cfg.options.hdr_interpolation_method = 1;
+        else if (!strcmp(a, "--no-alias-map")) cfg.options.hdr_no_alias_map = 1;
+        else if (!strcmp(a, "--alias-map")) cfg.options.hdr_no_alias_map = 0;
+        else if (!strncmp(a, "--prefetch=", 11)) prefetch = atoi(a + 11);
+        else if (!strncmp(a, "--readers=", 10)) readers = atoi(a + 10);
+        else if (!strncmp(a, "--frames=", 9)) limit = atoi(a + 9);
+        else if (!strncmp(a, "--dump=", 7)) dump = a + 7;
+        else { fprintf(stderr, "unknown option %s\n", a); return 2; }
+    }
+    frame_builder_configure(&cfg);
+    resource_manager_set_data_free(mlvb_host_free);
+    resource_manager_set_prefetch(prefetch, 0, frame_builder_frame_limit);
+
+    char mlv_file[4096];
+    snprintf(mlv_file, sizeof(mlv_file), "%s/%s", argv[1], g_clip);
+    g_nframes = mlv_get_frame_count(mlv_file);
+    if (limit >= 0 && limit < g_nframes) g_nframes = limit;
+    if (g_nframes <= 0) { fprintf(stderr, "no frames in %s\n", mlv_file); return 1; }
+    if (!mlvb_default_context()) { fprintf(stderr, "no CUDA device: no CPU path\n"); return 3; }
+    g_hash = calloc((size_t)g_nframes, sizeof(uint64_t));
+    if (dump) g_dump = fopen(dump, "wb");
+
+    if (readers < 1) readers = 1;
+    if (readers > 64) readers = 64;
+    pthread_t th[64];
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < readers; i++) pthread_create(&th[i], NULL, reader, NULL);
+    for (int i = 0; i < readers; i++) pthread_join(th[i], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    uint64_t all = 1469598103934665603ull, built = 0, hits = 0;
+    for (int i = 0; i < g_nframes; i++) { all ^= g_hash[i]; all *= 1099511628211ull; }
+    resource_manager_prefetch_stats(&built, &hits);
+    printf("{\"frames\": %d, \"failed\": %d, \"seconds\": %.6f, \"fps\": %.2f, \"readers\": %d, \"prefetch\": %d, "
+           "\"prefetch_built\": %llu, \"prefetch_hits\": %llu, \"hash\": \"%016llx\", \"frame0_hash\": \"%016llx\"}\n",
+           g_nframes, g_failed, dt, g_nframes / dt, readers, prefetch, (unsigned long long)built,
+           (unsigned long long)hits, (unsigned long long)all, (unsigned long long)g_hash[0]);
+    if (g_dump) fclose(g_dump);
+    resource_manager_shutdown();
+    free_all_image_buffers();
+    mlv_clip_close_all();
+    return g_failed ? 1 : 0;
+}

@@ -1,0 +1,56 @@
+/*
+ * resource_manager.h -- frame cache + --prefetch queue (host side, C99).
+ *
+ * Keeps the reference's frame-request API (resource_manager.h:33-51): the FUSE read handler calls
+ *     get_or_create_image_buffer(path, &process_frame, &was_created)          main.c:1460
+ * and release_image_buffer_by_path(path) on release (main.c:1634-1644), exactly as before.
+ * New: the --prefetch queue documented in the reference README (README.md:42) but absent from its
+ * sources.  After a frame of a clip is requested, the next `depth` frames are built ahead of time by
+ * worker threads through the same callback, so that their GPU work (mlvb_submit slots) overlaps the
+ * reader's memcpy of the current frame.
+ */
+#ifndef MLVB_HOST_RESOURCE_MANAGER_H
+#define MLVB_HOST_RESOURCE_MANAGER_H
+
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct image_buffer {                 /* reference resource_manager.h:33-43, same field order */
+    struct image_buffer *next;
+    char *dng_filename;
+    size_t header_size;
+    size_t size;
+    uint8_t *header;
+    uint16_t *data;
+    pthread_mutex_t mutex;
+    int in_use;
+    int prefetched;                   /* appended (front-ends never allocate this struct): built by the prefetch queue */
+};
+
+typedef int (*image_buffer_cbr)(struct image_buffer *);
+
+struct image_buffer *get_or_create_image_buffer(const char *path, image_buffer_cbr new_buffer_cbr, int *was_created);
+void release_image_buffer_by_path(const char *path);
+void release_image_buffer(struct image_buffer *image_buffer);
+void free_all_image_buffers(void);
+int  get_image_buffer_count(void);
+
+/* `data` may come from mlvb_host_alloc (pinned); the cache frees it with this hook (default free). */
+void resource_manager_set_data_free(void (*free_fn)(void *));
+
+/* --prefetch=N: build up to `depth` following frames ahead with `workers` threads (0 disables).
+ * `frame_limit(path)` returns the clip's frame count for a virtual DNG path (or <= 0 if unknown). */
+void resource_manager_set_prefetch(int depth, int workers, int (*frame_limit)(const char *dng_path));
+void resource_manager_shutdown(void);
+/* statistics for tests / the frame server: frames built by prefetch workers, cache hits on them */
+void resource_manager_prefetch_stats(uint64_t *built, uint64_t *hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,176 @@
+"""Host-side C layer (mlvfs_b200/host): MLV index cache and frame cache + prefetch queue.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from mlvfs_b200 import mlvformat as F, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "mlvfs_b200", "libmlvfs_b200_host.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(HOST_SO):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "mlvfs_b200", "host")])
+    lib = C.CDLL(HOST_SO)
+    lib.mlv_get_frame_headers.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    lib.mlv_get_frame_count.argtypes = [C.c_char_p]
+    lib.get_or_create_image_buffer.restype = C.c_void_p
+    lib.get_or_create_image_buffer.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.release_image_buffer_by_path.argtypes = [C.c_char_p]
+    lib.resource_manager_set_prefetch.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    lib.resource_manager_prefetch_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    return lib
+
+
+def _write_clip_with_metadata(path, w, h, nframes):
+    """MLV whose EXPO/LENS/WBAL blocks change mid-clip and whose blocks are stored out of timestamp order."""
+    hdr = F.make_frame_headers(w, h)
+    frames = [synth.make_frame(w, h, i) for i in range(nframes)]
+    blocks = []   # (timestamp, bytes)
+
+    def expo(ts, iso):
+        e = F.ExpoHdr()
+        F._tag(e.blockType, "EXPO")
+        e.blockSize = C.sizeof(F.ExpoHdr)
+        e.timestamp = ts
+        e.isoValue = iso
+        e.shutterValue = 20000 + iso
+        return bytes(e)
+
+    def lens(ts, fl):
+        l = F.LensHdr()
+        F._tag(l.blockType, "LENS")
+        l.blockSize = C.sizeof(F.LensHdr)
+        l.timestamp = ts
+        l.focalLength = fl
+        F._tag(l.lensName, "EF50mm")
+        return bytes(l)
+
+    def wbal(ts, k):
+        b = F.WbalHdr()
+        F._tag(b.blockType, "WBAL")
+        b.blockSize = C.sizeof(F.WbalHdr)
+        b.timestamp = ts
+        b.kelvin = k
+        return bytes(b)
+
+    def null(ts):
+        n = F.MlvHdr()
+        F._tag(n.blockType, "NULL")
+        n.blockSize = 64
+        n.timestamp = ts
+        return bytes(n) + b"\0" * (64 - C.sizeof(F.MlvHdr))
+
+    rawi = F.RawiHdr.from_buffer_copy(bytes(hdr.rawi_hdr))
+    rawi.timestamp = 1
+    idnt = F.IdntHdr.from_buffer_copy(bytes(hdr.idnt_hdr))
+    idnt.timestamp = 2
+    blocks.append((1, bytes(rawi)))
+    blocks.append((2, bytes(idnt)))
+    blocks.append((3, expo(3, 100)))
+    blocks.append((4, lens(4, 50)))
+    blocks.append((5, wbal(5, 5600)))
+    for i, fr in enumerate(frames):
+        ts = 1000 + i * 1000
+        v = F.VidfHdr.from_buffer_copy(bytes(hdr.vidf_hdr))
+        v.frameNumber = i
+        v.timestamp = ts
+        v.frameSpace = 8 * (i % 3)
+        payload = synth.pack_bits(fr).tobytes()
+        v.blockSize = C.sizeof(F.VidfHdr) + v.frameSpace + len(payload)
+        blocks.append((ts, bytes(v) + b"\0" * v.frameSpace + payload))
+        if i % 3 == 1:
+            blocks.append((ts + 10, expo(ts + 10, 200 + i)))
+        if i % 4 == 2:
+            blocks.append((ts + 20, lens(ts + 20, 24 + i)))
+            blocks.append((ts + 30, null(ts + 30)))
+    # store out of order: swap some neighbours so that the timestamp sort matters
+    order = list(range(len(blocks)))
+    for k in range(6, len(order) - 1, 5):
+        order[k], order[k + 1] = order[k + 1], order[k]
+    fh = F.FileHdr.from_buffer_copy(bytes(hdr.file_hdr))
+    fh.videoFrameCount = nframes
+    with open(path, "wb") as f:
+        f.write(bytes(fh))
+        for k in order:
+            f.write(blocks[k][1])
+    return hdr, frames
+
+
+def test_index_cache_matches_reference_header_walk(host, ref, tmp_path):
+    clip = str(tmp_path / "META.MLV")
+    hdr, frames = _write_clip_with_metadata(clip, 64, 32, 14)
+    assert host.mlv_get_frame_count(clip.encode()) == ref.ref_get_frame_count(clip.encode()) == 14
+    for i in range(14):
+        ours, theirs = F.FrameHeaders(), F.FrameHeaders()
+        assert host.mlv_get_frame_headers(clip.encode(), i, C.byref(ours)) == 1
+        assert ref.ref_get_frame_headers(clip.encode(), i, C.byref(theirs)) == 1
+        assert bytes(ours) == bytes(theirs), f"frame {i}: headers differ"
+    bad = F.FrameHeaders()
+    assert host.mlv_get_frame_headers(clip.encode(), 14, C.byref(bad)) == 0
+
+
+class ImageBuffer(C.Structure):
+    pass
+
+
+ImageBuffer._fields_ = [("next", C.POINTER(ImageBuffer)), ("dng_filename", C.c_char_p), ("header_size", C.c_size_t),
+                        ("size", C.c_size_t), ("header", C.c_void_p), ("data", C.c_void_p),
+                        ("mutex", C.c_byte * 40), ("in_use", C.c_int), ("prefetched", C.c_int)]
+CBR = C.CFUNCTYPE(C.c_int, C.POINTER(ImageBuffer))
+
+
+def test_frame_cache_and_prefetch_queue(host):
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    built = []
+    lock = threading.Lock()
+
+    def build(ib):
+        name = ib.contents.dng_filename.decode()
+        time.sleep(0.01)
+        with lock:
+            built.append(name)
+        ib.contents.size = 64
+        ib.contents.data = libc.malloc(64)
+        ib.contents.header = libc.malloc(16)
+        ib.contents.header_size = 16
+        return 1
+
+    cbr = CBR(build)
+    limit = C.CFUNCTYPE(C.c_int, C.c_char_p)(lambda p: 20)
+    host.free_all_image_buffers()
+    host.resource_manager_set_prefetch(4, 4, limit)
+    created = C.c_int()
+    try:
+        for i in range(20):
+            path = b"/clip.MLV/clip_%06d.dng" % i
+            ib = host.get_or_create_image_buffer(path, cbr, C.byref(created))
+            assert ib
+            assert C.cast(ib, C.POINTER(ImageBuffer)).contents.data
+            host.release_image_buffer_by_path(path)
+            time.sleep(0.005)
+        time.sleep(0.1)
+        # every frame built exactly once, none beyond the clip's frame limit
+        assert sorted(built) == sorted(set(built))
+        assert set(built) == {f"/clip.MLV/clip_{i:06d}.dng" for i in range(20)}
+        b, h = C.c_uint64(), C.c_uint64()
+        host.resource_manager_prefetch_stats(C.byref(b), C.byref(h))
+        assert b.value >= 10 and h.value >= 10, (b.value, h.value)
+        assert host.get_image_buffer_count() <= 16 + 4 * 4
+        # a cached frame is returned without calling the callback again
+        n = len(built)
+        path = b"/clip.MLV/clip_%06d.dng" % 19
+        host.get_or_create_image_buffer(path, cbr, C.byref(created))
+        assert created.value == 0 and len(built) == n
+    finally:
+        host.resource_manager_set_prefetch(0, 0, None)
+        host.free_all_image_buffers()
