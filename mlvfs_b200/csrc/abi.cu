@@ -22,7 +22,7 @@ bool is_pinned(const void *p)
 int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes)
 {
     size_t pb, fb;
-    round_up(packed_bytes + 16, 256, &pb);
+    round_up(packed_bytes + 1024, 256, &pb);
     round_up(frame_bytes, 256, &fb);
     if (pb > s.packed_cap) {
         if (s.d_packed) cudaFree(s.d_packed);
@@ -70,11 +70,17 @@ namespace {
 // Decode the VIDF payload into unpacked 16-bit frames at d_frames (main.c:569-706 dispatch).
 int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, const void *d_payload,
                    size_t payload_stride, size_t payload_bytes, uint16_t *d_frames, size_t frame_stride, int nframes,
-                   cudaStream_t st)
+                   int *d_status, cudaStream_t st)
 {
     const int vc = hdr->file_hdr.videoClass;
     if (vc & MLVB_VIDEO_CLASS_FLAG_LZMA) return MLVB_ERR_UNSUPPORTED;      // legacy codec stays on the CPU side
-    if (vc & MLVB_VIDEO_CLASS_FLAG_LJ92) return MLVB_ERR_UNSUPPORTED;      // TODO(lj92): device decoder
+    if (vc & MLVB_VIDEO_CLASS_FLAG_LJ92) {                                 // main.c:617-681
+        StageTimer t(ctx, ST_LJ92, st);
+        int rc = launch_lj92_decode(d_payload, payload_stride, payload_bytes, d_frames, frame_stride, g.w, g.h, nframes,
+                                    d_status, st);
+        if (rc == MLVB_OK) ctx->launches += 1;
+        return rc;
+    }
     if (payload_bytes < mlvb_packed_bytes((uint32_t)g.npix, g.bpp)) return MLVB_ERR_ARG;
     StageTimer t(ctx, ST_UNPACK, st);
     int rc = launch_unpack(d_payload, payload_stride, payload_bytes, d_frames, frame_stride, (uint32_t)g.npix, g.bpp,
@@ -87,7 +93,7 @@ int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const Fra
 // on device buffers.  Finished frames end up in d_out.
 int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options &opts, const char *mlv_filename,
                  const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_work, uint16_t *d_out,
-                 size_t frame_stride, int nframes, cudaStream_t st, mlvb_frame_result *res)
+                 size_t frame_stride, int nframes, int *d_status, cudaStream_t st, mlvb_frame_result *res)
 {
     const FrameGeom g = geom_from_headers(hdr);
     if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
@@ -101,7 +107,7 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
                     g.black <= MLVB_MAX_BLACK;
     // without an out-of-place stage the chain can run directly in d_out
     uint16_t *d_a = cs ? d_work : d_out;
-    int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, st);
+    int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
     if (rc) return rc;
     if (opts.fix_pattern_noise || opts.dual_iso || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: next stages
     // main.c:975: the outer chroma smoothing is skipped whenever dual_iso == 2
@@ -152,6 +158,10 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
     for (auto &s : ctx->slots) {
         MLVB_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         MLVB_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        MLVB_CUDA_OK(cudaMalloc(&s.d_status, sizeof(int)));
+        MLVB_CUDA_OK(cudaMemset(s.d_status, 0, sizeof(int)));
+        MLVB_CUDA_OK(cudaHostAlloc(&s.h_status, sizeof(int), cudaHostAllocDefault));
+        *s.h_status = 0;
     }
     MLVB_CUDA_OK(cudaStreamCreateWithFlags(&ctx->batch_stream, cudaStreamNonBlocking));
     *out = ctx;
@@ -171,7 +181,10 @@ void mlvb_context_destroy(mlvb_context *ctx)
         if (s.d_b) cudaFree(s.d_b);
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_status) cudaFree(s.d_status);
+        if (s.h_status) cudaFreeHost(s.h_status);
     }
+    if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
     if (ctx->batch_stream) cudaStreamDestroy(ctx->batch_stream);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_stat) cudaFree(ctx->d_stat);
@@ -290,8 +303,13 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
         return fail(MLVB_ERR_CUDA);
 
     s->result = mlvb_frame_result();
-    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->stream,
-                      &s->result);
+    *s->h_status = 0;
+    const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
+    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->d_status,
+                      s->stream, &s->result);
+    if (rc == MLVB_OK && coded &&
+        cudaMemcpyAsync(s->h_status, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
+        rc = MLVB_ERR_CUDA;
     if (rc) { cudaStreamSynchronize(s->stream); return fail(rc); }
 
     s->out_bytes = frame_bytes;
@@ -319,6 +337,9 @@ int mlvb_wait(mlvb_context *ctx, mlvb_ticket ticket, mlvb_frame_result *res)
     if (cudaEventSynchronize(s->done) != cudaSuccess) {
         fprintf(stderr, "libmlvfs_b200: frame failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         rc = MLVB_ERR_CUDA;
+    } else if (*s->h_status != 0) {
+        fprintf(stderr, "libmlvfs_b200: LJ92: Failed (%d)\n", *s->h_status);      // main.c:671-679
+        rc = MLVB_ERR_ARG;
     } else if (s->user_dst) {
         memcpy(s->user_dst, s->h_out, s->out_bytes);
     }
@@ -355,8 +376,24 @@ int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr
     int rc = ctx->ensure_scratch((size_t)nframes * out_stride_px * sizeof(uint16_t));
     if (rc) return rc;
     mlvb_frame_result res;
-    return run_pipeline(ctx, hdr, *opts, mlv_filename, d_payload, payload_stride, payload_bytes, (uint16_t *)ctx->d_scratch,
-                        d_out, out_stride_px, nframes, st, &res);
+    const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
+    if (coded && ctx->batch_status_cap < (size_t)nframes) {
+        if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
+        ctx->d_batch_status = nullptr; ctx->batch_status_cap = 0;
+        MLVB_CUDA_OK(cudaMalloc(&ctx->d_batch_status, sizeof(int) * nframes));
+        ctx->batch_status_cap = nframes;
+    }
+    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, d_payload, payload_stride, payload_bytes, (uint16_t *)ctx->d_scratch,
+                      d_out, out_stride_px, nframes, ctx->d_batch_status, st, &res);
+    if (rc == MLVB_OK && coded) {
+        // a compressed batch reports corrupt streams synchronously (the decode dwarfs the sync)
+        std::vector<int> status(nframes);
+        MLVB_CUDA_OK(cudaMemcpyAsync(status.data(), ctx->d_batch_status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
+        MLVB_CUDA_OK(cudaStreamSynchronize(st));
+        for (int f = 0; f < nframes; f++)
+            if (status[f] != 0) { fprintf(stderr, "libmlvfs_b200: LJ92: frame %d failed (%d)\n", f, status[f]); rc = MLVB_ERR_ARG; }
+    }
+    return rc;
 }
 
 }  // extern "C"

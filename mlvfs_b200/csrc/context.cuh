@@ -58,6 +58,7 @@ struct Slot {
     uint16_t *d_a = nullptr, *d_b = nullptr;  size_t frame_cap = 0;     // bytes each
     uint8_t *h_in = nullptr;   size_t h_in_cap = 0;                    // pinned staging
     uint16_t *h_out = nullptr; size_t h_out_cap = 0;
+    int *d_status = nullptr, *h_status = nullptr;                       // codec status (LJ92), device + pinned
     // in-flight bookkeeping
     bool busy = false;
     int64_t ticket = -1;
@@ -89,6 +90,7 @@ struct mlvb_context {
     cudaStream_t batch_stream = nullptr;
     void *d_scratch = nullptr;  size_t scratch_cap = 0;
     void *d_stat = nullptr;     size_t stat_cap = 0;
+    int *d_batch_status = nullptr; size_t batch_status_cap = 0;        // per-frame codec status of a batch
 
     std::atomic<uint64_t> launches{0};
 

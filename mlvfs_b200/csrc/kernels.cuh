@@ -44,3 +44,7 @@ int launch_stripes_count(const uint16_t *d_img, int w, int h, int black, int whi
                          cudaStream_t st);
 int launch_stripes_hist(const uint16_t *d_img, int w, int h, int black, int white, const unsigned long long *d_offsets,
                         const uint16_t *d_dither, unsigned *d_hist, unsigned *d_num, int *d_median_bin, cudaStream_t st);
+
+// ---- lj92.cu ----
+int launch_lj92_decode(const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_out,
+                       size_t out_stride_px, int w, int h, int nframes, int *d_status, cudaStream_t st);

@@ -58,6 +58,11 @@ int  orc_stripes_compute(const uint16_t *img, int w, int h, int black, int white
                          orc_rand_t *rng, int coef[8]);
 void orc_stripes_apply(uint16_t *img, size_t n, int w, int black, int white, int needed, const int coef[8]);
 
+/* ---- LJ92 (lj92.c:82-709, main.c:617-681) ---- */
+int  orc_lj92_decode(const uint8_t *data, int len, uint16_t *out, int cap, int *w, int *h, int *bits);
+void orc_lj92_untile(const uint16_t *src, uint16_t *dst, int w, int h);
+long orc_lj92_encode(const uint16_t *img, int w, int h, int depth, uint8_t *out, size_t cap);
+
 /* ---- whole single-ISO chain in process_frame order (main.c:942-997) ---- */
 typedef struct {
     int chroma_smooth;      /* 0,2,3,5 */

@@ -213,3 +213,43 @@ def single_iso_chain(frames, black, white, frame_size, *, chroma_smooth_method=0
             img = stripes_apply(img, black, white, needed, coef)
         outs.append(img)
     return outs, state
+
+
+# ---- LJ92 (oracle/orc_lj92.c) -------------------------------------------------------------------
+
+def lj92_encode(tiled, depth=14):
+    """Encode a (already quadrant-interleaved) uint16 image with the oracle's independent encoder."""
+    lib = load_oracle()
+    lib.orc_lj92_encode.restype = C.c_long
+    tiled = np.ascontiguousarray(tiled, dtype=np.uint16)
+    h, w = tiled.shape
+    buf = np.zeros(w * h * 4 + 1024, dtype=np.uint8)
+    n = lib.orc_lj92_encode(_p(tiled), w, h, depth, _p(buf), C.c_size_t(buf.size))
+    if n < 0:
+        raise RuntimeError("orc_lj92_encode failed")
+    return buf[:n].copy()
+
+
+def lj92_payload(img, depth=14):
+    """VIDF payload of an LJ92 MLV frame: uint32 decoded size + stream of the interleaved image
+    (inverse of main.c:656-668)."""
+    h, w = img.shape
+    tiled = np.concatenate([np.concatenate([img[0::2, 0::2], img[0::2, 1::2]], axis=1),
+                            np.concatenate([img[1::2, 0::2], img[1::2, 1::2]], axis=1)], axis=0)
+    stream = lj92_encode(tiled, depth)
+    return np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), stream])
+
+
+def lj92_decode_payload(payload, w, h):
+    """Oracle decode + de-interleave of a VIDF LJ92 payload -> uint16 [h, w]."""
+    lib = load_oracle()
+    payload = np.ascontiguousarray(payload, dtype=np.uint8)
+    tiled = np.zeros(w * h, dtype=np.uint16)
+    ww, hh, bb = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.orc_lj92_decode(C.c_void_p(payload.ctypes.data + 4), int(payload.size - 4), _p(tiled), w * h,
+                             C.byref(ww), C.byref(hh), C.byref(bb))
+    if rc != 0:
+        raise RuntimeError(f"orc_lj92_decode failed: {rc}")
+    out = np.zeros((h, w), dtype=np.uint16)
+    lib.orc_lj92_untile(_p(tiled), _p(out), w, h)
+    return out
