@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "context.cuh"
 
 namespace {
@@ -43,6 +45,23 @@ int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes)
         s.frame_cap = s.h_out_cap = fb;
     }
     return MLVB_OK;
+}
+
+int reserve_device(void **p, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return MLVB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    MLVB_CUDA_OK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return MLVB_OK;
+}
+
+size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts)
+{
+    size_t need = 0;
+    if (opts.fix_pattern_noise) need = std::max(need, pattern_noise_scratch_bytes(g.w, g.h));
+    return need;
 }
 
 Slot *acquire_slot(mlvb_context *ctx)
@@ -93,7 +112,7 @@ int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const Fra
 // on device buffers.  Finished frames end up in d_out.
 int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options &opts, const char *mlv_filename,
                  const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_work, uint16_t *d_out,
-                 size_t frame_stride, int nframes, int *d_status, cudaStream_t st, mlvb_frame_result *res)
+                 size_t frame_stride, int nframes, int *d_status, void *d_aux, cudaStream_t st, mlvb_frame_result *res)
 {
     const FrameGeom g = geom_from_headers(hdr);
     if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
@@ -109,7 +128,15 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
     uint16_t *d_a = cs ? d_work : d_out;
     int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
     if (rc) return rc;
-    if (opts.fix_pattern_noise || opts.dual_iso || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: next stages
+    if (opts.fix_pattern_noise) {                                                   // main.c:946-949
+        StageTimer t(ctx, ST_PATTERN, st);
+        for (int f = 0; f < nframes; f++) {
+            rc = launch_pattern_noise((int16_t *)(d_a + (size_t)f * frame_stride), g.w, g.h, g.white, d_aux, st);
+            if (rc) return rc;
+            ctx->launches += 10;
+        }
+    }
+    if (opts.dual_iso || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: next stages
     // main.c:975: the outer chroma smoothing is skipped whenever dual_iso == 2
     return run_single_iso_chain(ctx, hdr, g, opts, mlv_filename, d_a, d_out, frame_stride, nframes, opts.dual_iso == 2, st);
 }
@@ -182,9 +209,11 @@ void mlvb_context_destroy(mlvb_context *ctx)
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.d_status) cudaFree(s.d_status);
+        if (s.d_aux) cudaFree(s.d_aux);
         if (s.h_status) cudaFreeHost(s.h_status);
     }
     if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
+    if (ctx->d_batch_aux) cudaFree(ctx->d_batch_aux);
     if (ctx->batch_stream) cudaStreamDestroy(ctx->batch_stream);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_stat) cudaFree(ctx->d_stat);
@@ -305,8 +334,10 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
     s->result = mlvb_frame_result();
     *s->h_status = 0;
     const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
+    rc = reserve_device(&s->d_aux, &s->aux_cap, aux_bytes_for(g, *opts));
+    if (rc) return fail(rc);
     rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->d_status,
-                      s->stream, &s->result);
+                      s->d_aux, s->stream, &s->result);
     if (rc == MLVB_OK && coded &&
         cudaMemcpyAsync(s->h_status, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
         rc = MLVB_ERR_CUDA;
@@ -379,12 +410,15 @@ int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr
     const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
     if (coded && ctx->batch_status_cap < (size_t)nframes) {
         if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
+    if (ctx->d_batch_aux) cudaFree(ctx->d_batch_aux);
         ctx->d_batch_status = nullptr; ctx->batch_status_cap = 0;
         MLVB_CUDA_OK(cudaMalloc(&ctx->d_batch_status, sizeof(int) * nframes));
         ctx->batch_status_cap = nframes;
     }
+    rc = reserve_device(&ctx->d_batch_aux, &ctx->batch_aux_cap, aux_bytes_for(g, *opts));
+    if (rc) return rc;
     rc = run_pipeline(ctx, hdr, *opts, mlv_filename, d_payload, payload_stride, payload_bytes, (uint16_t *)ctx->d_scratch,
-                      d_out, out_stride_px, nframes, ctx->d_batch_status, st, &res);
+                      d_out, out_stride_px, nframes, ctx->d_batch_status, ctx->d_batch_aux, st, &res);
     if (rc == MLVB_OK && coded) {
         // a compressed batch reports corrupt streams synchronously (the decode dwarfs the sync)
         std::vector<int> status(nframes);

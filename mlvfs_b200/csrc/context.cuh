@@ -58,6 +58,7 @@ struct Slot {
     uint16_t *d_a = nullptr, *d_b = nullptr;  size_t frame_cap = 0;     // bytes each
     uint8_t *h_in = nullptr;   size_t h_in_cap = 0;                    // pinned staging
     uint16_t *h_out = nullptr; size_t h_out_cap = 0;
+    void *d_aux = nullptr; size_t aux_cap = 0;                          // per-slot scratch (pattern noise, dual ISO)
     int *d_status = nullptr, *h_status = nullptr;                       // codec status (LJ92), device + pinned
     // in-flight bookkeeping
     bool busy = false;
@@ -90,7 +91,8 @@ struct mlvb_context {
     cudaStream_t batch_stream = nullptr;
     void *d_scratch = nullptr;  size_t scratch_cap = 0;
     void *d_stat = nullptr;     size_t stat_cap = 0;
-    int *d_batch_status = nullptr; size_t batch_status_cap = 0;        // per-frame codec status of a batch
+    int *d_batch_status = nullptr; size_t batch_status_cap = 0;
+    void *d_batch_aux = nullptr; size_t batch_aux_cap = 0;        // per-frame codec status of a batch
 
     std::atomic<uint64_t> launches{0};
 
@@ -148,3 +150,7 @@ int compute_stripes(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img
 Slot *acquire_slot(mlvb_context *ctx);
 void release_slot(mlvb_context *ctx, Slot *s);
 int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes);
+int reserve_device(void **p, size_t *cap, size_t bytes);
+
+// stage scratch requirement for a frame of this geometry under these options (0 if none)
+size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts);

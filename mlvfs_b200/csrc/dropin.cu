@@ -275,4 +275,24 @@ void stripes_apply_correction(struct frame_headers *frame_headers, struct stripe
                          });
 }
 
+// ---------------------------------------------------------------- patternnoise.c:357-380
+
+void fix_pattern_noise(int16_t *raw, int w, int h, int white, int debug_flags)
+{
+    if (debug_flags) { fprintf(stderr, "libmlvfs_b200: fix_pattern_noise: debug views are not implemented\n"); return; }
+    if (w < 2 || h < 2) return;
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: fix_pattern_noise: no CUDA context (no CPU path)\n"); return; }
+    Lease L(ctx);
+    const size_t npix = (size_t)w * h;
+    if (slot_reserve(*L.s, 16, npix * 2) != MLVB_OK) return;
+    if (reserve_device(&L.s->d_aux, &L.s->aux_cap, pattern_noise_scratch_bytes(w, h)) != MLVB_OK) return;
+    cudaStream_t st = L.s->stream;
+    if (cudaMemcpyAsync(L.s->d_a, raw, npix * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return;
+    if (launch_pattern_noise((int16_t *)L.s->d_a, w, h, white, L.s->d_aux, st) != MLVB_OK) { cudaStreamSynchronize(st); return; }
+    ctx->launches += 10;
+    if (cudaMemcpyAsync(raw, L.s->d_a, npix * 2, cudaMemcpyDeviceToHost, st) != cudaSuccess) return;
+    sync_ok(st, "fix_pattern_noise");
+}
+
 }  // extern "C"

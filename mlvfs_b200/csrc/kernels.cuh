@@ -48,3 +48,7 @@ int launch_stripes_hist(const uint16_t *d_img, int w, int h, int black, int whit
 // ---- lj92.cu ----
 int launch_lj92_decode(const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_out,
                        size_t out_stride_px, int w, int h, int nframes, int *d_status, cudaStream_t st);
+
+// ---- patternnoise.cu ----
+size_t pattern_noise_scratch_bytes(int w, int h);
+int launch_pattern_noise(int16_t *d_raw, int w, int h, int white, void *d_scratch, cudaStream_t st);

@@ -63,6 +63,9 @@ int  orc_lj92_decode(const uint8_t *data, int len, uint16_t *out, int cap, int *
 void orc_lj92_untile(const uint16_t *src, uint16_t *dst, int w, int h);
 long orc_lj92_encode(const uint16_t *img, int w, int h, int depth, uint8_t *out, size_t cap);
 
+/* ---- pattern noise (patternnoise.c:47-380) ---- */
+void orc_fix_pattern_noise(int16_t *raw, int w, int h, int white);
+
 /* ---- whole single-ISO chain in process_frame order (main.c:942-997) ---- */
 typedef struct {
     int chroma_smooth;      /* 0,2,3,5 */

@@ -253,3 +253,13 @@ def lj92_decode_payload(payload, w, h):
     out = np.zeros((h, w), dtype=np.uint16)
     lib.orc_lj92_untile(_p(tiled), _p(out), w, h)
     return out
+
+
+# ---- pattern noise (oracle/orc_patternnoise.c) ---------------------------------------------------
+
+def fix_pattern_noise(img, white):
+    lib = load_oracle()
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    lib.orc_fix_pattern_noise(_p(out), w, h, int(white))
+    return out

@@ -169,3 +169,40 @@ def test_process_frame_chain_matches_reference(oracle, ref, tmp_path):
     assert len(state["badpix"]) > 10 and state["stripes"][0] == 1
     for i in range(3):
         assert np.array_equal(got[i], want[i]), i
+
+
+def test_pattern_noise_matches_reference(oracle, ref):
+    for (w, h) in [(320, 180), (130, 256)]:
+        img = synth.make_frame(w, h, 0)
+        rng = np.random.default_rng(1)
+        img = (img.astype(np.int32) + rng.integers(-12, 13, size=(1, w)) + rng.integers(-9, 10, size=(h, 1)))
+        img = img.clip(0, 16383).astype(np.uint16)
+        img[20:40, 50:90] = 15200
+        want = img.copy()
+        with oracle.quiet_stdout():
+            ref.fix_pattern_noise(_p(want), w, h, 15000, 0)
+        assert np.array_equal(oracle.fix_pattern_noise(img, 15000), want)
+
+
+def test_lj92_codec_matches_reference(oracle, ref):
+    """Our decoder reads the reference encoder's stream; the reference decoder reads our encoder's stream."""
+    w, h = 352, 198
+    img = synth.make_frame(w, h, 2, hot_cold=True, bad_density=1e-3)
+    tiled = np.ascontiguousarray(synth.quadrant_interleave(img))
+    # reference encode -> oracle decode
+    enc, n = C.POINTER(C.c_uint8)(), C.c_int()
+    ref.lj92_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p]
+    assert ref.lj92_encode(_p(tiled), w, h, 14, w * h, 0, None, 0, C.byref(enc), C.byref(n)) == 0
+    stream = np.ctypeslib.as_array(enc, (n.value,)).copy()
+    payload = np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), stream])
+    assert np.array_equal(oracle.lj92_decode_payload(payload, w, h), img)
+    # oracle encode -> reference decode
+    mine = oracle.lj92_encode(tiled)
+    hd, W, H, B = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+    assert ref.lj92_open(C.byref(hd), _p(mine), int(mine.size), C.byref(W), C.byref(H), C.byref(B)) == 0
+    assert (W.value, H.value, B.value) == (w, h, 14)
+    out = np.zeros(w * h, np.uint16)
+    ref.lj92_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    assert ref.lj92_decode(hd, _p(out), w * h, 0, None, 0) == 0
+    assert np.array_equal(out.reshape(h, w), tiled)
