@@ -275,6 +275,8 @@ void stripes_apply_correction(struct frame_headers *frame_headers, struct stripe
                          });
 }
 
+// ---------------------------------------------------------------- hdr.c (dual ISO): see dualiso.cu
+
 // ---------------------------------------------------------------- patternnoise.c:357-380
 
 void fix_pattern_noise(int16_t *raw, int w, int h, int white, int debug_flags)
