@@ -210,6 +210,120 @@ void launch_cs(const T *in, T *out, const CsParams &P, int nframes, cudaStream_t
     chroma_smooth_kernel<T, METHOD><<<grid, CS_THREADS, 0, st>>>(in, out, P);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 fast path (uint16, even w and h): register-only "warp strip" kernel.
+//
+// A warp owns 32 adjacent quad columns (lanes 1..30 produce output, lanes 0 and 31 are the halo
+// shared with the neighbouring strips) and walks down CS3_ROWS quad rows.  Every lane keeps the
+// (ge, dr, db) triplets of its own column for the rows y-1, y, y+1 in registers, sorts that
+// 3-element column once per step and obtains the neighbours' sorted columns with shuffles; the
+// median of 9 is then  med3( max(lows), med3(mids), min(highs) ).  No shared memory, no halo
+// recomputation beyond 2/32 lanes and 2/(CS3_ROWS+2) rows, no per-pixel index arithmetic.
+constexpr int CS3_ROWS = 34;         // output quad rows per warp
+constexpr int CS3_WARPS = 4;
+
+struct RowQ { uint32_t top, bot; int ge, dr, db; };      // top = r | g1<<16, bot = g2 | b<<16
+
+__device__ __forceinline__ void sort3(int &a, int &b, int &c)
+{
+    int t = min(a, b); b = max(a, b); a = t;
+    t = min(b, c); c = max(b, c); b = t;
+    t = min(a, b); b = max(a, b); a = t;
+}
+__device__ __forceinline__ int med3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+__device__ __forceinline__ RowQ load_rowq(const uint16_t *img, int w, int ph, int x, int qr, bool col_ok, const int *raw2ev)
+{
+    RowQ q = {0u, 0u, 0, 0, 0};
+    if (col_ok && qr >= 0 && qr < ph) {
+        const uint16_t *p = img + (size_t)(2 * qr) * w + x;
+        q.top = *reinterpret_cast<const uint32_t *>(p);
+        q.bot = *reinterpret_cast<const uint32_t *>(p + w);
+        q.ge = wadd(__ldg(raw2ev + (q.top >> 16)), __ldg(raw2ev + (q.bot & 0xFFFF))) / 2;
+        q.dr = wsub(__ldg(raw2ev + (q.top & 0xFFFF)), q.ge);
+        q.db = wsub(__ldg(raw2ev + (q.bot >> 16)), q.ge);
+    }
+    return q;
+}
+
+__device__ __forceinline__ int median9_columns(int a, int b, int c)
+{
+    sort3(a, b, c);                                               // own column: a <= b <= c
+    const int al = __shfl_up_sync(0xFFFFFFFFu, a, 1), ar = __shfl_down_sync(0xFFFFFFFFu, a, 1);
+    const int bl = __shfl_up_sync(0xFFFFFFFFu, b, 1), br = __shfl_down_sync(0xFFFFFFFFu, b, 1);
+    const int cl = __shfl_up_sync(0xFFFFFFFFu, c, 1), cr = __shfl_down_sync(0xFFFFFFFFu, c, 1);
+    return med3(max(max(al, a), ar), med3(bl, b, br), min(min(cl, c), cr));
+}
+
+// exact stripes.c:250-266 for 0 < coef: ((v - black) * coef >> 16) + black, clamped at white
+__device__ __forceinline__ uint32_t stripe_gain_fast(uint32_t v, uint32_t coef, int black16, int white16)
+{
+    if ((int)v > black16 + 64) {
+        const uint32_t t = __umulhi((v - (uint32_t)black16) << 16, coef) + (uint32_t)black16;
+        return min(t, (uint32_t)white16);
+    }
+    return v;
+}
+
+template <bool STRIPES>
+__global__ void __launch_bounds__(CS3_WARPS * 32)
+chroma3_strip_kernel(const uint16_t *__restrict__ in_base, uint16_t *__restrict__ out_base, const CsParams P)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = P.w, pw = w >> 1, ph = P.h >> 1;
+    const int strip = blockIdx.x * CS3_WARPS + warp;
+    const int qc = strip * 30 + lane - 1;
+    if (strip * 30 >= pw) return;                                  // whole warp out of the frame
+    const bool col_ok = qc >= 0 && qc < pw;
+    const int x = 2 * qc;
+    const uint16_t *in = in_base + (size_t)blockIdx.z * P.frame_stride;
+    uint16_t *out = out_base + (size_t)blockIdx.z * P.frame_stride;
+    const int *raw2ev = P.raw2ev;
+    const int qr0 = blockIdx.y * CS3_ROWS, qr1 = min(qr0 + CS3_ROWS, ph);
+    const bool x_inside = x >= 4 && x < w - 4;                     // chroma_smooth.c:28
+    const bool writer = col_ok && lane >= 1 && lane <= 30;
+    uint32_t c0 = 0, c1 = 0;
+    if (STRIPES) { c0 = (uint32_t)P.coef[x & 7]; c1 = (uint32_t)P.coef[(x + 1) & 7]; }
+
+    RowQ A = load_rowq(in, w, ph, x, qr0 - 1, col_ok, raw2ev);
+    RowQ B = load_rowq(in, w, ph, x, qr0, col_ok, raw2ev);
+    for (int qr = qr0; qr < qr1; qr++) {
+        const RowQ C = load_rowq(in, w, ph, x, qr + 1, col_ok, raw2ev);
+        const int mr = median9_columns(A.dr, B.dr, C.dr);
+        const int mb = median9_columns(A.db, B.db, C.db);
+        uint32_t top = B.top, bot = B.bot;
+        const int y = 2 * qr;
+        if (x_inside && y >= 4 && y < P.h - 5 && B.ge >= 2 * MLVB_EV_RES) {      // chroma_smooth.c:26,35
+            const int er = wadd(B.ge, mr), eb = wadd(B.ge, mb);
+            if (er > MLVB_EV_RES && eb > MLVB_EV_RES) {                          // chroma_smooth.c:63-64
+                const uint32_t r = (uint32_t)(__ldg(P.ev2raw_u16 + clamp_ev(er)) + P.black) & 0xFFFFu;
+                const uint32_t b = (uint32_t)(__ldg(P.ev2raw_u16 + clamp_ev(eb)) + P.black) & 0xFFFFu;
+                top = (top & 0xFFFF0000u) | r;
+                bot = (bot & 0x0000FFFFu) | (b << 16);
+            }
+        }
+        if (STRIPES) {
+            top = stripe_gain_fast(top & 0xFFFF, c0, P.black16, P.white16) | (stripe_gain_fast(top >> 16, c1, P.black16, P.white16) << 16);
+            bot = stripe_gain_fast(bot & 0xFFFF, c0, P.black16, P.white16) | (stripe_gain_fast(bot >> 16, c1, P.black16, P.white16) << 16);
+        }
+        if (writer) {
+            uint16_t *o = out + (size_t)y * w + x;
+            *reinterpret_cast<uint32_t *>(o) = top;
+            *reinterpret_cast<uint32_t *>(o + w) = bot;
+        }
+        A = B;
+        B = C;
+    }
+}
+
+void launch_cs3_fast(const uint16_t *in, uint16_t *out, const CsParams &P, int nframes, cudaStream_t st)
+{
+    const int pw = P.w / 2, ph = P.h / 2;
+    dim3 grid(ceil_div(ceil_div(pw, 30), CS3_WARPS), ceil_div(ph, CS3_ROWS), nframes);
+    if (P.stripes) chroma3_strip_kernel<true><<<grid, CS3_WARPS * 32, 0, st>>>(in, out, P);
+    else chroma3_strip_kernel<false><<<grid, CS3_WARPS * 32, 0, st>>>(in, out, P);
+}
+
 }  // namespace
 
 int launch_chroma_smooth_u16(const uint16_t *d_in, uint16_t *d_out, int w, int h, size_t frame_stride, int nframes,
@@ -231,7 +345,14 @@ int launch_chroma_smooth_u16(const uint16_t *d_in, uint16_t *d_out, int w, int h
     }
     switch (method) {
     case 2: launch_cs<uint16_t, 2>(d_in, d_out, P, nframes, st); break;
-    case 3: launch_cs<uint16_t, 3>(d_in, d_out, P, nframes, st); break;
+    case 3: {
+        bool fast = (w % 2 == 0) && (h % 2 == 0) && w >= 8 && h >= 8 && ((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out % 4 == 0) &&
+                    (frame_stride % 2 == 0);
+        for (int i = 0; i < 8 && P.stripes; i++) fast = fast && P.coef[i] > 0;     // fast gain needs positive coefficients
+        if (fast) launch_cs3_fast(d_in, d_out, P, nframes, st);
+        else launch_cs<uint16_t, 3>(d_in, d_out, P, nframes, st);
+        break;
+    }
     case 5: launch_cs<uint16_t, 5>(d_in, d_out, P, nframes, st); break;
     default: return MLVB_ERR_ARG;
     }
