@@ -61,6 +61,7 @@ size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts)
 {
     size_t need = 0;
     if (opts.fix_pattern_noise) need = std::max(need, pattern_noise_scratch_bytes(g.w, g.h));
+    if (opts.dual_iso == 2) need = std::max(need, dual_iso_scratch_bytes(g.w, g.h));
     return need;
 }
 
@@ -136,9 +137,25 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
             ctx->launches += 10;
         }
     }
-    if (opts.dual_iso || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: next stages
-    // main.c:975: the outer chroma smoothing is skipped whenever dual_iso == 2
-    return run_single_iso_chain(ctx, hdr, g, opts, mlv_filename, d_a, d_out, frame_stride, nframes, opts.dual_iso == 2, st);
+    if (opts.dual_iso == 1 || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: preview dual ISO, deflicker
+    if (opts.dual_iso == 2) {                                                       // main.c:956-973
+        for (int f = 0; f < nframes; f++) {
+            uint16_t *fa = d_a + (size_t)f * frame_stride, *fo = d_out + (size_t)f * frame_stride;
+            StageTimer *t = new StageTimer(ctx, ST_DUALISO, st);
+            rc = run_cr2hdr20(ctx, hdr, g, fa, opts.hdr_interpolation_method, !opts.hdr_no_fullres, !opts.hdr_no_alias_map,
+                              opts.chroma_smooth, opts.fix_bad_pixels, d_aux, st);
+            delete t;
+            if (rc < 0) return rc;
+            FrameGeom gf = g;
+            if (rc == 1) { gf.black *= 4; gf.white *= 4; }                         // hdr.c:1951-1952
+            if (f == 0) { res->is_dual_iso = rc; res->black_level = gf.black; res->white_level = gf.white; }
+            // converted: only stripes remain; not converted: the usual chain minus chroma smoothing (main.c:975)
+            rc = run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, 1, rc == 1, st);
+            if (rc) return rc;
+        }
+        return MLVB_OK;
+    }
+    return run_single_iso_chain(ctx, hdr, g, opts, mlv_filename, d_a, d_out, frame_stride, nframes, 0, 0, st);
 }
 
 std::mutex g_default_mu;
@@ -251,6 +268,7 @@ void mlvb_reset_clip_state(mlvb_context *ctx)
     for (auto &m : ctx->bad_maps) m = BadPixelMap();
     ctx->bad_map_cursor = 0;
     ctx->focus_maps.clear();
+    dual_iso_reset_tables(ctx);          // the 20-bit EV tables remember the first frame's white level (hdr.c:1089-1093)
 }
 
 void mlvb_seed_dither(mlvb_context *ctx, unsigned seed)

@@ -293,12 +293,12 @@ int compute_stripes(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img
 
 int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g,
                          const mlvb_options &opts, const char *mlv_filename, uint16_t *d_a, uint16_t *d_out,
-                         size_t frame_stride, int nframes, int skip_chroma, cudaStream_t st)
+                         size_t frame_stride, int nframes, int skip_chroma, int skip_pixfix, cudaStream_t st)
 {
-    int rc;
+    int rc = MLVB_OK;
     // --- focus pixels, then bad pixels (main.c:966-973), in place on d_a
     std::shared_ptr<PixelList> focus, bad;
-    {
+    if (!skip_pixfix) {
         std::lock_guard<std::mutex> lk(ctx->clip_mu);
         rc = get_focus_pixel_map(ctx, hdr, &focus);
         if (rc) return rc;
@@ -310,7 +310,7 @@ int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, con
         if (rc) return rc;
         ctx->launches += 1 + (focus->nlevels > 1);
     }
-    if (opts.fix_bad_pixels && g.black <= MLVB_MAX_BLACK) {
+    if (!skip_pixfix && opts.fix_bad_pixels && g.black <= MLVB_MAX_BLACK) {
         {
             std::lock_guard<std::mutex> lk(ctx->clip_mu);
             rc = get_bad_pixel_map(ctx, hdr, g, opts.fix_bad_pixels == 2, d_a, st, &bad);

@@ -138,7 +138,13 @@ FrameGeom geom_from_headers(const struct frame_headers *hdr);
 // only when no chroma smoothing is requested).  Creates per-clip state from frame 0 when missing.
 int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g,
                          const mlvb_options &opts, const char *mlv_filename, uint16_t *d_a, uint16_t *d_out,
-                         size_t frame_stride, int nframes, int skip_chroma, cudaStream_t st);
+                         size_t frame_stride, int nframes, int skip_chroma, int skip_pixfix, cudaStream_t st);
+
+// dualiso.cu
+size_t dual_iso_scratch_bytes(int w, int h);
+int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, int interp_method,
+                 int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st);
+void dual_iso_reset_tables(mlvb_context *ctx);
 
 // per-clip state accessors (call with ctx->clip_mu held)
 int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, int aggressive,

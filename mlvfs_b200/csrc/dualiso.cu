@@ -1,8 +1,784 @@
-// dualiso.cu -- dual-ISO entry points (reference hdr.c).  NOT BUILT YET in this round: both entry
-// points report failure loudly (return 0 = "not converted", exactly what the reference returns when it
-// cannot convert a frame, hdr.c:1953-1956), so a caller never receives silently unprocessed data
-// labelled as converted.  mlvb_process_frame returns MLVB_ERR_UNSUPPORTED for dual_iso != 0.
+// dualiso.cu -- full dual-ISO conversion ("cr2hdr 20-bit"), mean23 interpolation path.
+//
+// Replaces reference hdr.c:1932-1957 (cr2hdr20_convert_data) and hdr_interpolate hdr.c:1774-1930 with
+// its stages: hdr_check :407, identify_rggb_or_gbrg :441, identify_bright_and_dark_fields :497,
+// white_detect :250, convert_to_20bit :825, match_exposures :638, build_ev2raw_lut :839,
+// mean32_interpolate :1231 (mean2/mean3 :341-368), border_interpolate :1306, fullres_reconstruction
+// :1355, mix_images :1524, hdr_chroma_smooth :1502 (kernel in chroma.cu), build_alias_map :1382,
+// final_blend :1663, convert_20_to_16bit :1760.  The AMaZE + edge-directed interpolation
+// (hdr.c:917-1229, amaze_demosaic_RT.c) is NOT built yet: interp_method 0 fails loudly.
+//
+// Structure: three frame-global statistics barriers (row-field detection -> white levels -> exposure
+// matching), each a histogram / selection kernel plus a tiny scalar epilogue on the host (the same
+// integer logic as the reference, O(bins)); everything per-pixel runs on the GPU.  Statistics are
+// exact integers; the per-pixel blends use IEEE fp64 without FMA contraction (-fmad=false) like the
+// reference's SSE2 code; log2/cos/pow inside the mixing curves come from CUDA's fp64 library
+// (<= 2 ulp from glibc), which can move a blend by one EV-LUT step (1/32768 EV) at most: the stage
+// is a tolerance stage (<= 1 DN on the 16-bit output) as the north star states.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "context.cuh"
+
+namespace {
+
+constexpr int EVR = MLVB_EV_RES;
+constexpr int N20 = 1 << 20;
+constexpr int ALIAS_MAP_MAX = 15000;
+constexpr double FULLRES_THR = 0.8;
+constexpr int DARK_NOISE = 512;         // compute_noise sees an empty window: 8 DN * 64
+constexpr double DARK_NOISE_EV = 9.0;
+
+// ------------------------------------------------------------------ phase A: frame statistics
+
+struct StatsA {
+    double ev_sum;                      // hdr_check
+    unsigned long long ev_num;
+    unsigned hist_cfa[4][16384];        // identify_rggb_or_gbrg
+    unsigned hist_field[2][4][16384];   // identify_bright_and_dark_fields for row offset 0 (RGGB) and 1 (GBRG)
+};
+
+__global__ void __launch_bounds__(256)
+diso_stats_a_kernel(const uint16_t *__restrict__ img, int w, int h, int black, int white, const double *__restrict__ raw2evf,
+                    StatsA *__restrict__ S)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    double ev = 0.0;
+    unsigned num = 0;
+    if (x < w) {
+        const int p = img[x + (size_t)y * w];
+        if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
+        if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
+        const int ys = y - 1;                                                                          // GBRG: frame starts one row lower
+        if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
+        if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {                                              // hdr.c:419-433
+            const int p2 = img[x + (size_t)(y + 2) * w];
+            if ((p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
+                ev = fabs(raw2evf[p2] - raw2evf[p]);
+                num = 1;
+            }
+        }
+    }
+    // block reduction of the hdr_check sum
+    __shared__ double s_ev[8];
+    __shared__ unsigned s_num[8];
+    for (int o = 16; o; o >>= 1) { ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o); num += __shfl_xor_sync(0xFFFFFFFFu, num, o); }
+    if ((threadIdx.x & 31) == 0) { s_ev[threadIdx.x >> 5] = ev; s_num[threadIdx.x >> 5] = num; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e = 0; unsigned n = 0;
+        for (int i = 0; i < 8; i++) { e += s_ev[i]; n += s_num[i]; }
+        if (n) { atomicAdd(&S->ev_sum, e); atomicAdd(&S->ev_num, (unsigned long long)n); }
+    }
+}
+
+// ------------------------------------------------------------------ phase B: white levels (hdr.c:250-300)
+
+struct FieldInfo { int is_bright[4]; int y1; };
+
+__global__ void diso_white_kernel(const uint16_t *__restrict__ img, int w, int h, FieldInfo F, int max_pix,
+                                  unsigned n_dark, unsigned n_bright, unsigned *__restrict__ hist /* [2][65536] */)
+{
+    const int nx = (w + 2) / 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int x = 3 * i, y = F.y1 + 3 * j;
+    if (i >= nx || y >= h) return;
+    const int c = F.is_bright[y % 4];
+    // rank of this sample among its class in raster order: class rows before row j (period 4 in j)
+    int per_period = 0, partial = 0;
+    for (int k = 0; k < 4; k++) per_period += (F.is_bright[(F.y1 + 3 * k) % 4] == c);
+    for (int k = 0; k < (j & 3); k++) partial += (F.is_bright[(F.y1 + 3 * k) % 4] == c);
+    const unsigned rank = (unsigned)((j >> 2) * per_period + partial) * nx + i;
+    const unsigned n_c = c ? n_bright : n_dark;
+    // a full array keeps overwriting its last slot: only the last sample survives there (hdr.c:279-281)
+    if (rank < (unsigned)(max_pix - 1) || rank == n_c - 1) atomicAdd(&hist[c * 65536 + img[x + (size_t)y * w]], 1u);
+}
+
+// ------------------------------------------------------------------ phase C: exposure matching statistics (hdr.c:638-722)
+
+struct ExpoParams { int black16, clip, clip0, y0; };
+
+__device__ __forceinline__ int p16_of(uint16_t v) { return (int)(((uint32_t)v << 2) & 0xFFFF); }   // ((v << 6) & 0xFFFFF) >> 4
+
+__global__ void diso_expo_pairs_kernel(const uint16_t *__restrict__ img, int w, int h, FieldInfo F, ExpoParams E,
+                                       int2 *__restrict__ pairs, unsigned *__restrict__ hist /* [2][HB] bright, dark */, int HB)
+{
+    const int nx = (w + 2) / 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int x = 3 * i, y = E.y0 + 3 * j;
+    if (i >= nx || y >= h - 2) return;
+    const int pa = p16_of(img[x + (size_t)(y - 2) * w]) - E.black16, pb = p16_of(img[x + (size_t)(y + 2) * w]) - E.black16;
+    int pn = p16_of(img[x + (size_t)y * w]) - E.black16;
+    int pi = (pa + pb + 1) / 2;
+    if (pa >= E.clip || pb >= E.clip) pi = E.clip0;
+    if (pi >= E.clip) pn = E.clip0;
+    const int b = F.is_bright[y % 4] ? pn : pi, d = F.is_bright[y % 4] ? pi : pn;
+    pairs[(size_t)j * nx + i] = make_int2(b, d);
+    if (b < E.clip) {
+        atomicAdd(&hist[min(max(b + E.black16, 0), HB - 1)], 1u);
+        atomicAdd(&hist[HB + min(max(d + E.black16, 0), HB - 1)], 1u);
+    }
+}
+
+__global__ void diso_highlights_kernel(const int2 *__restrict__ pairs, unsigned n, int b_lo, int b_hi, int2 *__restrict__ sel,
+                                       unsigned *__restrict__ nsel, unsigned cap)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 p = pairs[i];
+    if (p.x >= b_hi || p.x <= b_lo) return;                        // hdr.c:737-738
+    const unsigned k = atomicAdd(nsel, 1u);
+    if (k < cap) sel[k] = p;
+}
+
+// one CTA per candidate slope (hdr.c:751-772)
+__global__ void diso_score_kernel(const int2 *__restrict__ sel, const unsigned *__restrict__ nsel, unsigned cap,
+                                  const double *__restrict__ test_a, int dmed, int bmed, unsigned *__restrict__ scores)
+{
+    const double ta = test_a[blockIdx.x], tb = (double)dmed - (double)bmed * ta;
+    const unsigned n = min(*nsel, cap);
+    unsigned s = 0;
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 p = sel[i];
+        const int e = (int)((double)p.y - ((double)p.x * ta + tb));
+        s += (abs(e) < 50);
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    __shared__ unsigned sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned t = 0; for (unsigned i = 0; i < blockDim.x / 32; i++) t += sw[i]; scores[blockIdx.x] = t; }
+}
+
+// ------------------------------------------------------------------ phase D: per-pixel pipeline
+
+struct PixParams {
+    int w, h;
+    int is_bright[4];
+    int black, white, white_darkened;                 // 20-bit
+    double a, b20;                                    // exposure match (hdr.c:784-808)
+    double corr_ev, overlap, max_ev;                  // mixing curve (hdr.c:1540-1571)
+    const int *raw2ev;                                // 20-bit tables (hdr.c:839-874)
+    const int *ev2raw;                                // pointer pre-offset by 10 EV
+    int use_fullres, use_alias;
+};
+
+// 14 -> 20 bit (hdr.c:825-837) + exposure matching apply (hdr.c:784-808)
+__global__ void diso_to20_kernel(const uint16_t *__restrict__ img, uint32_t *__restrict__ raw32, const PixParams P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.w) return;
+    const size_t i = x + (size_t)y * P.w;
+    int p = (int)(((uint32_t)img[i] << 6) & 0xFFFFF);
+    if (p != 0) {
+        if (P.is_bright[y % 4]) p = (int)((double)(p - P.black) * P.a + (double)P.black + P.b20 * P.a);
+        else p = (int)((double)p - P.b20 + P.b20 * P.a);
+        p = min(max(p, 0), 0xFFFFF);
+    }
+    raw32[i] = (uint32_t)p;
+}
+
+__device__ __forceinline__ int mean2_ev(int a, int b, int white) { return (a >= white || b >= white) ? white : (a + b) / 2; }
+__device__ __forceinline__ int mean3_ev(int a, int b, int c, int white)
+{
+    const int m = (a + b + c) / 3;
+    return (a >= white || b >= white || c >= white) ? max(m, white) : m;
+}
+
+// mean32_interpolate + border_interpolate + fullres_reconstruction, one thread per pixel
+__global__ void diso_interp_kernel(const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark, uint32_t *__restrict__ bright,
+                                   uint32_t *__restrict__ fullres, const PixParams P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int w = P.w, h = P.h;
+    if (x >= w) return;
+#define R(xx, yy) ((int)raw32[(xx) + (size_t)(yy) * w])
+    const int br = P.is_bright[y % 4];
+    uint32_t native, interp;
+    // precedence = order of the loops in border_interpolate (hdr.c:1312-1352), later loops win
+    if (y >= 2 && x < 2) { interp = R(x, y - 2); native = R(x, y); }
+    else if (y >= 2 && x >= w - 3) { interp = R(x - 2, y - 2); native = R(x - 2, y); }
+    else if (y >= h - 4) { interp = R(x, y - 2); native = R(x, y); }
+    else if (y < 3) { interp = R(x, y + 2); native = R(x, y); }
+    else {
+        // mean23 interior (hdr.c:1255-1299); pairs start at even x
+        const int white = !br ? P.white_darkened : P.white;
+        const int wev = __ldg(P.raw2ev + white);
+        const int s = (P.is_bright[y % 4] == P.is_bright[(y + 1) % 4]) ? -1 : 1;
+        const int xe = x & ~1;
+        int ev;
+        if ((y & 1) == 0) {
+            if (x == xe) ev = mean2_ev(__ldg(P.raw2ev + R(x, y - 2)), __ldg(P.raw2ev + R(x, y + 2)), wev);
+            else ev = mean3_ev(__ldg(P.raw2ev + R(xe + 2, y + s)), __ldg(P.raw2ev + R(xe, y + s)), __ldg(P.raw2ev + R(xe + 1, y - 2 * s)), wev);
+        } else {
+            if (x == xe) ev = mean3_ev(__ldg(P.raw2ev + R(xe + 1, y + s)), __ldg(P.raw2ev + R(xe - 1, y + s)), __ldg(P.raw2ev + R(xe, y - 2 * s)), wev);
+            else ev = mean2_ev(__ldg(P.raw2ev + R(x, y - 2)), __ldg(P.raw2ev + R(x, y + 2)), wev);
+        }
+        interp = (uint32_t)__ldg(P.ev2raw + ev);
+        native = R(x, y);
+    }
+#undef R
+    const size_t i = x + (size_t)y * w;
+    const uint32_t d = br ? interp : native, b = br ? native : interp;
+    dark[i] = d;
+    bright[i] = b;
+    uint32_t f = 0;
+    if (P.use_fullres) {                                                     // hdr.c:1365-1378
+        if (br) f = ((int)b < P.white_darkened) ? b : max(b, d);
+        else f = d;
+    }
+    fullres[i] = f;
+}
+
+__device__ __forceinline__ double fullres_curve_at(int i, int black)         // hdr.c:904-909
+{
+    const double ev2 = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0));
+    const double c2 = -cos(fmax(fmin(ev2 - 4.0, 4.0), 0.0) * M_PI / 4.0);
+    return (c2 + 1.0) / 2.0;
+}
+
+// half-res blend (hdr.c:1562-1611) + overexposure flags (hdr.c:1627-1633) + alias-map skip mask
+__global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, uint32_t *__restrict__ halfres,
+                                uint16_t *__restrict__ over, uint8_t *__restrict__ skip, const PixParams P)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
+    if (i >= np) return;
+    const int b = (int)bright[i], d = (int)dark[i];
+    const double ev = log2(fmax((double)(b & 0xFFFFF) / 64.0 - (double)P.black / 64.0, 1.0)) + P.corr_ev;
+    const double c = -cos(fmax(fmin(ev - (P.max_ev - P.overlap), P.overlap), 0.0) * M_PI / P.overlap);
+    double k = (c + 1.0) / 2.0;
+    k = fmax(fmin(k, 1.0), 0.0);
+    const int mixed = (int)((double)__ldg(P.raw2ev + b) * (1.0 - k) + (double)__ldg(P.raw2ev + d) * k);
+    halfres[i] = (uint32_t)__ldg(P.ev2raw + mixed);
+    over[i] = (b >= P.white_darkened || d >= P.white) ? 100 : 0;
+    skip[i] = fullres_curve_at(b & 0xFFFFF, P.black) > FULLRES_THR;
+}
+
+// alias map, pass 1 (hdr.c:1397-1415)
+__global__ void diso_alias1_kernel(const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint8_t *__restrict__ skip,
+                                   uint16_t *__restrict__ amap, uint16_t *__restrict__ aux, const PixParams P)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
+    if (i >= np) return;
+    uint16_t v = 0;
+    if (!skip[i]) {
+        const int f = (int)frs[i], hh = (int)hrs[i];
+        const int e_lin = max(abs(f - hh) - DARK_NOISE * 3 / 2, 0), e_log = abs(__ldg(P.raw2ev + f) - __ldg(P.raw2ev + hh));
+        v = (uint16_t)min(min(e_lin / 2, e_log / 16), 65530);
+    }
+    amap[i] = v;
+    aux[i] = v;
+}
+
+// pass 2: 6th largest of the 37-point ring (hdr.c:1420-1440); writes aux
+__global__ void diso_alias2_kernel(const uint16_t *__restrict__ amap, const uint8_t *__restrict__ skip, uint16_t *__restrict__ aux, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < 6 || x >= w - 6 || y < 6 || y >= h - 6) return;
+    const size_t i = x + (size_t)y * w;
+    if (skip[i]) return;
+    int top[6] = {-1, -1, -1, -1, -1, -1};                               // six largest, descending
+    auto push = [&](int v) {
+        if (v <= top[5]) return;
+        top[5] = v;
+#pragma unroll
+        for (int k = 5; k > 0; k--) if (top[k] > top[k - 1]) { int t = top[k]; top[k] = top[k - 1]; top[k - 1] = t; }
+    };
+#pragma unroll
+    for (int dy = -6; dy <= 6; dy += 2) {
+        const int reach = (dy == -6 || dy == 6) ? 2 : ((dy == -4 || dy == 4) ? 4 : 6);
+        for (int dx = -reach; dx <= reach; dx += 2) push((int)amap[(x + dx) + (size_t)(y + dy) * w]);
+    }
+    aux[i] = (uint16_t)top[5];
+}
+
+// pass 3: the 13-tap "gaussian" with its duplicated terms (hdr.c:1443-1464); writes amap with uint16 wrap
+__global__ void diso_alias3_kernel(const uint16_t *__restrict__ aux, const uint8_t *__restrict__ skip, uint16_t *__restrict__ amap, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < 6 || x >= w - 6 || y < 6 || y >= h - 6) return;
+    const size_t i = x + (size_t)y * w;
+    if (skip[i]) return;
+#define A(dx, dy) ((int)aux[(x + (dx)) + (size_t)(y + (dy)) * w])
+    const int cross = A(0, -2) + A(-2, 0) + A(2, 0) + A(0, 2), diag = A(-2, -2) + A(2, -2) + A(-2, 2) + A(2, 2);
+    const int far4 = A(0, -6) + A(-6, 0) + A(6, 0) + A(0, 6);
+    const int knight = A(-2, -6) + A(2, -6) + A(-6, -2) + A(6, -2) + A(-6, 2) + A(6, 2) + A(-2, 6) + A(2, 6);
+    const int c = A(0, 0) + cross * 820 / 1024 + diag * 657 / 1024 + cross * 421 / 1024 + (2 * diag) * 337 / 1024 + diag * 173 / 1024 +
+                  far4 * 139 / 1024 + knight * 111 / 1024 + knight * 57 / 1024;
+#undef A
+    amap[i] = (uint16_t)c;
+}
+
+// pass 4: 2x2 max, clamp (hdr.c:1466-1483)
+__global__ void diso_alias4_kernel(uint16_t *__restrict__ amap, int w, int h)
+{
+    const int x = 2 + 2 * (blockIdx.x * blockDim.x + threadIdx.x), y = 2 + 2 * blockIdx.y;
+    if (x >= w - 2 || y >= h - 2) return;
+    uint16_t *p = amap + x + (size_t)y * w;
+    const int c = min(max(max((int)p[0], (int)p[1]), max((int)p[w], (int)p[w + 1])), ALIAS_MAP_MAX);
+    p[0] = p[1] = p[w] = p[w + 1] = (uint16_t)c;
+}
+
+// 3x3 "blur" of the overexposure flags (hdr.c:1636-1655): in -> out
+__global__ void diso_over_blur_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t i = x + (size_t)y * w;
+    int v = in[i];
+    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+#define O(dx, dy) ((int)in[(x + (dx)) + (size_t)(y + (dy)) * w])
+        v = O(0, 0) + (O(0, -1) + O(-1, 0) + O(1, 0) + O(0, 1)) * 820 / 1024 + (O(-1, -1) + O(1, -1) + O(-1, 1) + O(1, 1)) * 657 / 1024;
+#undef O
+    }
+    out[i] = (uint16_t)v;
+}
+
+// final_blend (hdr.c:1691-1752) + convert_20_to_16bit (hdr.c:1760-1772)
+__global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, const uint32_t *__restrict__ fullres,
+                                  const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint16_t *__restrict__ over,
+                                  const uint16_t *__restrict__ amap, uint16_t *__restrict__ out16, const PixParams P)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
+    if (i >= np) return;
+    const int b = (int)bright[i];
+    const int hrev = __ldg(P.raw2ev + hrs[i]), frev = __ldg(P.raw2ev + fullres[i]), frsev = __ldg(P.raw2ev + frs[i]);
+    double f = fullres_curve_at(b & 0xFFFFF, P.black), c = 0.0;
+    if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
+    const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
+    c = fmax(c, ovf);
+    const double noo = fmax(ovf, 1.0 - f);
+    f = fmax(f, c);
+    const double fev = noo * (double)frsev + (1.0 - noo) * (double)frev;
+    const int sig = (int)((dark[i] + bright[i]) / 2);
+    f = fmax(0.0, fmin(f, (double)(sig - P.black) / (double)(4 * DARK_NOISE)));
+    int o = (int)((double)hrev * (1.0 - f) + fev * f);
+    o = min(max(o, -10 * EVR), 14 * EVR - 1);
+    const uint32_t v20 = (uint32_t)__ldg(P.ev2raw + o);
+    out16[i] = (uint16_t)min(max((int)((double)v20 / 16.0 + 0.5), 0), 0xFFFF);
+}
+
+// ------------------------------------------------------------------ host: tables and scalar epilogues
+
+// hdr.c:839-874, built with the host libm so every entry equals the reference's
+void build_luts20(int black, int white, std::vector<int> &raw2ev, std::vector<int> &ev2raw_0)
+{
+    raw2ev.resize(N20);
+    ev2raw_0.assign(24 * EVR, 0);
+    int *ev2raw = ev2raw_0.data() + 10 * EVR;
+    for (int i = 0; i < N20; i++) {
+        const double signal = std::max(i / 64.0 - black / 64.0, -1023.0);
+        raw2ev[i] = signal > 0 ? (int)round(log2(1 + signal) * EVR) : -(int)round(log2(1 - signal) * EVR);
+    }
+    for (int i = -10 * EVR; i < 0; i++)
+        ev2raw[i] = (int)std::max(std::min(black + 64 - round(64 * pow(2, ((double)-i / EVR))), (double)black), 0.0);
+    for (int i = 0; i < 14 * EVR; i++) {
+        ev2raw[i] = (int)std::max(std::min(black - 64 + round(64 * pow(2, ((double)i / EVR))), (double)(N20 - 1)), (double)black);
+        if (i >= raw2ev[white]) ev2raw[i] = std::max(ev2raw[i], white);
+    }
+    ev2raw[raw2ev[0]] = 0;
+}
+
+// smallest r with prefix[r] >= ref, prefix[r] = sum of hist[0..r)
+int cursor_at(const std::vector<long long> &prefix, long long ref)
+{
+    return (int)(std::lower_bound(prefix.begin(), prefix.end(), ref) - prefix.begin());
+}
+
+// identify_bright_and_dark_fields (hdr.c:497-636) from the four green histograms, closed form of the walk
+bool fields_from_hist(const unsigned hist[4][16384], int black, int is_bright[4])
+{
+    const int white = 10000;
+    std::vector<long long> pre[4];
+    for (int i = 0; i < 4; i++) {
+        pre[i].resize(16385);
+        pre[i][0] = 0;
+        for (int r = 0; r < 16384; r++) pre[i][r + 1] = pre[i][r] + hist[i][r];
+    }
+    const long long total = pre[0][16384];
+    const int ref_max = (int)(total * 0.998), ref_off = (int)(total * 0.05);
+    int raw[4] = {0, 0, 0, 0}, off[4] = {0, 0, 0, 0};
+    if (ref_max > 0) {
+        long long ref_break = ref_max;                       // first ref at which some cursor reaches `white`
+        for (int i = 0; i < 4; i++) ref_break = std::min(ref_break, pre[i][white - 1] + 1);   // cursor >= white <=> prefix[white-1] < ref
+        const long long ref_final = std::min<long long>(ref_break, ref_max - 1);
+        for (int i = 0; i < 4; i++) raw[i] = cursor_at(pre[i], ref_final);
+        const int T = black + (white - black) / 4;
+        if (T > 0) {
+            long long ref_o = std::min<long long>(ref_off - 1, ref_final);
+            for (int i = 0; i < 4; i++) ref_o = std::min(ref_o, pre[i][std::min(T - 1, 16384)]);   // cursor < T  <=>  prefix[T-1] >= ref
+            if (ref_o >= 0)
+                for (int i = 0; i < 4; i++) off[i] = cursor_at(pre[i], ref_o);
+        }
+    }
+    int s[4];
+    for (int i = 0; i < 4; i++) { raw[i] -= off[i]; s[i] = raw[i]; }
+    std::sort(s, s + 4);
+    const double median_bright = (s[1] + s[2]) / 2;
+    for (int i = 0; i < 4; i++) is_bright[i] = raw[i] > median_bright;
+    if (is_bright[0] + is_bright[1] + is_bright[2] + is_bright[3] != 2) return false;
+    if (is_bright[0] == is_bright[2] || is_bright[1] == is_bright[3]) return false;
+    return true;
+}
+
+// k-th smallest (0-based) of the multiset described by hist (value = bin - bias)
+int kth_from_hist(const unsigned *hist, int nbins, long long k, int bias)
+{
+    long long acc = 0;
+    for (int i = 0; i < nbins; i++) {
+        acc += hist[i];
+        if (acc > k) return i - bias;
+    }
+    return 0;
+}
+
+struct DisoScratch {        // carved out of the slot's aux buffer
+    StatsA *statsA;
+    unsigned *hist_white;   // [2][65536]
+    unsigned *hist_expo;    // [2][HB]
+    int2 *pairs, *sel;
+    unsigned *nsel, *scores;
+    uint32_t *raw32, *dark, *bright, *fullres, *halfres, *frs, *hrs;
+    uint16_t *over, *over2, *amap, *aux;
+    uint8_t *skip;
+};
+
+constexpr int HB = 65536 + 8;
+
+size_t carve(uint8_t *base, size_t npix, size_t ngrid, DisoScratch *S)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { void *p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return p; };
+    DisoScratch s;
+    s.statsA = (StatsA *)take(sizeof(StatsA));
+    s.hist_white = (unsigned *)take(2 * 65536 * sizeof(unsigned));
+    s.hist_expo = (unsigned *)take(2 * HB * sizeof(unsigned));
+    s.pairs = (int2 *)take(ngrid * sizeof(int2));
+    s.sel = (int2 *)take(ngrid * sizeof(int2));
+    s.nsel = (unsigned *)take(256);
+    s.scores = (unsigned *)take(4096 * sizeof(unsigned));
+    s.raw32 = (uint32_t *)take(npix * 4); s.dark = (uint32_t *)take(npix * 4); s.bright = (uint32_t *)take(npix * 4);
+    s.fullres = (uint32_t *)take(npix * 4); s.halfres = (uint32_t *)take(npix * 4);
+    s.frs = (uint32_t *)take(npix * 4); s.hrs = (uint32_t *)take(npix * 4);
+    s.over = (uint16_t *)take(npix * 2); s.over2 = (uint16_t *)take(npix * 2);
+    s.amap = (uint16_t *)take(npix * 2); s.aux = (uint16_t *)take(npix * 2);
+    s.skip = (uint8_t *)take(npix);
+    if (S) *S = s;
+    return o;
+}
+
+}  // namespace
+
+size_t dual_iso_scratch_bytes(int w, int h)
+{
+    const size_t ngrid = (size_t)((w + 2) / 3 + 1) * ((h + 2) / 3 + 1);
+    return carve(nullptr, (size_t)w * h, ngrid, nullptr);
+}
+
+// Per-context dual-ISO tables: the 20-bit EV LUTs keyed by black like the reference's statics (built
+// from the first converted frame's white level, hdr.c:1089-1093), the fp64 log table of hdr_check and
+// the 3000 candidate slopes of match_exposures.
+struct DualIsoTables {
+    std::mutex mu;
+    int lut_black = -1;
+    int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
+    double *d_raw2evf = nullptr;        // 16384 + MAX_BLACK doubles
+    double *d_test_a = nullptr;
+    std::vector<double> test_a;
+};
+
+static DualIsoTables *tables_of(mlvb_context *ctx)
+{
+    static std::mutex g_mu;
+    static std::map<mlvb_context *, DualIsoTables *> g_tabs;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_tabs.find(ctx);
+    if (it != g_tabs.end()) return it->second;
+    DualIsoTables *t = new DualIsoTables();
+    g_tabs[ctx] = t;
+    return t;
+}
+
+void dual_iso_reset_tables(mlvb_context *ctx)
+{
+    DualIsoTables *t = tables_of(ctx);
+    std::lock_guard<std::mutex> lk(t->mu);
+    t->lut_black = -1;
+}
+
+// hdr_interpolate on a device-resident 14-bit frame (in place -> 16-bit).  Returns 1 converted,
+// 0 not dual ISO / failed (frame keeps its 14-bit content), < 0 MLVB_ERR_*.
+int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int black14, int interp_method, int use_fullres,
+                        int use_alias_map, int cs_method, void *d_aux, cudaStream_t st)
+{
+    if (w <= 0 || h <= 0) return 0;
+    if (interp_method == 0) {
+        fprintf(stderr, "libmlvfs_b200: dual ISO --amaze-edge is not implemented yet (use --mean23)\n");
+        return MLVB_ERR_UNSUPPORTED;
+    }
+    if (w < 16 || h < 16 || (w & 1)) return MLVB_ERR_UNSUPPORTED;
+    DualIsoTables *T = tables_of(ctx);
+    {
+        std::lock_guard<std::mutex> lk(T->mu);
+        if (!T->d_raw2evf) {
+            const size_t n = 16384 + MLVB_MAX_BLACK;
+            MLVB_CUDA_OK(cudaMalloc(&T->d_raw2evf, n * sizeof(double)));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_raw2evf, host_raw2evf_base(), n * sizeof(double), cudaMemcpyHostToDevice));
+            for (double ev = 0; ev < 6; ev += 0.002) T->test_a.push_back(pow(2, -ev));          // hdr.c:753-755
+            MLVB_CUDA_OK(cudaMalloc(&T->d_test_a, T->test_a.size() * sizeof(double)));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_test_a, T->test_a.data(), T->test_a.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    if (black14 > MLVB_MAX_BLACK) return 0;
+
+    const size_t npix_full = (size_t)w * h;
+    DisoScratch D;
+    carve((uint8_t *)d_aux, npix_full, (size_t)((w + 2) / 3 + 1) * ((h + 2) / 3 + 1), &D);
+
+    // ---------------- phase A
+    MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
+    diso_stats_a_kernel<<<dim3(ceil_div(w, 256), h), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
+    ctx->launches += 1;
+    std::vector<uint8_t> hostA(sizeof(StatsA));
+    MLVB_CUDA_OK(cudaMemcpyAsync(hostA.data(), D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    const StatsA *A = (const StatsA *)hostA.data();
+
+    // identify_rggb_or_gbrg (hdr.c:467-494)
+    double d_rggb = 0, d_gbrg = 0;
+    {
+        long long acc[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 16384; i++) {
+            for (int k = 0; k < 4; k++) acc[k] += A->hist_cfa[k][i];
+            d_rggb += (double)llabs(acc[1] - acc[2]);
+            d_gbrg += (double)llabs(acc[0] - acc[3]);
+        }
+    }
+    const int rggb = d_rggb < d_gbrg;
+    FieldInfo F;
+    F.y1 = rggb ? 0 : 1;
+    if (!rggb) { d_img += w; h--; }                                   // hdr.c:1784-1791
+    if (!fields_from_hist(A->hist_field[rggb ? 0 : 1], black14, F.is_bright)) return 0;
+
+    const int black = black14 * 64;
+    // ---------------- phase B: white levels
+    const int max_pix = w * h / 2 / 9;
+    unsigned n_class[2] = {0, 0};
+    const int nx = (w + 2) / 3;
+    for (int y = F.y1; y < h; y += 3) n_class[F.is_bright[y % 4]] += nx;
+    MLVB_CUDA_OK(cudaMemsetAsync(D.hist_white, 0, 2 * 65536 * sizeof(unsigned), st));
+    const int ny_w = (h - F.y1 + 2) / 3;
+    if (ny_w > 0) diso_white_kernel<<<dim3(ceil_div(nx, 128), ny_w), 128, 0, st>>>(d_img, w, h, F, max_pix, n_class[0], n_class[1], D.hist_white);
+    ctx->launches += 1;
+    std::vector<unsigned> hw(2 * 65536);
+    MLVB_CUDA_OK(cudaMemcpyAsync(hw.data(), D.hist_white, hw.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    int whites[2];
+    for (int c = 0; c < 2; c++) {
+        const long long kept = std::min<long long>(n_class[c], std::max(max_pix, 0));
+        const int k = c ? 50 : 10, margin = c ? 1500 : 100;
+        int kth_largest = 0;                                           // kth_smallest_int of the negated values (hdr.c:286-287)
+        if (kept > 0) {
+            long long acc = 0;
+            for (int v = 65535; v >= 0; v--) { acc += hw[c * 65536 + v]; if (acc > k) { kth_largest = v; break; } }
+        }
+        whites[c] = kth_largest - margin;
+    }
+    const int white = std::min(std::max(whites[0], 10000), 16383) * 64;
+    const int white_bright = std::min(std::max(whites[1], 5000), 16383) * 64;
+
+    // ---------------- phase C: exposure matching (hdr.c:638-823)
+    int white_darkened = white_bright;
+    const int white20 = std::min(white, white_darkened);
+    ExpoParams E;
+    E.black16 = black / 16;
+    const int white16 = white20 / 16;
+    E.clip0 = white16 - E.black16;
+    E.clip = (int)(E.clip0 * 0.95);
+    E.y0 = F.y1 + 2;
+    const int ny_e = (h - 2 - E.y0 + 2) / 3;
+    const unsigned ngrid = (unsigned)std::max(ny_e, 0) * nx;
+    MLVB_CUDA_OK(cudaMemsetAsync(D.hist_expo, 0, 2 * HB * sizeof(unsigned), st));
+    if (ngrid) diso_expo_pairs_kernel<<<dim3(ceil_div(nx, 128), ny_e), 128, 0, st>>>(d_img, w, h, F, E, D.pairs, D.hist_expo, HB);
+    ctx->launches += 1;
+    std::vector<unsigned> he(2 * HB);
+    MLVB_CUDA_OK(cudaMemcpyAsync(he.data(), D.hist_expo, he.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    long long n = 0;
+    for (int i = 0; i < HB; i++) n += he[i];
+    auto med_idx = [](long long m) { return (m & 1) ? m / 2 : m / 2 - 1; };
+    int bmed = 0, b_lo = 0, b_hi = 0, dmed = 0;
+    if (n > 0) {
+        bmed = kth_from_hist(he.data(), HB, med_idx(n), E.black16);
+        b_lo = kth_from_hist(he.data(), HB, n * 98 / 100, E.black16);
+        b_hi = kth_from_hist(he.data(), HB, (long long)(int)(n * 99.9 / 100), E.black16);
+        dmed = kth_from_hist(he.data() + HB, HB, med_idx(n), E.black16);
+    }
+    const int nmax = (w + 2) * (h + 2) / 9;
+    const unsigned hi_cap = (unsigned)std::max(nmax / 50, 0);
+    MLVB_CUDA_OK(cudaMemsetAsync(D.nsel, 0, sizeof(unsigned), st));
+    const unsigned ncand = (unsigned)T->test_a.size();
+    if (ngrid) diso_highlights_kernel<<<ceil_div(ngrid, 256), 256, 0, st>>>(D.pairs, ngrid, b_lo, b_hi, D.sel, D.nsel, ngrid);
+    diso_score_kernel<<<ncand, 256, 0, st>>>(D.sel, D.nsel, ngrid, T->d_test_a, dmed, bmed, D.scores);
+    ctx->launches += 2;
+    std::vector<unsigned> scores(ncand);
+    unsigned nsel = 0;
+    MLVB_CUDA_OK(cudaMemcpyAsync(scores.data(), D.scores, ncand * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(&nsel, D.nsel, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    if (nsel >= hi_cap && hi_cap > 0) {
+        // the reference truncates its highlight list in raster order here (hdr.c:727-745); not reproduced
+        fprintf(stderr, "libmlvfs_b200: dual ISO: highlight sample cap reached (%u >= %u), frame not converted\n", nsel, hi_cap);
+        return MLVB_ERR_UNSUPPORTED;
+    }
+    double a = 0, b = 0;
+    unsigned best = 0;
+    for (unsigned c = 0; c < ncand; c++)
+        if (scores[c] > best) { best = scores[c]; a = T->test_a[c]; b = dmed - bmed * a; }
+
+    PixParams P;
+    memset(&P, 0, sizeof(P));
+    P.w = w; P.h = h;
+    memcpy(P.is_bright, F.is_bright, sizeof(P.is_bright));
+    P.black = black; P.white = white;
+    P.a = a; P.b20 = b * 16;
+    white_darkened = (int)((white20 - black + P.b20) * a + black);
+    P.white_darkened = white_darkened;
+    const double factor = 1 / a;
+    if (factor < 1.2 || !std::isfinite(factor)) return 0;               // "Doesn't look like interlaced ISO"
+    P.corr_ev = log2(factor);
+    const double lowiso_dr = log2(white - black) - DARK_NOISE_EV;
+    double overlap = lowiso_dr - P.corr_ev;
+    overlap -= std::min(3.0, overlap - 3);
+    if (overlap < 0.5) return 0;                                         // "Overlap error"
+    P.overlap = overlap;
+    P.max_ev = log2(white / 64 - black / 64);
+    P.use_fullres = use_fullres; P.use_alias = use_alias_map;
+
+    // 20-bit EV tables, rebuilt only when black changes (with this frame's white), hdr.c:1089-1093
+    {
+        std::lock_guard<std::mutex> lk(T->mu);
+        if (T->lut_black != black) {
+            std::vector<int> r2e, e2r;
+            build_luts20(black, white, r2e, e2r);
+            if (!T->d_raw2ev) MLVB_CUDA_OK(cudaMalloc(&T->d_raw2ev, N20 * sizeof(int)));
+            if (!T->d_ev2raw_0) MLVB_CUDA_OK(cudaMalloc(&T->d_ev2raw_0, 24 * EVR * sizeof(int)));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_raw2ev, r2e.data(), N20 * sizeof(int), cudaMemcpyHostToDevice));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
+            T->lut_black = black;
+        }
+        P.raw2ev = T->d_raw2ev;
+        P.ev2raw = T->d_ev2raw_0 + 10 * EVR;
+    }
+
+    // ---------------- phase D: per-pixel pipeline
+    const size_t np = (size_t)w * h;
+    const dim3 g2(ceil_div(w, 256), h);
+    const int g1 = ceil_div(np, 256);
+    diso_to20_kernel<<<g2, 256, 0, st>>>(d_img, D.raw32, P);
+    diso_interp_kernel<<<g2, 256, 0, st>>>(D.raw32, D.dark, D.bright, D.fullres, P);
+    diso_mix_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
+    ctx->launches += 3;
+    const uint32_t *frs = D.fullres, *hrs = D.halfres;
+    if (cs_method == 2 || cs_method == 3 || cs_method == 5) {
+        int rc;
+        if (use_fullres) {
+            rc = launch_chroma_smooth_u32(D.fullres, D.frs, w, h, cs_method, P.raw2ev, P.ev2raw, st);
+            if (rc) return rc;
+            frs = D.frs;
+            ctx->launches += 1;
+        }
+        rc = launch_chroma_smooth_u32(D.halfres, D.hrs, w, h, cs_method, P.raw2ev, P.ev2raw, st);
+        if (rc) return rc;
+        hrs = D.hrs;
+        ctx->launches += 1;
+    } else if (cs_method) {
+        fprintf(stderr, "Unsupported chroma smooth method\n");          // hdr.c:1519
+    }
+    if (use_alias_map) {
+        diso_alias1_kernel<<<g1, 256, 0, st>>>(frs, hrs, D.skip, D.amap, D.aux, P);
+        diso_alias2_kernel<<<g2, 256, 0, st>>>(D.amap, D.skip, D.aux, w, h);
+        diso_alias3_kernel<<<g2, 256, 0, st>>>(D.aux, D.skip, D.amap, w, h);
+        diso_alias4_kernel<<<dim3(ceil_div(w / 2, 128), std::max((h - 2) / 2, 1)), 128, 0, st>>>(D.amap, w, h);
+        ctx->launches += 4;
+    }
+    diso_over_blur_kernel<<<g2, 256, 0, st>>>(D.over, D.over2, w, h);
+    diso_final_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
+    ctx->launches += 2;
+    MLVB_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+// cr2hdr20_convert_data (hdr.c:1932-1957) on a device frame: hdr_check, focus / bad pixels with the
+// horizontal interpolator, hdr_interpolate.  Returns like run_hdr_interpolate.
+int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, int interp_method,
+                 int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st)
+{
+    if (g.black > MLVB_MAX_BLACK) return 0;
+    if (interp_method == 0) {
+        fprintf(stderr, "libmlvfs_b200: dual ISO --amaze-edge is not implemented yet (use --mean23)\n");
+        return MLVB_ERR_UNSUPPORTED;
+    }
+    DualIsoTables *T = tables_of(ctx);
+    (void)T;
+    // hdr_check needs the statistics of the untouched frame: run phase A's reduction once here
+    DisoScratch D;
+    carve((uint8_t *)d_aux, g.npix, (size_t)((g.w + 2) / 3 + 1) * ((g.h + 2) / 3 + 1), &D);
+    {
+        std::lock_guard<std::mutex> lk(T->mu);
+        if (!T->d_raw2evf) {
+            const size_t n = 16384 + MLVB_MAX_BLACK;
+            MLVB_CUDA_OK(cudaMalloc(&T->d_raw2evf, n * sizeof(double)));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_raw2evf, host_raw2evf_base(), n * sizeof(double), cudaMemcpyHostToDevice));
+            for (double ev = 0; ev < 6; ev += 0.002) T->test_a.push_back(pow(2, -ev));
+            MLVB_CUDA_OK(cudaMalloc(&T->d_test_a, T->test_a.size() * sizeof(double)));
+            MLVB_CUDA_OK(cudaMemcpy(T->d_test_a, T->test_a.data(), T->test_a.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
+    diso_stats_a_kernel<<<dim3(ceil_div(g.w, 256), g.h), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
+                                                                      T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA);
+    ctx->launches += 1;
+    double ev_sum = 0;
+    unsigned long long ev_num = 0;
+    MLVB_CUDA_OK(cudaMemcpyAsync(&ev_sum, &D.statsA->ev_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(&ev_num, &D.statsA->ev_num, sizeof(ev_num), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    const double avg_ev = ev_sum / (double)ev_num;                        // 0/0 -> NaN -> "not HDR" (hdr.c:435-438)
+    if (!(avg_ev > 0.5)) return 0;
+
+    // fix_focus_pixels(.., 1) and fix_bad_pixels(.., 1): horizontal interpolation only (hdr.c:1944-1948)
+    int rc;
+    std::shared_ptr<PixelList> focus, bad;
+    {
+        std::lock_guard<std::mutex> lk(ctx->clip_mu);
+        rc = get_focus_pixel_map(ctx, hdr, &focus);
+        if (rc) return rc;
+    }
+    if (focus && focus->nlevels) {
+        rc = launch_pixel_fix(d_img, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, 1, 1, focus->d_by_level, focus->d_level_start,
+                              focus->level_start.data(), focus->nlevels, ctx->luts, st);
+        if (rc) return rc;
+        ctx->launches += 1 + (focus->nlevels > 1);
+    }
+    if (fix_bad_pixels_mode) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->clip_mu);
+            rc = get_bad_pixel_map(ctx, hdr, g, fix_bad_pixels_mode == 2, d_img, st, &bad);
+            if (rc) return rc;
+        }
+        if (bad && bad->nlevels) {
+            rc = launch_pixel_fix(d_img, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, 1, 0, bad->d_by_level, bad->d_level_start,
+                                  bad->level_start.data(), bad->nlevels, ctx->luts, st);
+            if (rc) return rc;
+            ctx->launches += 1 + (bad->nlevels > 1);
+        }
+    }
+    return run_hdr_interpolate(ctx, d_img, g.w, g.h, g.black, interp_method, use_fullres, use_alias_map, cs_method, d_aux, st);
+}
 
 extern "C" {
 
@@ -16,10 +792,29 @@ int hdr_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, 
 int cr2hdr20_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, int interp_method, int fullres,
                           int use_alias_map, int chroma_smooth, int fix_bad_pixels_mode)
 {
-    (void)frame_headers; (void)image_data; (void)interp_method; (void)fullres; (void)use_alias_map;
-    (void)chroma_smooth; (void)fix_bad_pixels_mode;
-    fprintf(stderr, "libmlvfs_b200: cr2hdr20_convert_data (dual ISO, hdr.c:1932-1957) is not implemented yet\n");
-    return 0;
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: cr2hdr20_convert_data: no CUDA context (no CPU path)\n"); return 0; }
+    const FrameGeom g = geom_from_headers(frame_headers);
+    Slot *s = acquire_slot(ctx);
+    cudaSetDevice(ctx->device);
+    int ret = 0;
+    if (slot_reserve(*s, 16, g.npix * 2) == MLVB_OK &&
+        reserve_device(&s->d_aux, &s->aux_cap, dual_iso_scratch_bytes(g.w, g.h)) == MLVB_OK &&
+        cudaMemcpyAsync(s->d_a, image_data, g.npix * 2, cudaMemcpyHostToDevice, s->stream) == cudaSuccess) {
+        const int rc = run_cr2hdr20(ctx, frame_headers, g, s->d_a, interp_method, fullres, use_alias_map, chroma_smooth,
+                                    fix_bad_pixels_mode, s->d_aux, s->stream);
+        // the frame is copied back in both cases: a failed conversion still carries the focus / bad-pixel fixes
+        if (rc >= 0 && cudaMemcpyAsync(image_data, s->d_a, g.npix * 2, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+            cudaStreamSynchronize(s->stream) == cudaSuccess && rc == 1) {
+            frame_headers->rawi_hdr.raw_info.black_level *= 4;          // hdr.c:1951-1952
+            frame_headers->rawi_hdr.raw_info.white_level *= 4;
+            ret = 1;
+        } else {
+            cudaStreamSynchronize(s->stream);
+        }
+    }
+    release_slot(ctx, s);
+    return ret;
 }
 
 }  // extern "C"

@@ -66,6 +66,23 @@ long orc_lj92_encode(const uint16_t *img, int w, int h, int depth, uint8_t *out,
 /* ---- pattern noise (patternnoise.c:47-380) ---- */
 void orc_fix_pattern_noise(int16_t *raw, int w, int h, int white);
 
+/* ---- dual ISO (hdr.c:250-1957) ---- */
+typedef struct {                 /* the reference's function-static LUT state */
+    int *raw2ev, *ev2raw_0;      /* 20-bit tables (hdr.c:839-874) */
+    int lut_black, lut_white;
+    double *fullres_curve;       /* hdr.c:890-913 */
+    int curve_black;
+} orc_diso_state;
+typedef struct {                 /* intermediate results, for stage-level parity checks */
+    int rggb, is_bright[4], white_dark, white_bright, white_darkened;
+    double a, b, corr_ev, overlap;
+} orc_diso_info;
+void orc_diso_state_init(orc_diso_state *S);
+void orc_diso_state_free(orc_diso_state *S);
+int  orc_hdr_check(const uint16_t *img, int w, int h, int black, int white);
+int  orc_hdr_interpolate(uint16_t *image, int w, int h, int black14, int interp_method, int use_fullres,
+                         int use_alias_map, int cs_method, orc_diso_state *S, orc_diso_info *info);
+
 /* ---- whole single-ISO chain in process_frame order (main.c:942-997) ---- */
 typedef struct {
     int chroma_smooth;      /* 0,2,3,5 */

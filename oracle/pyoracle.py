@@ -263,3 +263,54 @@ def fix_pattern_noise(img, white):
     h, w = out.shape
     lib.orc_fix_pattern_noise(_p(out), w, h, int(white))
     return out
+
+
+# ---- dual ISO (oracle/orc_dualiso.c) -------------------------------------------------------------
+
+class DisoState(C.Structure):
+    _fields_ = [("raw2ev", C.c_void_p), ("ev2raw_0", C.c_void_p), ("lut_black", C.c_int), ("lut_white", C.c_int),
+                ("fullres_curve", C.c_void_p), ("curve_black", C.c_int)]
+
+
+class DisoInfo(C.Structure):
+    _fields_ = [("rggb", C.c_int), ("is_bright", C.c_int * 4), ("white_dark", C.c_int), ("white_bright", C.c_int),
+                ("white_darkened", C.c_int), ("a", C.c_double), ("b", C.c_double), ("corr_ev", C.c_double),
+                ("overlap", C.c_double)]
+
+
+def new_diso_state():
+    st = DisoState()
+    load_oracle().orc_diso_state_init(C.byref(st))
+    return st
+
+
+def cr2hdr20(img, black, white, *, interp_method=1, fullres=1, use_alias_map=1, chroma_smooth_method=0,
+             fix_bad_pixels_mode=0, state=None, badpix_state=None, focus_map=None, crop=(0, 0)):
+    """cr2hdr20_convert_data (hdr.c:1932-1957) on an unpacked frame.
+
+    Returns (converted, out_frame, info); on converted == 1 the caller's black/white are x4.
+    `badpix_state` is a dict holding the clip's bad-pixel list (detected on first use, cs.c:233-312).
+    """
+    lib = load_oracle()
+    lib.orc_hdr_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+    lib.orc_hdr_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    info = DisoInfo()
+    if state is None:
+        state = new_diso_state()
+    if not lib.orc_hdr_check(_p(out), w, h, black, white):
+        return 0, out, info
+    if focus_map is not None and len(focus_map):
+        out = focuspix_apply(out, black, focus_map, crop=crop, dual_iso=1)
+    if fix_bad_pixels_mode:
+        badpix_state = badpix_state if badpix_state is not None else {}
+        if "list" not in badpix_state:
+            badpix_state["list"] = badpix_detect(out, black, fix_bad_pixels_mode == 2, crop=crop)
+        out = badpix_apply(out, black, badpix_state["list"], crop=crop, dual_iso=1)
+    rc = lib.orc_hdr_interpolate(_p(out), w, h, black, interp_method, fullres, use_alias_map, chroma_smooth_method,
+                                 C.byref(state), C.byref(info))
+    if rc < 0:
+        raise NotImplementedError("oracle: this dual-ISO interpolation method is not restated yet")
+    return rc, out, info

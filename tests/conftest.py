@@ -57,4 +57,6 @@ def fresh_ctx(gpu_ctx):
     import mlvfs_b200
     mlvfs_b200.lib().free_focus_pixel_maps()
     mlvfs_b200.lib().stripes_free_corrections()
+    # the drop-in symbols run on the process-wide default context: clear its per-clip / dual-ISO state too
+    mlvfs_b200.Context.default().reset_clip_state()
     return gpu_ctx

@@ -1,0 +1,89 @@
+"""GPU parity: full dual-ISO conversion (--dual-iso --mean23), BASELINE config 3 options.
+
+Statistics (row fields, white levels, exposure match) are integer-exact; the per-pixel blends are fp64
+with CUDA's log2/cos, so the frame is a tolerance stage: <= 1 DN on the 16-bit output (PSNR reported)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mlvfs_b200 as M
+from mlvfs_b200 import mlvformat as F, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_DN = 1     # north_star tolerance for the floating-point dual-ISO stages
+
+
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return float("inf") if mse == 0 else 10 * np.log10(65535.0 ** 2 / mse)
+
+
+def _check(got, want, label):
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    print(f"{label}: max |diff| = {d.max()} DN, differing px = {np.count_nonzero(d)} / {d.size}, PSNR = {_psnr(got, want):.1f} dB")
+    assert d.max() <= TOL_DN, f"{label}: max diff {d.max()} DN at {np.unravel_index(d.argmax(), d.shape)}"
+
+
+@pytest.mark.parametrize("w,h,cs,alias,badpix,fullres", [
+    (640, 360, 0, 0, 0, 1), (640, 360, 5, 1, 0, 1), (640, 362, 3, 1, 2, 1), (1920, 1080, 5, 1, 0, 1), (384, 216, 3, 1, 0, 0)])
+def test_cr2hdr20_dropin_matches_oracle(fresh_ctx, oracle, w, h, cs, alias, badpix, fullres):
+    img = synth.make_frame(w, h, 0, dual_iso=True, hot_cold=True, bad_density=1e-4)
+    hdr = F.make_frame_headers(w, h, file_guid=0xA100 + cs * 64 + alias * 16 + badpix * 4 + fullres)
+    rc, want, info = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, fullres=fullres, use_alias_map=alias,
+                                     chroma_smooth_method=cs, fix_bad_pixels_mode=badpix)
+    assert rc == 1
+    got = img.copy()
+    L = M.lib()
+    L.cr2hdr20_convert_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    r = L.cr2hdr20_convert_data(C.byref(hdr), got.ctypes.data_as(C.c_void_p), 1, fullres, alias, cs, badpix)
+    assert r == 1
+    assert hdr.rawi_hdr.raw_info.black_level == 8192 and hdr.rawi_hdr.raw_info.white_level == 60000
+    _check(got, want, f"cr2hdr20 {w}x{h} cs{cs} alias{alias} badpix{badpix} fullres{fullres}")
+
+
+def test_dual_iso_row_phases_and_gbrg(fresh_ctx, oracle):
+    w, h = 480, 272
+    base = synth.make_frame(w, h + 3, 3, dual_iso=True)
+    L = M.lib()
+    L.cr2hdr20_convert_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    for k, img in enumerate([base[2:h + 2], base[1:h + 1], base[3:h + 3]]):
+        img = np.ascontiguousarray(img)
+        hdr = F.make_frame_headers(w, h, file_guid=0xA200 + k)
+        rc, want, info = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, chroma_smooth_method=3)
+        got = img.copy()
+        r = L.cr2hdr20_convert_data(C.byref(hdr), got.ctypes.data_as(C.c_void_p), 1, 1, 1, 3, 0)
+        assert r == rc, k
+        _check(got, want, f"phase/cfa case {k} (rggb={info.rggb}, pattern={list(info.is_bright)})")
+
+
+def test_plain_footage_is_not_converted(fresh_ctx, oracle):
+    """--dual-iso on ordinary footage: detection fails, frame keeps the horizontal bad-pixel repairs, then
+    process_frame repairs again in 2-D and skips chroma smoothing (main.c:956-978)."""
+    w, h = 640, 360
+    hdr = F.make_frame_headers(w, h, file_guid=0xA300)
+    ri = hdr.rawi_hdr.raw_info
+    img = synth.make_frame(w, h, 1, hot_cold=True, bad_density=1e-4)
+    rc, mid, _ = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, fix_bad_pixels_mode=1)
+    assert rc == 0
+    lst = oracle.badpix_detect(img, 2048, 0)           # the map was detected on the untouched frame
+    want = oracle.badpix_apply(mid, 2048, lst)
+    o = M.Options(dual_iso=2, hdr_interpolation_method=1, fix_bad_pixels=1, chroma_smooth=3)
+    out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(img), o, "plain.MLV")
+    assert res.is_dual_iso == 0 and res.black_level == 2048
+    assert np.array_equal(out, want)
+
+
+def test_dual_iso_through_process_frame(fresh_ctx, oracle):
+    """BASELINE config 3 options through the fused entry: --dual-iso --mean23 --cs5x5 (alias map on)."""
+    w, h = 960, 384
+    hdr = F.make_frame_headers(w, h, file_guid=0xA400)
+    o = M.Options(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5)
+    st = oracle.new_diso_state()
+    for i in range(2):
+        img = synth.make_frame(w, h, i, dual_iso=True)
+        rc, want, _ = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, chroma_smooth_method=5, state=st)
+        out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(img), o, "c3.MLV")
+        assert rc == 1 and res.is_dual_iso == 1 and res.black_level == 8192 and res.white_level == 60000
+        _check(out, want, f"process_frame dual ISO frame {i}")

@@ -206,3 +206,50 @@ def test_lj92_codec_matches_reference(oracle, ref):
     ref.lj92_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     assert ref.lj92_decode(hd, _p(out), w * h, 0, None, 0) == 0
     assert np.array_equal(out.reshape(h, w), tiled)
+
+
+def _ref_cr2hdr20(ref, oracle, hdr, img, interp, fullres, alias, cs, badpix):
+    ref.cr2hdr20_convert_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    out = img.copy()
+    with oracle.quiet_stdout():
+        r = ref.cr2hdr20_convert_data(C.byref(hdr), _p(out), interp, fullres, alias, cs, badpix)
+    return r, out
+
+
+@pytest.mark.parametrize("w,h,cs,alias,badpix,fullres", [
+    (640, 360, 0, 0, 0, 1), (640, 360, 5, 1, 0, 1), (640, 362, 3, 1, 2, 1), (320, 180, 2, 0, 1, 1), (384, 216, 3, 1, 0, 0)])
+def test_dual_iso_mean23_matches_reference(oracle, ref, w, h, cs, alias, badpix, fullres):
+    """cr2hdr20_convert_data with --mean23: statistics, exposure match, interpolation, alias map, blend."""
+    img = synth.make_frame(w, h, 0, dual_iso=True, hot_cold=True, bad_density=1e-4)
+    hdr = F.make_frame_headers(w, h, file_guid=0x9100 + cs * 64 + alias * 16 + badpix * 4 + fullres)
+    r, want = _ref_cr2hdr20(ref, oracle, hdr, img, 1, fullres, alias, cs, badpix)
+    rc, got, info = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, fullres=fullres, use_alias_map=alias,
+                                    chroma_smooth_method=cs, fix_bad_pixels_mode=badpix)
+    assert r == rc == 1
+    assert hdr.rawi_hdr.raw_info.black_level == 2048 * 4 and hdr.rawi_hdr.raw_info.white_level == 15000 * 4
+    assert list(info.is_bright) == [0, 0, 1, 1] and 2.9 < info.corr_ev < 3.1
+    assert np.array_equal(got, want)
+
+
+def test_dual_iso_other_row_phase_and_gbrg(oracle, ref):
+    """Bright rows at y%4 in {0,1} (pattern BBdd) and a GBRG frame (one row cropped, hdr.c:1784-1791)."""
+    w, h = 480, 272
+    base = synth.make_frame(w, h + 3, 3, dual_iso=True)
+    for k, img in enumerate([base[2:h + 2], base[1:h + 1], base[3:h + 3]]):
+        img = np.ascontiguousarray(img)
+        hdr = F.make_frame_headers(w, h, file_guid=0x9200 + k)
+        r, want = _ref_cr2hdr20(ref, oracle, hdr, img, 1, 1, 1, 3, 0)
+        rc, got, info = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, chroma_smooth_method=3)
+        assert r == rc, k
+        assert np.array_equal(got, want), k
+
+
+def test_dual_iso_rejects_plain_footage(oracle, ref):
+    w, h = 320, 180
+    img = synth.make_frame(w, h, 1, hot_cold=True, bad_density=1e-4)
+    hdr = F.make_frame_headers(w, h, file_guid=0x9300)
+    r, want = _ref_cr2hdr20(ref, oracle, hdr, img, 1, 1, 1, 0, 1)
+    rc, got, _ = oracle.cr2hdr20(img, 2048, 15000, interp_method=1, fix_bad_pixels_mode=1)
+    assert r == rc == 0
+    assert hdr.rawi_hdr.raw_info.black_level == 2048
+    assert np.array_equal(got, want)          # still carries the horizontal bad-pixel repairs (hdr.c:1944-1948)
