@@ -62,6 +62,8 @@ size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts)
     size_t need = 0;
     if (opts.fix_pattern_noise) need = std::max(need, pattern_noise_scratch_bytes(g.w, g.h));
     if (opts.dual_iso == 2) need = std::max(need, dual_iso_scratch_bytes(g.w, g.h));
+    if (opts.dual_iso == 1) need = std::max(need, hdr_preview_scratch_bytes((uint16_t)g.white));
+    if (opts.deflicker) need = std::max(need, deflicker_scratch_bytes(g.bpp));
     return need;
 }
 
@@ -129,6 +131,15 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
     uint16_t *d_a = cs ? d_work : d_out;
     int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
     if (rc) return rc;
+    if (opts.deflicker) {                                                           // main.c:943, 895-906
+        int32_t bias[2];
+        for (int f = nframes - 1; f >= 0; f--) {                                    // frame 0 last: its bias is reported
+            rc = run_deflicker(ctx, g, d_a + (size_t)f * frame_stride, opts.deflicker, d_aux, st, bias);
+            if (rc) return rc;
+        }
+        res->exposure_bias[0] = bias[0];
+        res->exposure_bias[1] = bias[1];
+    }
     if (opts.fix_pattern_noise) {                                                   // main.c:946-949
         StageTimer t(ctx, ST_PATTERN, st);
         for (int f = 0; f < nframes; f++) {
@@ -137,7 +148,25 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
             ctx->launches += 10;
         }
     }
-    if (opts.dual_iso == 1 || opts.deflicker) return MLVB_ERR_UNSUPPORTED;   // TODO: preview dual ISO, deflicker
+    if (opts.dual_iso == 1) {                                                       // main.c:952-955
+        for (int f = 0; f < nframes; f++) {
+            uint16_t *fa = d_a + (size_t)f * frame_stride, *fo = d_out + (size_t)f * frame_stride;
+            {
+                StageTimer t(ctx, ST_DUALISO, st);
+                rc = run_hdr_preview(ctx, hdr, g, fa, d_aux, st);
+            }
+            if (rc < 0) return rc;
+            FrameGeom gf = g;
+            if (rc == 1) { gf.black *= 4; gf.white *= 4; }                         // hdr.c:222-223
+            if (f == 0) { res->is_dual_iso = rc; res->black_level = gf.black; res->white_level = gf.white; }
+            // Converted frames skip the focus / bad-pixel stage (main.c:961-973).  The reference would
+            // still chroma-smooth them with the x4 black level, which indexes its EV table out of bounds
+            // (values reach 65535 against 24576 entries); we do not smooth converted preview frames.
+            rc = run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, rc == 1, rc == 1, st);
+            if (rc) return rc;
+        }
+        return MLVB_OK;
+    }
     if (opts.dual_iso == 2) {                                                       // main.c:956-973
         for (int f = 0; f < nframes; f++) {
             uint16_t *fa = d_a + (size_t)f * frame_stride, *fo = d_out + (size_t)f * frame_stride;

@@ -146,6 +146,14 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
                  int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st);
 void dual_iso_reset_tables(mlvb_context *ctx);
 
+// hdrpreview.cu
+size_t hdr_preview_scratch_bytes(int white);
+size_t deflicker_scratch_bytes(int bpp);
+int run_hdr_preview(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, void *d_aux,
+                    cudaStream_t st);
+int run_deflicker(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, int target, void *d_aux, cudaStream_t st,
+                  int32_t bias[2]);
+
 // per-clip state accessors (call with ctx->clip_mu held)
 int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, int aggressive,
                       const uint16_t *d_img, cudaStream_t st, std::shared_ptr<PixelList> *out);

@@ -784,9 +784,29 @@ extern "C" {
 
 int hdr_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, off_t offset, size_t max_size)
 {
-    (void)frame_headers; (void)image_data; (void)offset; (void)max_size;
-    fprintf(stderr, "libmlvfs_b200: hdr_convert_data (dual-ISO preview, hdr.c:40-227) is not implemented yet\n");
-    return 0;
+    (void)offset;                                                       // unused by the reference as well
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: hdr_convert_data: no CUDA context (no CPU path)\n"); return 0; }
+    const FrameGeom g = geom_from_headers(frame_headers);
+    if (max_size < g.npix * 2) { fprintf(stderr, "libmlvfs_b200: hdr_convert_data needs the whole frame\n"); return 0; }
+    Slot *s = acquire_slot(ctx);
+    cudaSetDevice(ctx->device);
+    int ret = 0;
+    if (slot_reserve(*s, 16, g.npix * 2) == MLVB_OK &&
+        reserve_device(&s->d_aux, &s->aux_cap, hdr_preview_scratch_bytes((uint16_t)g.white)) == MLVB_OK &&
+        cudaMemcpyAsync(s->d_a, image_data, g.npix * 2, cudaMemcpyHostToDevice, s->stream) == cudaSuccess) {
+        const int rc = run_hdr_preview(ctx, frame_headers, g, s->d_a, s->d_aux, s->stream);
+        if (rc == 1 && cudaMemcpyAsync(image_data, s->d_a, g.npix * 2, cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+            cudaStreamSynchronize(s->stream) == cudaSuccess) {
+            frame_headers->rawi_hdr.raw_info.black_level *= 4;          // hdr.c:222-223
+            frame_headers->rawi_hdr.raw_info.white_level *= 4;
+            ret = 1;
+        } else {
+            cudaStreamSynchronize(s->stream);
+        }
+    }
+    release_slot(ctx, s);
+    return ret;
 }
 
 int cr2hdr20_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, int interp_method, int fullres,

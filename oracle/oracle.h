@@ -83,6 +83,11 @@ int  orc_hdr_check(const uint16_t *img, int w, int h, int black, int white);
 int  orc_hdr_interpolate(uint16_t *image, int w, int h, int black14, int interp_method, int use_fullres,
                          int use_alias_map, int cs_method, orc_diso_state *S, orc_diso_info *info);
 
+/* ---- dual-ISO preview (hdr.c:40-227) and deflicker (main.c:895-906, histogram.c) ---- */
+int  orc_hdr_preview(uint16_t *img, int width, int height, int black_level, int white_level, size_t max_size,
+                     const orc_pixel *focus, size_t nfocus, int crop_x, int crop_y);
+void orc_deflicker(const uint16_t *img, size_t bytes, int bpp, int black_level, int target, int bias[2]);
+
 /* ---- whole single-ISO chain in process_frame order (main.c:942-997) ---- */
 typedef struct {
     int chroma_smooth;      /* 0,2,3,5 */

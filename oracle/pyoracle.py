@@ -314,3 +314,27 @@ def cr2hdr20(img, black, white, *, interp_method=1, fullres=1, use_alias_map=1, 
     if rc < 0:
         raise NotImplementedError("oracle: this dual-ISO interpolation method is not restated yet")
     return rc, out, info
+
+
+# ---- dual-ISO preview + deflicker (oracle/orc_preview.c) -----------------------------------------
+
+def hdr_preview(img, black, white, focus_map=None, crop=(0, 0)):
+    """hdr_convert_data (hdr.c:40-227) -> (converted, frame); black/white x4 on success is the caller's job."""
+    lib = load_oracle()
+    lib.orc_hdr_preview.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t,
+                                    C.c_int, C.c_int]
+    out = np.ascontiguousarray(img, dtype=np.uint16).copy()
+    h, w = out.shape
+    fm = np.ascontiguousarray(focus_map, dtype=np.int32) if focus_map is not None and len(focus_map) else None
+    rc = lib.orc_hdr_preview(_p(out), w, h, black, white, out.nbytes, _p(fm) if fm is not None else None,
+                             len(fm) if fm is not None else 0, crop[0], crop[1])
+    return rc, out
+
+
+def deflicker(img, bpp, black, target):
+    lib = load_oracle()
+    lib.orc_deflicker.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    img = np.ascontiguousarray(img, dtype=np.uint16)
+    bias = (C.c_int * 2)()
+    lib.orc_deflicker(_p(img), img.nbytes, bpp, black, target, bias)
+    return bias[0], bias[1]

@@ -117,3 +117,9 @@ size_t ref_offsetof_frame_headers(int field)
     default: return (size_t)-1;
     }
 }
+
+/* main.c:895-906 (static): per-frame exposure compensation written into raw_info.exposure_bias */
+void ref_deflicker(struct frame_headers *hdrs, int target, uint16_t *data, size_t size_bytes)
+{
+    deflicker(hdrs, target, data, size_bytes);
+}

@@ -253,3 +253,35 @@ def test_dual_iso_rejects_plain_footage(oracle, ref):
     assert r == rc == 0
     assert hdr.rawi_hdr.raw_info.black_level == 2048
     assert np.array_equal(got, want)          # still carries the horizontal bad-pixel repairs (hdr.c:1944-1948)
+
+
+@pytest.mark.parametrize("w,h,shift,white", [(640, 360, 0, 15000), (642, 362, 1, 15000), (640, 360, 2, 12000), (640, 360, 3, 15000)])
+def test_dual_iso_preview_matches_reference(oracle, ref, w, h, shift, white):
+    base = synth.make_frame(w, h + 4, 0, dual_iso=True, white=white)
+    img = np.ascontiguousarray(base[shift:shift + h])
+    if white == 12000:
+        img[100:140, 200:300] = 0                 # deep shadows on dark rows: patched from the bright rows
+    hdr = F.make_frame_headers(w, h, white=white)
+    want = img.copy()
+    ref.hdr_convert_data.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_size_t]
+    assert ref.hdr_convert_data(C.byref(hdr), _p(want), 0, want.nbytes) == 1
+    rc, got = oracle.hdr_preview(img, 2048, white)
+    assert rc == 1 and np.array_equal(got, want)
+    assert hdr.rawi_hdr.raw_info.black_level == 8192
+    plain = synth.make_frame(w, h, 1)
+    assert oracle.hdr_preview(plain, 2048, white)[0] == 0
+
+
+def test_deflicker_matches_reference(oracle, ref):
+    w, h = 640, 360
+    for seed, target in [(0, 3000), (3, 5000), (5, 2100)]:
+        img = synth.make_frame(w, h, seed)
+        hdr = F.make_frame_headers(w, h)
+        ref.ref_deflicker.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        ref.ref_deflicker(C.byref(hdr), target, _p(img), img.nbytes)
+        want = (hdr.rawi_hdr.raw_info.exposure_bias[0], hdr.rawi_hdr.raw_info.exposure_bias[1])
+        assert oracle.deflicker(img, 14, 2048, target) == want
+    flat = np.full((h, w), 3000, np.uint16)        # > 65535 samples in one bin: the uint16 counter wraps
+    hdr = F.make_frame_headers(w, h)
+    ref.ref_deflicker(C.byref(hdr), 4000, _p(flat), flat.nbytes)
+    assert oracle.deflicker(flat, 14, 2048, 4000) == (hdr.rawi_hdr.raw_info.exposure_bias[0], 10000)
