@@ -150,3 +150,69 @@ def make_clip(path, w, h, nframes, *, headers=None, variant=None, bpp=14):
               for i in range(nframes)]
     write_mlv(path, (pack_bits(fr, bpp).tobytes() for fr in frames), headers)
     return headers, frames
+
+
+# ---- LJ92 test-input generator (vectorised; fixed Huffman table) ---------------------------------
+# Produces a valid lossless-JPEG stream (SOF3, one component, predictor 6) for the quadrant-interleaved
+# frame, i.e. what a compressed MLV stores (reference main.c:617-681 decodes it with lj92.c).  Input
+# generation only: it never touches the decode path.
+
+# code length per SSSS category 0..16 (canonical code, Kraft sum < 1 so no all-ones code word)
+_LJ_LEN = np.array([5, 4, 3, 3, 3, 3, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13], dtype=np.int64)
+
+
+def _lj_table():
+    order = sorted(range(17), key=lambda s: (_LJ_LEN[s], s))
+    codes = np.zeros(17, dtype=np.int64)
+    code, prev = 0, _LJ_LEN[order[0]]
+    for s in order:
+        code <<= int(_LJ_LEN[s] - prev)
+        prev = _LJ_LEN[s]
+        codes[s] = code
+        code += 1
+    counts = [int((_LJ_LEN == l).sum()) for l in range(1, 17)]
+    return codes, counts, order
+
+
+def lj92_encode_tiled(tiled, depth=14):
+    """Encode an (already interleaved) uint16 [h, w] image; returns the JPEG stream as uint8."""
+    t = np.ascontiguousarray(tiled, dtype=np.int64)
+    h, w = t.shape
+    pred = np.empty_like(t)
+    pred[0, 0] = 1 << (depth - 1)
+    pred[0, 1:] = t[0, :-1]
+    pred[1:, 0] = t[:-1, 0]
+    pred[1:, 1:] = t[:-1, 1:] + ((t[1:, :-1] - t[:-1, :-1]) >> 1)          # predictor 6
+    diff = (t - pred).reshape(-1)
+    mag = np.abs(diff)
+    ssss = np.zeros(diff.shape, dtype=np.int64)
+    nz = mag > 0
+    ssss[nz] = np.floor(np.log2(mag[nz])).astype(np.int64) + 1
+    extra = np.where(diff < 0, diff + (1 << ssss) - 1, diff)
+    codes, counts, order = _lj_table()
+    nbits = _LJ_LEN[ssss] + ssss
+    sym = (codes[ssss] << ssss) | extra                                     # code word followed by the magnitude bits
+    ends = np.cumsum(nbits)
+    total = int(ends[-1])
+    starts = ends - nbits
+    # expand every symbol into its bits (MSB first)
+    idx = np.repeat(np.arange(sym.size), nbits)
+    bitpos = np.arange(total) - np.repeat(starts, nbits)
+    bits = ((sym[idx] >> (np.repeat(nbits, nbits) - 1 - bitpos)) & 1).astype(np.uint8)
+    pad = (-total) % 8
+    if pad:
+        bits = np.concatenate([bits, np.ones(pad, np.uint8)])
+    body = np.packbits(bits)
+    ff = np.flatnonzero(body == 0xFF)
+    if ff.size:                                                             # byte stuffing: 0xFF -> 0xFF 0x00
+        body = np.insert(body, ff + 1, 0)
+    head = bytearray([0xFF, 0xD8, 0xFF, 0xC3, 0, 11, depth, h >> 8, h & 255, w >> 8, w & 255, 1, 0, 0x11, 0,
+                      0xFF, 0xC4, 0, 19 + 17, 0] + counts + order + [0xFF, 0xDA, 0, 8, 1, 0, 0, 6, 0, 0])
+    return np.concatenate([np.frombuffer(bytes(head), np.uint8), body, np.array([0xFF, 0xD9], np.uint8)])
+
+
+def lj92_payload(img, depth=14):
+    """VIDF payload of an LJ92 MLV frame: uint32 decoded size + stream of the interleaved frame."""
+    h, w = img.shape
+    stream = lj92_encode_tiled(quadrant_interleave(img), depth)
+    return np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), stream])
