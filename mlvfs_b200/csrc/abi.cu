@@ -125,11 +125,16 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
     res->exposure_bias[0] = hdr->rawi_hdr.raw_info.exposure_bias[0];
     res->exposure_bias[1] = hdr->rawi_hdr.raw_info.exposure_bias[1];
 
+    // steady state of the full single-ISO chain: one fused kernel, one pass over HBM (fused.cu)
+    int rc = try_fused_single_iso(ctx, hdr, g, opts, mlv_filename, d_payload, payload_stride, payload_bytes, d_out, frame_stride,
+                                  nframes, st);
+    if (rc <= 0) return rc;
+
     const bool cs = (opts.chroma_smooth == 2 || opts.chroma_smooth == 3 || opts.chroma_smooth == 5) && opts.dual_iso != 2 &&
                     g.black <= MLVB_MAX_BLACK;
     // without an out-of-place stage the chain can run directly in d_out
     uint16_t *d_a = cs ? d_work : d_out;
-    int rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
+    rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
     if (rc) return rc;
     if (opts.deflicker) {                                                           // main.c:943, 895-906
         int32_t bias[2];

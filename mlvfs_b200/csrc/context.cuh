@@ -38,6 +38,7 @@ struct BadPixelMap {                       // reference cs.c:186-193 + the 8-slo
     int aggressive = 0;
     bool valid = false;
     std::shared_ptr<PixelList> list;
+    std::shared_ptr<void> fused_plan;      // fused.cu: per-warp patch buckets for this map (built lazily)
 };
 
 struct FocusPixelMap {                     // reference cs.c:176-184
@@ -145,6 +146,11 @@ size_t dual_iso_scratch_bytes(int w, int h);
 int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, int interp_method,
                  int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st);
 void dual_iso_reset_tables(mlvb_context *ctx);
+
+// fused.cu: MLVB_OK = enqueued, 1 = not eligible (use the general path), < 0 = error
+int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, const mlvb_options &opts,
+                         const char *mlv_filename, const void *d_payload, size_t payload_stride, size_t payload_bytes,
+                         uint16_t *d_out, size_t out_stride_px, int nframes, cudaStream_t st);
 
 // hdrpreview.cu
 size_t hdr_preview_scratch_bytes(int white);
