@@ -216,3 +216,14 @@ def lj92_payload(img, depth=14):
     h, w = img.shape
     stream = lj92_encode_tiled(quadrant_interleave(img), depth)
     return np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), stream])
+
+
+def amaze_test_mosaic(w, h, seed):
+    """20-bit-range float mosaic with edges, texture at the Nyquist frequency and noise (AMaZE input as
+    hdr.c:977-1026 prepares it: greens halved around black)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = 30000 + 20000 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + 100000 * ((xx // 32 + yy // 32) % 2) + rng.integers(-3000, 3000, (h, w))
+    base = np.where((xx % 2) != (yy % 2), base * 0.5 + 60000, base)
+    base[:, w // 2:] += 40000 * (xx[:, w // 2:] % 2)
+    return np.clip(base, 0, 0xFFFFF).astype(np.int32).astype(np.float32)

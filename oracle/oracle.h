@@ -72,6 +72,7 @@ typedef struct {                 /* the reference's function-static LUT state */
     int lut_black, lut_white;
     double *fullres_curve;       /* hdr.c:890-913 */
     int curve_black;
+    int amaze_fresh_tiles;       /* test knob, see orc_amaze.c */
 } orc_diso_state;
 typedef struct {                 /* intermediate results, for stage-level parity checks */
     int rggb, is_bright[4], white_dark, white_bright, white_darkened;
@@ -82,6 +83,10 @@ void orc_diso_state_free(orc_diso_state *S);
 int  orc_hdr_check(const uint16_t *img, int w, int h, int black, int white);
 int  orc_hdr_interpolate(uint16_t *image, int w, int h, int black14, int interp_method, int use_fullres,
                          int use_alias_map, int cs_method, orc_diso_state *S, orc_diso_info *info);
+
+/* ---- AMaZE demosaic, SSE2 variant (amaze_demosaic_RT.c:113-1487) ---- */
+void orc_amaze_demosaic(const float *raw, float *red, float *green, float *blue, int stride, int width, int height,
+                        int fresh_tiles);
 
 /* ---- dual-ISO preview (hdr.c:40-227) and deflicker (main.c:895-906, histogram.c) ---- */
 int  orc_hdr_preview(uint16_t *img, int width, int height, int black_level, int white_level, size_t max_size,

@@ -1,6 +1,6 @@
 /* oracle/orc_dualiso.c -- TEST INFRASTRUCTURE.  Full dual-ISO conversion ("cr2hdr 20-bit"), restating
- * hdr.c:250-1957 for the mean23 interpolation path.  The AMaZE + edge-directed path (hdr.c:917-1229,
- * amaze_demosaic_RT.c) is not restated yet: interp_method 0 returns -1.
+ * hdr.c:250-1957: both interpolation paths, mean23 (hdr.c:1231-1304) and AMaZE + edge-directed
+ * (hdr.c:917-1229 on top of orc_amaze.c).
  *
  * The reference keeps its 20-bit EV tables and the full-res curve in function-static storage that is
  * rebuilt only when the black level changes (hdr.c:1080-1093, 1240-1253, 1575-1588, 1672-1685,
@@ -276,6 +276,106 @@ static void mean23(const uint32_t *raw32, uint32_t *dark, uint32_t *bright, int 
 #undef R
 }
 
+/* hdr.c:917-938: {ack, a, b, bck} offsets, y to be multiplied by s */
+static const int edge_dirs[11][8] = {
+    {-4, 2, -2, 1,  4, -2,  6, -3}, {-3, 2, -1, 1,  3, -2,  4, -3}, {-2, 2, -1, 1,  2, -2,  3, -3}, {-1, 2, -1, 1,  1, -2,  2, -3},
+    {-1, 2,  0, 1,  1, -2,  1, -3}, { 0, 2,  0, 1,  0, -2,  0, -3}, { 1, 2,  0, 1, -1, -2, -1, -3}, { 1, 2,  1, 1, -1, -2, -2, -3},
+    { 2, 2,  1, 1, -2, -2, -3, -3}, { 3, 2,  1, 1, -3, -2, -4, -3}, { 4, 2,  2, 1, -4, -2, -6, -3}};
+
+/* hdr.c:940-952 */
+static int edge_interp(const float *plane, int stride, const int *squeezed, const int *raw2ev, int dir, int x, int y, int s)
+{
+    int pa = iclamp((int)plane[(size_t)squeezed[y + edge_dirs[dir][3] * s] * stride + x + edge_dirs[dir][2]], 0, 0xFFFFF);
+    int pb = iclamp((int)plane[(size_t)squeezed[y + edge_dirs[dir][5] * s] * stride + x + edge_dirs[dir][4]], 0, 0xFFFFF);
+    return (raw2ev[pa] * 2 + raw2ev[pb]) / 3;
+}
+
+/* amaze_interpolate, hdr.c:954-1229 */
+static void amaze_edge(const uint32_t *raw32, uint32_t *dark, uint32_t *bright, int w, int h, int black, int white_darkened,
+                       const int is_bright[4], const int *raw2ev, const int *ev2raw, const double *curve, int fresh_tiles)
+{
+    const int ws = w + 16;
+    size_t np = (size_t)w * h, nps = (size_t)ws * h;
+    int *squeezed = calloc((size_t)h, sizeof(int));
+    float *rawf = calloc(nps, sizeof(float)), *red = calloc(nps, sizeof(float)), *green = calloc(nps, sizeof(float)),
+          *blue = calloc(nps, sizeof(float));
+    /* squeeze: dark rows to the top, bright rows from h/4*2 on; greens halved (hdr.c:977-1026) */
+    for (int pass = 0; pass < 2; pass++) {
+        int yh = -1;
+        for (int y = 0; y < h; y++) {
+            if (is_bright[y % 4] != pass) continue;
+            if (yh < 0) yh = pass ? h / 4 * 2 + y : y;
+            for (int x = 0; x < w; x++) {
+                int p = (int)raw32[x + (size_t)y * w];
+                if (x % 2 != y % 2) p = (p - black) / 2 + black;
+                rawf[(size_t)yh * ws + x] = p;
+            }
+            squeezed[y] = yh;
+            yh++;
+            if (pass && yh >= h) break;
+        }
+    }
+    orc_amaze_demosaic(rawf, red, green, blue, ws, w, h, fresh_tiles);
+    /* hdr.c:1045-1053 */
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)y * ws + x;
+            float g = (green[i] - black) * 2 + black;
+            g = g < 0xFFFFF ? g : 0xFFFFF; green[i] = g > 0 ? g : 0;
+            float r = red[i]; r = r < 0xFFFFF ? r : 0xFFFFF; red[i] = r > 0 ? r : 0;
+            float b = blue[i]; b = b < 0xFFFFF ? b : 0xFFFFF; blue[i] = b > 0 ? b : 0;
+        }
+    uint32_t *gray = malloc(np * 4);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)squeezed[y] * ws + x;
+            gray[x + (size_t)y * w] = (uint32_t)(green[i] / 2 + red[i] / 4 + blue[i] / 4);
+        }
+    uint8_t *edir = malloc(np);
+    const int d0 = 5;
+    memset(edir, d0, np);
+    for (int y = 5; y < h - 5; y++) {
+        int s = (is_bright[y % 4] == is_bright[(y + 1) % 4]) ? -1 : 1;
+        for (int x = 5; x < w - 5; x++) {
+            uint32_t p = raw32[x + (size_t)y * w];
+            int search;
+            if (!is_bright[y % 4]) search = !(curve[p] > fullres_thr);
+            else search = !(p < (uint32_t)white_darkened);
+            if (!search) continue;
+            int e_best = 0x7FFFFFFF, d_best = d0;
+            for (int d = 0; d <= 10; d++) {
+                int e = 0;
+                for (int j = -5; j <= 5; j++) {
+                    int p1 = raw2ev[gray[x + edge_dirs[d][0] + j + (y + edge_dirs[d][1] * s) * w]];
+                    int p2 = raw2ev[gray[x + edge_dirs[d][2] + j + (y + edge_dirs[d][3] * s) * w]];
+                    int p3 = raw2ev[gray[x + edge_dirs[d][4] + j + (y + edge_dirs[d][5] * s) * w]];
+                    int p4 = raw2ev[gray[x + edge_dirs[d][6] + j + (y + edge_dirs[d][7] * s) * w]];
+                    e += abs(p1 - p2) + abs(p2 - p3) + abs(p3 - p4);
+                }
+                e += abs(d - d0) * EV / 8;
+                if (e < e_best) { e_best = e; d_best = d; }
+            }
+            edir[x + (size_t)y * w] = (uint8_t)d_best;
+        }
+    }
+    for (int y = 2; y < h - 2; y++) {
+        int br = is_bright[y % 4];
+        uint32_t *native = br ? bright : dark, *interp = br ? dark : bright;
+        int is_rg = (y % 2 == 0);
+        int s = (is_bright[y % 4] == is_bright[(y + 1) % 4]) ? -1 : 1;
+        for (int x = 2; x < w - 2; x++) {
+            const float *plane = is_rg ? (x % 2 == 0 ? red : green) : (x % 2 == 0 ? green : blue);
+            int dir = edir[x + (size_t)y * w];
+            int pi0 = edge_interp(plane, ws, squeezed, raw2ev, dir, x, y, s);
+            int pip = edge_interp(plane, ws, squeezed, raw2ev, imin(dir + 1, 10), x, y, s);
+            int pim = edge_interp(plane, ws, squeezed, raw2ev, imax(dir - 1, 0), x, y, s);
+            interp[x + (size_t)y * w] = (uint32_t)ev2raw[(2 * pi0 + pip + pim) / 4];
+            native[x + (size_t)y * w] = raw32[x + (size_t)y * w];
+        }
+    }
+    free(edir); free(gray); free(squeezed); free(rawf); free(red); free(green); free(blue);
+}
+
 /* hdr.c:1306-1353 */
 static void border(const uint32_t *raw32, uint32_t *dark, uint32_t *bright, int w, int h, const int is_bright[4])
 {
@@ -348,7 +448,6 @@ int orc_hdr_interpolate(uint16_t *image, int w, int h, int black14, int interp_m
                         int cs_method, orc_diso_state *S, orc_diso_info *info)
 {
     if (w <= 0 || h <= 0) return 0;
-    if (interp_method == 0) return -1;
     orc_diso_info local;
     if (!info) info = &local;
     memset(info, 0, sizeof(*info));
@@ -381,7 +480,11 @@ int orc_hdr_interpolate(uint16_t *image, int w, int h, int black14, int interp_m
         double lowiso_dr = log2(white - black) - dark_noise_ev;
         if (black != S->lut_black) build_luts(S, black, white);
         const int *raw2ev = S->raw2ev, *ev2raw = S->ev2raw_0 + 10 * EV;
-        mean23(raw32, dark, bright, w, h, white, white_darkened, is_bright, raw2ev, ev2raw);
+        if (interp_method == 0)
+            amaze_edge(raw32, dark, bright, w, h, black, white_darkened, is_bright, raw2ev, ev2raw, fullres_curve_for(S, black),
+                       S->amaze_fresh_tiles);
+        else
+            mean23(raw32, dark, bright, w, h, white, white_darkened, is_bright, raw2ev, ev2raw);
         border(raw32, dark, bright, w, h, is_bright);
         if (use_fullres)                                              /* hdr.c:1355-1380 */
             for (int y = 0; y < h; y++)

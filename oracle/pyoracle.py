@@ -269,7 +269,7 @@ def fix_pattern_noise(img, white):
 
 class DisoState(C.Structure):
     _fields_ = [("raw2ev", C.c_void_p), ("ev2raw_0", C.c_void_p), ("lut_black", C.c_int), ("lut_white", C.c_int),
-                ("fullres_curve", C.c_void_p), ("curve_black", C.c_int)]
+                ("fullres_curve", C.c_void_p), ("curve_black", C.c_int), ("amaze_fresh_tiles", C.c_int)]
 
 
 class DisoInfo(C.Structure):
@@ -338,3 +338,46 @@ def deflicker(img, bpp, black, target):
     bias = (C.c_int * 2)()
     lib.orc_deflicker(_p(img), img.nbytes, bpp, black, target, bias)
     return bias[0], bias[1]
+
+
+# ---- AMaZE demosaic (oracle/orc_amaze.c) ---------------------------------------------------------
+
+def _amaze_planes(rawf):
+    rawf = np.ascontiguousarray(rawf, dtype=np.float32)
+    h, w = rawf.shape
+    ws = w + 16                                     # hdr.c:969: rows are w+16 floats, zero-filled
+    src = np.zeros((h, ws), np.float32)
+    src[:, :w] = rawf
+    outs = [np.full((h, ws), np.nan, np.float32) for _ in range(3)]
+    return src, outs, h, w, ws
+
+
+def amaze_demosaic(rawf, fresh_tiles=0):
+    """orc_amaze_demosaic on an (h, w) float32 mosaic; returns red, green, blue (h, w) float32.
+    Cells the algorithm never writes come back as NaN."""
+    lib = load_oracle()
+    lib.orc_amaze_demosaic.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+    lib.orc_amaze_demosaic.restype = None
+    src, outs, h, w, ws = _amaze_planes(rawf)
+    lib.orc_amaze_demosaic(_p(src), _p(outs[0]), _p(outs[1]), _p(outs[2]), ws, w, h, int(fresh_tiles))
+    return [o[:, :w].copy() for o in outs]
+
+
+def ref_amaze_demosaic(rawf):
+    """The compiled reference's amaze_demosaic_RT (amaze_demosaic_RT.c:113) on the same layout."""
+    ref = load_ref()
+    if ref is None:
+        return None
+    src, outs, h, w, ws = _amaze_planes(rawf)
+    RowPtrs = C.POINTER(C.c_float) * h
+
+    def rows(a):
+        base = a.ctypes.data
+        return RowPtrs(*[C.cast(base + r * ws * 4, C.POINTER(C.c_float)) for r in range(h)])
+
+    ref.amaze_demosaic_RT.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+    ref.amaze_demosaic_RT.restype = None
+    ptrs = [rows(a) for a in [src] + outs]
+    with quiet_stdout():
+        ref.amaze_demosaic_RT(ptrs[0], ptrs[1], ptrs[2], ptrs[3], 0, 0, w, h)
+    return [o[:, :w].copy() for o in outs]

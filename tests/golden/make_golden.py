@@ -117,6 +117,26 @@ def main():
         g["chain_out"] = np.stack(outs)
     np.savez_compressed(os.path.join(OUT, "single_iso.npz"), **g)
     print("wrote", os.path.join(OUT, "single_iso.npz"), os.path.getsize(os.path.join(OUT, "single_iso.npz")), "bytes")
+    dual_iso_golden(ref)
+
+
+def dual_iso_golden(ref):
+    """AMaZE planes (amaze_demosaic_RT) and whole cr2hdr20_convert_data frames, mean23 and AMaZE-edge."""
+    g = {}
+    r, gr, b = O.ref_amaze_demosaic(synth.amaze_test_mosaic(160, 104, 7))
+    g["amaze_rgb"] = np.stack([r, gr, b])
+    ref.cr2hdr20_convert_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    w, h = 256, 136
+    img = synth.make_frame(w, h, 0, dual_iso=True, hot_cold=True, bad_density=1e-4)
+    for name, interp, cs, badpix in (("mean23", 1, 3, 1), ("amaze", 0, 0, 1)):
+        hdr = F.make_frame_headers(w, h, file_guid=0x7100 + interp)
+        out = img.copy()
+        with O.quiet_stdout():
+            rc = ref.cr2hdr20_convert_data(C.byref(hdr), p(out), interp, 1, 1, cs, badpix)
+        assert rc == 1
+        g[f"diso_{name}_out"] = out
+    np.savez_compressed(os.path.join(OUT, "dual_iso.npz"), **g)
+    print("wrote", os.path.join(OUT, "dual_iso.npz"), os.path.getsize(os.path.join(OUT, "dual_iso.npz")), "bytes")
 
 
 if __name__ == "__main__":

@@ -65,3 +65,22 @@ def test_chain_golden(oracle):
     got, _ = oracle.single_iso_chain(frames, ri.black_level, ri.white_level, ri.frame_size,
                                      chroma_smooth_method=3, fix_bad_pixels=1, fix_stripes=1)
     assert np.array_equal(np.stack(got), G["chain_out"])
+
+
+# ---- dual ISO / AMaZE fixtures (tests/golden/dual_iso.npz, same generator script) ----------------------
+GD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dual_iso.npz"))
+
+
+def test_amaze_planes_golden(oracle):
+    """AMaZE red/green/blue float planes, bit for bit (amaze_demosaic_RT.c:113-1487, SSE2 build)."""
+    got = np.stack(oracle.amaze_demosaic(synth.amaze_test_mosaic(160, 104, 7)))
+    assert np.array_equal(got.view(np.uint32), GD["amaze_rgb"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,interp,cs,badpix", [("mean23", 1, 3, 1), ("amaze", 0, 0, 1)])
+def test_dual_iso_golden(oracle, name, interp, cs, badpix):
+    w, h = 256, 136
+    img = synth.make_frame(w, h, 0, dual_iso=True, hot_cold=True, bad_density=1e-4)
+    rc, got, _ = oracle.cr2hdr20(img, 2048, 15000, interp_method=interp, chroma_smooth_method=cs, fix_bad_pixels_mode=badpix)
+    assert rc == 1
+    assert np.array_equal(got, GD[f"diso_{name}_out"])

@@ -285,3 +285,43 @@ def test_deflicker_matches_reference(oracle, ref):
     hdr = F.make_frame_headers(w, h)
     ref.ref_deflicker(C.byref(hdr), 4000, _p(flat), flat.nbytes)
     assert oracle.deflicker(flat, 14, 2048, 4000) == (hdr.rawi_hdr.raw_info.exposure_bias[0], 10000)
+
+
+# ---- AMaZE + edge-directed dual ISO (amaze_demosaic_RT.c, hdr.c:917-1229) -------------------------------
+
+@pytest.mark.parametrize("w,h", [(160, 160), (288, 200), (256, 344), (384, 270), (128, 96)])
+def test_amaze_planes_match_reference(oracle, ref, w, h):
+    """The SSE2 build of amaze_demosaic_RT vs the lane-by-lane restatement: float planes bit for bit,
+    including partial right/bottom tiles and the reference's border-fill overrun (h - top in (144, 160))."""
+    raw = synth.amaze_test_mosaic(w, h, w * 7 + h)
+    want = oracle.ref_amaze_demosaic(raw)
+    got = oracle.amaze_demosaic(raw)
+    for name, a, b in zip("RGB", got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("w,h", [(256, 216), (384, 328), (512, 136)])
+def test_amaze_tiles_are_independent(oracle, w, h):
+    """What lets the CUDA path run one block per tile: with width % 128 == 0 (all BASELINE configs) the
+    reference's tile-to-tile persistent work planes never influence the output.  `fresh_tiles=1` clears the
+    block per tile, `-1` poisons every plane except pmwt (zeroed) with NaN."""
+    raw = synth.amaze_test_mosaic(w, h, 3)
+    base = oracle.amaze_demosaic(raw, fresh_tiles=0)
+    for mode in (1, -1):
+        other = oracle.amaze_demosaic(raw, fresh_tiles=mode)
+        for a, b in zip(base, other):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), mode
+
+
+@pytest.mark.parametrize("w,h,cs,alias,badpix,fullres", [
+    (640, 360, 0, 0, 0, 1), (640, 362, 3, 1, 2, 1), (384, 216, 5, 1, 0, 0), (300, 200, 0, 1, 1, 1)])
+def test_dual_iso_amaze_matches_reference(oracle, ref, w, h, cs, alias, badpix, fullres):
+    """cr2hdr20_convert_data with --amaze-edge (interp_method 0): squeeze, AMaZE, gray, edge-direction search,
+    edge-directed interpolation, then the shared mix/alias/blend stages."""
+    img = synth.make_frame(w, h, 0, dual_iso=True, hot_cold=True, bad_density=1e-4)
+    hdr = F.make_frame_headers(w, h, file_guid=0xB100 + cs * 64 + alias * 16 + badpix * 4 + fullres + w)
+    r, want = _ref_cr2hdr20(ref, oracle, hdr, img, 0, fullres, alias, cs, badpix)
+    rc, got, info = oracle.cr2hdr20(img, 2048, 15000, interp_method=0, fullres=fullres, use_alias_map=alias,
+                                    chroma_smooth_method=cs, fix_bad_pixels_mode=badpix)
+    assert r == rc == 1
+    assert np.array_equal(got, want)
