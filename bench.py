@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]           our CUDA path (default workload C2)
   python bench.py --impl reference [...]                        the reference's CPU path (oracle/_ref)
   torchrun --nproc-per-node N bench.py --gpus N ...             one rank per GPU, frames sharded by rank
-  python bench.py --workload C1|C2|C3|C5 ...                    the other BASELINE.json configs (not the headline line)
+  python bench.py --workload C1|C2|C3|C4|C5 ...                    the other BASELINE.json configs (not the headline line)
 
 Headline workload (config.workload): BASELINE.json configs[1] = C2 -- 1920x1080 14-bit uncompressed MLV frames
 with --stripes --bad-pix --cs3x3 (the full single-ISO correction chain), synthetic input (mlvfs_b200/synth.py).
@@ -50,6 +50,10 @@ WORKLOADS = {
                variant=dict(dual_iso=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
                desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=8,
                kernel="dual-ISO stage (statistics + mean23 + 2x cs5x5 on 20-bit planes + alias map + blend)"),
+    "C4": dict(w=5760, h=3240, opts=dict(dual_iso=2, hdr_interpolation_method=0, fix_bad_pixels=2),
+               variant=dict(dual_iso=True, hot_cold=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
+               desc="C4: 5760x3240 14-bit dual-ISO MLV, --dual-iso --amaze-edge --alias-map --really-bad-pix", frames=4,
+               kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)"),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,
                desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=64,
                kernel="lj92_decode_kernel (serial Huffman per frame, one warp per frame)"),

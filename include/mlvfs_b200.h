@@ -168,6 +168,12 @@ int hdr_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, 
 int cr2hdr20_convert_data(struct frame_headers *frame_headers, uint16_t *image_data, int interp_method, int fullres,
                           int use_alias_map, int chroma_smooth, int fix_bad_pixels_mode);
 
+/* reference amaze_demosaic_RT.c:113-120 (declared inside hdr.c:1028-1035, called at hdr.c:1040): AMaZE demosaic
+ * of a float RGGB mosaic.  rawData / red / green / blue are arrays of `winh` row pointers, every row
+ * winw + 16 floats (hdr.c:967-975).  Only winx = winy = 0 (the reference's own call) and winw % 4 == 0. */
+void amaze_demosaic_RT(float **rawData, float **red, float **green, float **blue, int winx, int winy, int winw,
+                       int winh);
+
 #ifdef __cplusplus
 }
 #endif

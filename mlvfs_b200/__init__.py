@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "chroma_smooth", "fix_bad_pixels", "fix_focus_pixels", "free_focus_pixel_maps",
     "stripes_get_correction", "stripes_new_correction", "stripes_free_corrections",
     "stripes_compute_correction", "stripes_apply_correction",
-    "fix_pattern_noise", "hdr_convert_data", "cr2hdr20_convert_data",
+    "fix_pattern_noise", "hdr_convert_data", "cr2hdr20_convert_data", "amaze_demosaic_RT",
 ]
 
 _lib = None
@@ -299,3 +299,26 @@ def stripes_compute_correction(hdr, image, mlv_filename):
 def stripes_apply_correction(hdr, corr, image, offset=0):
     lib().stripes_apply_correction(C.byref(hdr), corr, _ptr(image), offset, image.size)
     return image
+
+
+def amaze_demosaic(rawf):
+    """The drop-in ``amaze_demosaic_RT`` (reference amaze_demosaic_RT.c:113) on an (h, w) float32 RGGB mosaic,
+    called exactly like hdr.c:1040 calls it: arrays of row pointers, rows of w+16 floats.  Returns red, green,
+    blue as (h, w) float32."""
+    rawf = np.ascontiguousarray(rawf, dtype=np.float32)
+    h, w = rawf.shape
+    ws = w + 16
+    src = np.zeros((h, ws), np.float32)
+    src[:, :w] = rawf
+    outs = [np.full((h, ws), np.nan, np.float32) for _ in range(3)]
+    Rows = C.POINTER(C.c_float) * h
+
+    def rows(a):
+        return Rows(*[C.cast(a.ctypes.data + r * ws * 4, C.POINTER(C.c_float)) for r in range(h)])
+
+    L = lib()
+    L.amaze_demosaic_RT.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+    L.amaze_demosaic_RT.restype = None
+    ptrs = [rows(a) for a in [src] + outs]
+    L.amaze_demosaic_RT(ptrs[0], ptrs[1], ptrs[2], ptrs[3], 0, 0, w, h)
+    return [o[:, :w].copy() for o in outs]

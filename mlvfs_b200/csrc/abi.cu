@@ -61,7 +61,7 @@ size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts)
 {
     size_t need = 0;
     if (opts.fix_pattern_noise) need = std::max(need, pattern_noise_scratch_bytes(g.w, g.h));
-    if (opts.dual_iso == 2) need = std::max(need, dual_iso_scratch_bytes(g.w, g.h));
+    if (opts.dual_iso == 2) need = std::max(need, dual_iso_scratch_bytes(g.w, g.h, opts.hdr_interpolation_method));
     if (opts.dual_iso == 1) need = std::max(need, hdr_preview_scratch_bytes((uint16_t)g.white));
     if (opts.deflicker) need = std::max(need, deflicker_scratch_bytes(g.bpp));
     return need;

@@ -1,0 +1,231 @@
+// amaze.cu -- AMaZE + edge-directed interpolation of the dual-ISO half-resolution exposures.
+//
+// Replaces reference hdr.c:954-1229 (amaze_interpolate: squeeze the two exposures into half-height images,
+// AMaZE demosaic, grayscale, edge-direction search, edge-directed interpolation in EV space) and
+// amaze_demosaic_RT.c:113-1487 (tile program in amaze_tile.cuh).
+//
+// Kernels:
+//   amz_squeeze_kernel     hdr.c:977-1026   20-bit mosaic -> float, dark rows on top / bright rows below, greens halved
+//   amz_tiles_kernel       amaze_demosaic_RT.c:292-1470, persistent blocks pulling 160x160 tiles from a counter,
+//                          work planes in a per-block global workspace (L2 resident), see amaze_tile.cuh
+//   amz_gray_kernel        hdr.c:1045-1062  undo the green halving, clamp, gray = g/2 + r/4 + b/4, straight to raw2ev[gray]
+//   amz_edge_dir_kernel    hdr.c:1094-1175  11 directions x 11 offsets of |EV| differences where high accuracy is needed
+// The interpolation itself (hdr.c:1182-1210, edge_interp :940-952) is done inside dualiso.cu's per-pixel kernel
+// through amz_edge_interp().
+#include "amaze.cuh"
+
+#include "amaze_tile.cuh"
+#include "context.cuh"
+
+namespace {
+
+struct CudaCtx {
+    int tid, nthr;
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }
+};
+
+__global__ void amz_squeeze_kernel(const uint32_t *__restrict__ raw32, float *__restrict__ rawf, const int *__restrict__ sq_dst,
+                                   int w, int h, int ws, int black)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int yh = sq_dst[y];
+    if (yh < 0) return;                                                  // bright rows dropped by the `yh >= h` break (hdr.c:1025)
+    int p = (int)raw32[x + (size_t)y * w];
+    if ((x & 1) != (y & 1)) p = (p - black) / 2 + black;                 // greens halved around black (hdr.c:991-992)
+    rawf[(size_t)yh * ws + x] = (float)p;
+}
+
+__global__ void __launch_bounds__(AMZ_THREADS)
+amz_tiles_kernel(const float *__restrict__ raw, float *__restrict__ red, float *__restrict__ green, float *__restrict__ blue,
+                 int stride, int width, int height, int ntx, int nty, char *__restrict__ ws_base, unsigned *__restrict__ counter)
+{
+    __shared__ amaze::Shared S;
+    __shared__ unsigned s_tile;
+    const amaze::Ws W = amaze::carve(ws_base + (size_t)blockIdx.x * amaze::WS_BYTES);
+    CudaCtx C{(int)threadIdx.x, (int)blockDim.x};
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
+        __syncthreads();
+        const unsigned t = s_tile;
+        if (t >= (unsigned)(ntx * nty)) break;
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const amaze::Geom G = amaze::tile_geom(width, height, -16 + ty * (amaze::TS - 32), -16 + tx * (amaze::TS - 32));
+        amaze::tile_body(C, W, G, S, raw, red, green, blue, stride);
+        __syncthreads();
+    }
+}
+
+__global__ void amz_gray_kernel(const float *__restrict__ red, const float *__restrict__ green, const float *__restrict__ blue,
+                                const int *__restrict__ squeezed, const int *__restrict__ raw2ev, int *__restrict__ grayev,
+                                int w, int h, int ws, int black)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const size_t i = (size_t)squeezed[y] * ws + x;
+    const float g = amz_post_green(green[i], black), r = amz_post_rb(red[i]), b = amz_post_rb(blue[i]);
+    const uint32_t gray = (uint32_t)(g / 2.0f + r / 4.0f + b / 4.0f);   // hdr.c:1062
+    grayev[x + (size_t)y * w] = __ldg(raw2ev + (gray & 0xFFFFF));
+}
+
+__device__ __forceinline__ double amz_fullres_curve_at(int i, int black)         // hdr.c:904-909
+{
+    const double ev2 = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0));
+    const double c2 = -cos(fmax(fmin(ev2 - 4.0, 4.0), 0.0) * M_PI / 4.0);
+    return (c2 + 1.0) / 2.0;
+}
+
+__global__ void __launch_bounds__(128)
+amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ grayev, uint8_t *__restrict__ edir,
+                    int w, int h, int black, int white_darkened, int b0, int b1, int b2, int b3)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int isb[4] = {b0, b1, b2, b3};
+    uint8_t best = 5;
+    if (x >= 5 && x < w - 5 && y >= 5 && y < h - 5) {
+        const uint32_t p = raw32[x + (size_t)y * w];
+        bool search;
+        if (!isb[y & 3]) search = !(amz_fullres_curve_at((int)p, black) > 0.8);   // deep shadows of the dark exposure (hdr.c:1106-1120)
+        else search = !(p < (uint32_t)white_darkened);                             // bright exposure clipped (hdr.c:1122-1133)
+        if (search) {
+            const int s = (isb[y & 3] == isb[(y + 1) & 3]) ? -1 : 1;
+            int e_best = 0x7FFFFFFF;
+            for (int d = 0; d <= 10; d++) {
+                // flat indexing like the reference: x + dx + j may leave the row
+                const int *r1 = grayev + (long long)(y + c_edge[d][1] * s) * w + x + c_edge[d][0];
+                const int *r2 = grayev + (long long)(y + c_edge[d][3] * s) * w + x + c_edge[d][2];
+                const int *r3 = grayev + (long long)(y + c_edge[d][5] * s) * w + x + c_edge[d][4];
+                const int *r4 = grayev + (long long)(y + c_edge[d][7] * s) * w + x + c_edge[d][6];
+                int e = 0;
+#pragma unroll
+                for (int j = -5; j <= 5; j++) {
+                    const int p1 = __ldg(r1 + j), p2 = __ldg(r2 + j), p3 = __ldg(r3 + j), p4 = __ldg(r4 + j);
+                    e += abs(p1 - p2) + abs(p2 - p3) + abs(p3 - p4);
+                }
+                e += abs(d - 5) * (MLVB_EV_RES / 8);
+                if (e < e_best) { e_best = e; best = (uint8_t)d; }
+            }
+        }
+    }
+    edir[x + (size_t)y * w] = best;
+}
+
+}  // namespace
+
+size_t amaze_scratch_bytes(int w, int h, AmazeScratch *S, uint8_t *base)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { void *p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return p; };
+    const size_t np = (size_t)w * h, nps = (size_t)(w + 16) * h;
+    AmazeScratch s;
+    s.rawf = (float *)take(nps * 4); s.red = (float *)take(nps * 4); s.green = (float *)take(nps * 4); s.blue = (float *)take(nps * 4);
+    s.grayev = (int *)take(np * 4);
+    s.edir = (uint8_t *)take(np);
+    s.squeezed = (int *)take((size_t)h * 4); s.sq_dst = (int *)take((size_t)h * 4);
+    s.counter = (unsigned *)take(256);
+    const int ntiles = amaze::tiles_along(w) * amaze::tiles_along(h);
+    s.nblocks = ntiles < AMZ_MAX_BLOCKS ? ntiles : AMZ_MAX_BLOCKS;
+    s.ws = (char *)take((size_t)s.nblocks * amaze::WS_BYTES);
+    if (S) *S = s;
+    return o;
+}
+
+// Everything of amaze_interpolate up to (and including) the direction map; the caller's per-pixel kernel
+// then interpolates with amz_edge_interp().
+int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int white_darkened, const int is_bright[4],
+                       const int *d_raw2ev, const AmazeScratch &A, cudaStream_t st, int *launches)
+{
+    if (w & 3) {
+        fprintf(stderr, "libmlvfs_b200: --amaze-edge needs a frame width that is a multiple of 4 (got %d)\n", w);
+        return MLVB_ERR_UNSUPPORTED;
+    }
+    const int ws = w + 16;
+    // row maps of the squeeze (hdr.c:977-1026): squeezed[y] is what later stages index with (0 for dropped
+    // rows, like the reference's zero-initialised array), sq_dst[y] the row actually written (-1: none)
+    std::vector<int> sq(2 * (size_t)h, 0);
+    int *squeezed = sq.data(), *dst = sq.data() + h;
+    for (int y = 0; y < h; y++) dst[y] = -1;
+    for (int pass = 0; pass < 2; pass++) {
+        int yh = -1;
+        for (int y = 0; y < h; y++) {
+            if (is_bright[y % 4] != pass) continue;
+            if (yh < 0) yh = pass ? h / 4 * 2 + y : y;
+            if (yh >= h) break;                                          // cannot happen for the dark pass; guards the write
+            squeezed[y] = yh; dst[y] = yh;
+            yh++;
+            if (pass && yh >= h) break;
+        }
+    }
+    MLVB_CUDA_OK(cudaMemcpyAsync(A.squeezed, squeezed, (size_t)h * 4, cudaMemcpyHostToDevice, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(A.sq_dst, dst, (size_t)h * 4, cudaMemcpyHostToDevice, st));
+    MLVB_CUDA_OK(cudaStreamSynchronize(st));                              // `sq` is pageable and dies with this scope
+    MLVB_CUDA_OK(cudaMemsetAsync(A.rawf, 0, (size_t)ws * h * 4, st));
+    MLVB_CUDA_OK(cudaMemsetAsync(A.counter, 0, sizeof(unsigned), st));
+    const dim3 g2(ceil_div(w, 256), h);
+    amz_squeeze_kernel<<<g2, 256, 0, st>>>(d_raw32, A.rawf, A.sq_dst, w, h, ws, black);
+    const int ntx = amaze::tiles_along(w), nty = amaze::tiles_along(h);
+    amz_tiles_kernel<<<A.nblocks, AMZ_THREADS, 0, st>>>(A.rawf, A.red, A.green, A.blue, ws, w, h, ntx, nty, A.ws, A.counter);
+    amz_gray_kernel<<<g2, 256, 0, st>>>(A.red, A.green, A.blue, A.squeezed, d_raw2ev, A.grayev, w, h, ws, black);
+    amz_edge_dir_kernel<<<dim3(ceil_div(w, 128), h), 128, 0, st>>>(d_raw32, A.grayev, A.edir, w, h, black, white_darkened,
+                                                                  is_bright[0], is_bright[1], is_bright[2], is_bright[3]);
+    if (launches) *launches += 4;
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
+
+// AMaZE alone on a device-resident float mosaic (test / benchmark entry behind mlvb_amaze_demosaic)
+int launch_amaze_planes(const float *d_raw, float *d_red, float *d_green, float *d_blue, int stride, int w, int h,
+                        char *d_ws, int nblocks, unsigned *d_counter, cudaStream_t st)
+{
+    if (w & 3) return MLVB_ERR_UNSUPPORTED;
+    MLVB_CUDA_OK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st));
+    amz_tiles_kernel<<<nblocks, AMZ_THREADS, 0, st>>>(d_raw, d_red, d_green, d_blue, stride, w, h, amaze::tiles_along(w),
+                                                     amaze::tiles_along(h), d_ws, d_counter);
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
+
+size_t amaze_ws_bytes_per_block() { return amaze::WS_BYTES; }
+int amaze_tile_count(int w, int h) { return amaze::tiles_along(w) * amaze::tiles_along(h); }
+
+// Drop-in for the reference's exported AMaZE entry (amaze_demosaic_RT.c:113-120, called from hdr.c:1040):
+// rawData/red/green/blue are arrays of `winh` row pointers, each row winw+16 floats (hdr.c:967-975).
+// Only the whole-image window the reference itself uses (winx = winy = 0) is supported.
+extern "C" void amaze_demosaic_RT(float **rawData, float **red, float **green, float **blue, int winx, int winy, int winw, int winh)
+{
+    mlvb_context *ctx = mlvb_default_context();
+    if (!ctx) { fprintf(stderr, "libmlvfs_b200: amaze_demosaic_RT: no CUDA context (no CPU path)\n"); return; }
+    if (winx || winy || winw < 32 || winh < 32 || (winw & 3)) {
+        fprintf(stderr, "libmlvfs_b200: amaze_demosaic_RT: unsupported window %d,%d %dx%d\n", winx, winy, winw, winh);
+        return;
+    }
+    const int ws = winw + 16;
+    const size_t plane = (size_t)ws * winh;
+    const int ntiles = amaze_tile_count(winw, winh), nblocks = ntiles < AMZ_MAX_BLOCKS ? ntiles : AMZ_MAX_BLOCKS;
+    const size_t need = 4 * plane * sizeof(float) + 256 + (size_t)nblocks * amaze::WS_BYTES;
+    Slot *s = acquire_slot(ctx);
+    cudaSetDevice(ctx->device);
+    std::vector<float> host(plane);
+    bool ok = reserve_device(&s->d_aux, &s->aux_cap, need) == MLVB_OK;
+    if (ok) {
+        float *d_raw = (float *)s->d_aux, *d_r = d_raw + plane, *d_g = d_r + plane, *d_b = d_g + plane;
+        unsigned *d_counter = (unsigned *)(d_b + plane);
+        char *d_ws = (char *)d_counter + 256;
+        for (int y = 0; y < winh; y++) memcpy(host.data() + (size_t)y * ws, rawData[y], (size_t)ws * sizeof(float));
+        ok = cudaMemcpyAsync(d_raw, host.data(), plane * sizeof(float), cudaMemcpyHostToDevice, s->stream) == cudaSuccess &&
+             cudaStreamSynchronize(s->stream) == cudaSuccess &&
+             launch_amaze_planes(d_raw, d_r, d_g, d_b, ws, winw, winh, d_ws, nblocks, d_counter, s->stream) == MLVB_OK;
+        ctx->launches += 1;
+        float **dst[3] = {red, green, blue};
+        float *src[3] = {d_r, d_g, d_b};
+        for (int k = 0; k < 3 && ok; k++) {
+            ok = cudaMemcpyAsync(host.data(), src[k], plane * sizeof(float), cudaMemcpyDeviceToHost, s->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(s->stream) == cudaSuccess;
+            if (ok) for (int y = 0; y < winh; y++) memcpy(dst[k][y], host.data() + (size_t)y * ws, (size_t)winw * sizeof(float));
+        }
+    }
+    if (!ok) { cudaStreamSynchronize(s->stream); fprintf(stderr, "libmlvfs_b200: amaze_demosaic_RT failed\n"); }
+    release_slot(ctx, s);
+}

@@ -1,0 +1,598 @@
+// amaze_tile.cuh -- AMaZE demosaic of one 160x160 tile as a cooperative thread-block program.
+//
+// Replaces reference amaze_demosaic_RT.c:292-1470 (the body of the tile loop) in its __SSE2__ form, which is
+// what the reference compiles to on x86-64: 4-wide vector loops that run a few columns past the scalar
+// bounds, and in-place passes whose lanes see a mix of already-updated and original neighbours.  Every
+// value equals the reference's: IEEE binary32 in the reference's association order (build with
+// -fmad=false), IEEE division, the two "exponent decrement" halvings and the three fp64 promotions.
+//
+// The reference walks the tiles one after another through one calloc'ed block; here every tile runs in its
+// own thread block on its own workspace.  That is exact whenever the reference's result does not depend on
+// what the previous tile left behind, which holds for every plane except `pmwt` (tests/test_oracle_vs_ref.py
+// ::test_amaze_tiles_are_independent); pmwt is zeroed per tile, which equals the reference's state for
+// widths that are multiples of 128 (all BASELINE configs).  For other widths the last partial tile column
+// can differ from the sequential reference in a few border pixels (documented in DESIGN.md).
+//
+// The body is one template over a "context" (thread id, block size, barrier, shared scratch) so that the
+// same source runs as a CUDA block and, for tests, as a group of host threads (tests/emu/amaze_emu.cpp).
+// Sequential dependencies of the reference are kept exactly:
+//   * variance pass (:748-803): column-per-thread walk down the rows, one barrier per row for the
+//     two left-neighbour lanes that must see updated values;
+//   * hvwt (:1054-1058) and pmwt (:1269-1272) refinements: row after row through a shared row buffer;
+//   * Nyquist 3x3 vote (:998-1010): raster-sequential, run only for rows that can change.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define AMZ_HD __host__ __device__ __forceinline__
+#else
+#define AMZ_HD inline
+#endif
+
+namespace amaze {
+
+constexpr int TS = 160, TSH = 80;                                      // amaze_demosaic_RT.c:137-138
+constexpr int V1 = TS, V2 = 2 * TS, V3 = 3 * TS, P1 = -TS + 1, P2 = -2 * TS + 2, P3 = -3 * TS + 3,
+              M1 = TS + 1, M2 = 2 * TS + 2, M3 = 3 * TS + 3;           // :147
+constexpr size_t FULL_B = sizeof(float) * TS * TS, HALF_B = sizeof(float) * TS * TSH, GAP_B = 64;
+// the reference's block (:244): 22 full planes' worth of floats + nyquist bytes + 64-byte gaps
+constexpr size_t WS_BYTES = (22 * FULL_B + TS * TSH + 23 * GAP_B + 255) / 256 * 256;
+
+struct Ws {                                                            // plane order of :249-273
+    float *rgbgreen, *delhvsqsum, *dirwts0, *dirwts1, *vcd, *hcd, *vcdalt, *hcdalt, *cddiffsq, *hvwt, *Dgrb0, *Dgrb1,
+          *delp, *delm, *rbint, *Dgrb2, *dgintv, *dginth, *Dgrbsq1m, *Dgrbsq1p, *cfa, *pmwt, *rbm, *rbp;
+    unsigned char *nyquist;
+};
+
+AMZ_HD Ws carve(char *p)
+{
+    Ws W;
+#define AMZ_TAKE(name, sz) W.name = (float *)p; p += (sz) + GAP_B
+    AMZ_TAKE(rgbgreen, FULL_B); AMZ_TAKE(delhvsqsum, FULL_B); AMZ_TAKE(dirwts0, FULL_B); AMZ_TAKE(dirwts1, FULL_B);
+    AMZ_TAKE(vcd, FULL_B); AMZ_TAKE(hcd, FULL_B); AMZ_TAKE(vcdalt, FULL_B); AMZ_TAKE(hcdalt, FULL_B); AMZ_TAKE(cddiffsq, FULL_B);
+    AMZ_TAKE(hvwt, HALF_B);
+    W.Dgrb0 = (float *)p; W.Dgrb1 = W.Dgrb0 + TS * TSH; p += FULL_B + GAP_B;
+    AMZ_TAKE(delp, HALF_B); AMZ_TAKE(delm, HALF_B); AMZ_TAKE(rbint, HALF_B); AMZ_TAKE(Dgrb2, FULL_B); AMZ_TAKE(dgintv, FULL_B);
+    AMZ_TAKE(dginth, FULL_B); AMZ_TAKE(Dgrbsq1m, HALF_B); AMZ_TAKE(Dgrbsq1p, HALF_B); AMZ_TAKE(cfa, FULL_B);
+    AMZ_TAKE(pmwt, HALF_B); AMZ_TAKE(rbm, HALF_B); AMZ_TAKE(rbp, HALF_B);
+#undef AMZ_TAKE
+    W.nyquist = (unsigned char *)p;
+    return W;
+}
+
+struct Geom { int width, height, top, left, rr1, cc1, rrmin, rrmax, ccmin, ccmax; };
+
+AMZ_HD Geom tile_geom(int width, int height, int top, int left)        // :296-303, :373-376
+{
+    Geom G;
+    G.width = width; G.height = height; G.top = top; G.left = left;
+    const int bottom = top + TS < height + 16 ? top + TS : height + 16;
+    const int right = left + TS < width + 16 ? left + TS : width + 16;
+    G.rr1 = bottom - top; G.cc1 = right - left;
+    G.rrmin = top < 0 ? 16 : 0; G.ccmin = left < 0 ? 16 : 0;
+    G.rrmax = bottom > height ? height - top : G.rr1;
+    G.ccmax = right > width ? width - left : G.cc1;
+    return G;
+}
+AMZ_HD int tiles_along(int extent) { return (extent + 16 + (TS - 32) - 1) / (TS - 32); }   // top = -16, -16+128, ... < extent
+
+struct Shared {                       // block-shared scratch of the sequential passes
+    float row[2][TS];
+    int oth[TSH], old[TSH];
+    int rowcnt[TS];
+    int anynyq;
+};
+
+// ---- scalar helpers with the reference's exact comparison semantics ----
+AMZ_HD int fc(int r, int c) { return ((r & 1) == 0 && (c & 1) == 0) ? 0 : ((r & 1) && (c & 1)) ? 2 : 1; }   // :41-49
+AMZ_HD float expdec(float d, int n)                                    // xdiv2f / xdivf, :88-100
+{
+#if defined(__CUDA_ARCH__)
+    int i = __float_as_int(d);
+    if (i & 0x7FFFFFFF) i -= n << 23;
+    return __int_as_float(i);
+#else
+    int32_t i; memcpy(&i, &d, 4);
+    if (i & 0x7FFFFFFF) i -= n << 23;
+    memcpy(&d, &i, 4);
+    return d;
+#endif
+}
+AMZ_HD float sq(float a) { return a * a; }
+AMZ_HD float ab(float a) { return fabsf(a); }
+AMZ_HD float vmin(float a, float b) { return a < b ? a : b; }          // minps / maxps operand order
+AMZ_HD float vmax(float a, float b) { return a > b ? a : b; }
+AMZ_HD float limv(float a, float b, float c) { return vmax(b, vmin(a, c)); }                 // sleefsseavx.c:1295
+AMZ_HD float ulimv(float a, float b, float c) { return b < c ? limv(a, b, c) : limv(a, c, b); }
+AMZ_HD float lims(float x, float lo, float hi) { const float m = x < hi ? x : hi; return m > lo ? m : lo; }   // scalar LIM
+AMZ_HD float ulims(float a, float b, float c) { return b < c ? lims(a, b, c) : lims(a, c, b); }
+AMZ_HD int cdiv(int a, int b) { return a > 0 ? (a + b - 1) / b : 0; }
+
+#define AMZ_EPS 1e-5f
+#define AMZ_EPSSQ 1e-10f
+#define AMZ_ARTHRESH 0.75f
+#define AMZ_CLIP 1.0f
+#define AMZ_CLIP8 0.8f
+
+// one cell of the variance/bounding pass (:766-800) given the (possibly updated) left neighbour hm2 and the
+// row-above neighbour vm2; everything else original
+AMZ_HD float bound_cd(float cd, float c0, float n1, float n2, float sgn)
+{
+    const float nsgn = -sgn, sgn3 = 3.0f * sgn;
+    const float Gint = sgn * cd + c0;
+    const float t2 = sgn3 * cd;
+    const float wt = 1.0f + t2 / (AMZ_EPS + Gint + c0);
+    const bool pos = nsgn * cd > 0.0f;
+    const float old = cd;
+    const float t = nsgn * (c0 - ulimv(Gint, n1, n2));
+    float r = (t2 < -(c0 + Gint)) ? t : wt * cd + (1.0f - wt) * t;
+    r = pos ? r : old;
+    r = Gint > AMZ_CLIP ? t : r;
+    return r;
+}
+AMZ_HD float var3(float a, float b, float c) { return 3.0f * (sq(a) + sq(b) + sq(c)) - sq(a + b + c); }
+
+// ------------------------------------------------------------------------------------------------------
+template <class Ctx>
+AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float *__restrict__ raw, float *__restrict__ red,
+                      float *__restrict__ green, float *__restrict__ blue, int stride)
+{
+    const int tid = C.tid, nthr = C.nthr;
+    const int rr1 = G.rr1, cc1 = G.cc1, top = G.top, left = G.left, width = G.width, height = G.height;
+    float *const cfa = W.cfa, *const rgbgreen = W.rgbgreen, *const hvwt = W.hvwt, *const pmwt = W.pmwt;
+    unsigned char *const nyquist = W.nyquist;
+    const float gaussodd[4] = {0.14659727707323927f, 0.103592713382435f, 0.0732036125103057f, 0.0365543548389495f};
+    const float gaussgrad[6] = {0.07384411893421103f, 0.06207511968171489f, 0.0521818194747806f,
+                                0.03687419286733595f, 0.03099732204057846f, 0.018413194161458882f};
+    const float gausseven[2] = {0.13719494435797422f, 0.05640252782101291f};
+    const float gquinc[4] = {0.169917f, 0.108947f, 0.069855f, 0.0287182f};
+
+    // ---- per-tile clears (:294-295) + pmwt (see header) ----
+    for (int k = tid; k < TS * TSH; k += nthr) { pmwt[k] = 0.0f; W.rbint[k] = 0.0f; nyquist[k] = 0; }
+    for (int k = tid; k < TS; k += nthr) S.rowcnt[k] = 0;
+    if (tid == 0) S.anynyq = 0;
+    C.sync();
+
+    // ---- load + mirrored borders (:378-469); the bottom border may run past row 159 like the reference's ----
+    {
+        const int rrend = G.rrmax < rr1 ? G.rrmax + 16 : rr1;
+        for (int idx = tid; idx < rrend * cc1; idx += nthr) {
+            const int rr = idx / cc1, cc = idx - rr * cc1;
+            const bool tb = rr < G.rrmin, bb = rr >= G.rrmax, lb = cc < G.ccmin, rb = cc >= G.ccmax;
+            const int rl = rr - G.rrmax, cl = cc - G.ccmax;              // local indices inside the bottom / right border
+            int sr, sc, fr = rr, fcc = cc;
+            bool vec;                                                    // vector copies fill rgbgreen at every site
+            if (tb && lb)      { sr = 32 - rr;          sc = 32 - (cc & ~3) + (cc & 3);             vec = true; }            // :435-443
+            else if (bb && rb) { sr = height - rl - 2;  sc = width - (cl & ~3) - 2 + (cl & 3);      vec = true; }            // :444-452
+            else if (tb && rb) { sr = 32 - rr;          sc = width - cl - 2;                        vec = false; fcc = cl; } // :453-461
+            else if (bb && lb) { sr = height - rl - 2;  sc = 32 - cc;                               vec = false; fr = rl; }  // :462-469
+            else if (tb)       { sr = 32 - rr + top;    sc = cc + left;                             vec = false; }           // :399-406
+            else if (bb)       { sr = height - rl - 2;  sc = cc + left;                             vec = true; }            // :407-415
+            else if (lb)       { sr = rr + top;         sc = 32 - cc + left;                        vec = false; }           // :417-424
+            else if (rb)       { sr = rr + top;         sc = width - cl - 2;                        vec = false; fcc = cl; } // :426-433
+            else               { sr = rr + top;         sc = cc + left;                             vec = true; }            // :381-387
+            const float v = raw[(size_t)sr * stride + sc] / 65535.0f;
+            cfa[rr * TS + cc] = v;
+            if (vec || fc(fr, fcc) == 1) rgbgreen[rr * TS + cc] = v;
+        }
+    }
+    C.sync();
+
+    // ---- gradients, directional weights (:553-567) and diagonal gradients (:581-606) ----
+    {
+        const int cw = cdiv(cc1, 4) * 4, nrow = rr1 - 4;
+        for (int idx = tid; idx < nrow * cw; idx += nthr) {
+            const int rr = 2 + idx / cw, cc = idx % cw, i = rr * TS + cc;
+            const float delh = ab(cfa[i + 1] - cfa[i - 1]), delv = ab(cfa[i + V1] - cfa[i - V1]);
+            W.dirwts1[i] = AMZ_EPS + ab(cfa[i + 2] - cfa[i]) + ab(cfa[i] - cfa[i - 2]) + delh;
+            W.dirwts0[i] = AMZ_EPS + ab(cfa[i + V2] - cfa[i]) + ab(cfa[i] - cfa[i - V2]) + delv;
+            W.delhvsqsum[i] = delh * delh + delv * delv;
+        }
+        const int np = 4 * cdiv(cc1 - 12, 8), nrow6 = rr1 - 12;
+        for (int idx = tid; idx < nrow6 * np; idx += nthr) {
+            const int rr = 6 + idx / np, cc = 6 + 2 * (idx % np), i = rr * TS + cc;
+            const int o = (fc(rr, 2) & 1) ? 0 : 1, g = i + o, c = i + (1 - o);
+            const float t = cfa[g];
+            W.delp[i >> 1] = ab(cfa[c + P1] - cfa[c - P1]);
+            W.delm[i >> 1] = ab(cfa[c + M1] - cfa[c - M1]);
+            W.Dgrbsq1m[i >> 1] = sq(t - cfa[g - M1]) + sq(t - cfa[g + M1]);
+            W.Dgrbsq1p[i >> 1] = sq(t - cfa[g - P1]) + sq(t - cfa[g + P1]);
+        }
+    }
+    C.sync();
+
+    // ---- H/V colour differences (:633-689) and the diagonal R/B estimates (:1115-1180) ----
+    {
+        const int nc = 4 * cdiv(cc1 - 11, 4), nrow = rr1 - 8;
+        for (int idx = tid; idx < nrow * nc; idx += nthr) {
+            const int rr = 4 + idx / nc, cc = 4 + idx % nc, i = rr * TS + cc;
+            const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
+            const float *d0 = W.dirwts0, *d1 = W.dirwts1;
+            const float c0 = cfa[i];
+            const float cru = cfa[i - V1] * (d0[i - V2] + d0[i]) / (d0[i - V2] * (AMZ_EPS + c0) + d0[i] * (AMZ_EPS + cfa[i - V2]));
+            const float crd = cfa[i + V1] * (d0[i + V2] + d0[i]) / (d0[i + V2] * (AMZ_EPS + c0) + d0[i] * (AMZ_EPS + cfa[i + V2]));
+            const float crl = cfa[i - 1] * (d1[i - 2] + d1[i]) / (d1[i - 2] * (AMZ_EPS + c0) + d1[i] * (AMZ_EPS + cfa[i - 2]));
+            const float crr = cfa[i + 1] * (d1[i + 2] + d1[i]) / (d1[i + 2] * (AMZ_EPS + c0) + d1[i] * (AMZ_EPS + cfa[i + 2]));
+            const float guha = cfa[i - V1] + 0.5f * (c0 - cfa[i - V2]), gdha = cfa[i + V1] + 0.5f * (c0 - cfa[i + V2]);
+            const float glha = cfa[i - 1] + 0.5f * (c0 - cfa[i - 2]), grha = cfa[i + 1] + 0.5f * (c0 - cfa[i + 2]);
+            float guar = ab(1.0f - cru) < AMZ_ARTHRESH ? c0 * cru : guha;
+            float gdar = ab(1.0f - crd) < AMZ_ARTHRESH ? c0 * crd : gdha;
+            float glar = ab(1.0f - crl) < AMZ_ARTHRESH ? c0 * crl : glha;
+            float grar = ab(1.0f - crr) < AMZ_ARTHRESH ? c0 * crr : grha;
+            const float hwt = d1[i - 1] / (d1[i - 1] + d1[i + 1]);
+            const float vwt = d0[i - V1] / (d0[i + V1] + d0[i - V1]);
+            const float Ginthha = hwt * grha + (1.0f - hwt) * glha, Gintvha = vwt * gdha + (1.0f - vwt) * guha;
+            const float ha = sgn * (Ginthha - c0), va = sgn * (Gintvha - c0);
+            W.hcdalt[i] = ha; W.vcdalt[i] = va;
+            const bool clip = (c0 > AMZ_CLIP8) | (Gintvha > AMZ_CLIP8) | (Ginthha > AMZ_CLIP8);
+            if (clip) { guar = guha; gdar = gdha; glar = glha; grar = grha; }
+            W.vcd[i] = clip ? va : sgn * ((vwt * gdar + (1.0f - vwt) * guar) - c0);
+            W.hcd[i] = clip ? ha : sgn * ((hwt * grar + (1.0f - hwt) * glar) - c0);
+            W.dgintv[i] = vmin(sq(guha - gdha), sq(guar - gdar));
+            W.dginth[i] = vmin(sq(glha - grha), sq(glar - grar));
+        }
+        const int nrow8 = rr1 - 16;
+        for (int par = 0; par < 2; par++) {                               // rows of one parity share a site count
+            const int ns = 4 * cdiv(cc1 - 16 - par, 8), nr = (nrow8 + 1 - par) / 2;      // rows 8+par, 10+par, ...
+            for (int idx = tid; idx < nr * ns; idx += nthr) {
+                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+                const float c0 = cfa[i];
+                float t1, t2, w;
+                t1 = cfa[i + M1]; t2 = cfa[i + M2];
+                float rbse = (t1 + t1) / (AMZ_EPS + c0 + t2);
+                rbse = ab(1.0f - rbse) < AMZ_ARTHRESH ? c0 * rbse : t1 + 0.5f * (c0 - t2);
+                t1 = cfa[i - M1]; t2 = cfa[i - M2];
+                float rbnw = (t1 + t1) / (AMZ_EPS + c0 + t2);
+                rbnw = ab(1.0f - rbnw) < AMZ_ARTHRESH ? c0 * rbnw : t1 + 0.5f * (c0 - t2);
+                t1 = AMZ_EPS + W.delm[i1];
+                const float wtse = t1 + W.delm[(i + M1) >> 1] + W.delm[(i + M2) >> 1], wtnw = t1 + W.delm[(i - M1) >> 1] + W.delm[(i - M2) >> 1];
+                const float m = (wtse * rbnw + wtnw * rbse) / (wtse + wtnw);
+                t1 = ulimv(m, cfa[i - M1], cfa[i + M1]);
+                w = 2.0f * (c0 - m) / (AMZ_EPS + m + c0);
+                t2 = w * m + (1.0f - w) * t1;
+                t2 = (m + m < c0) ? t1 : t2;
+                t2 = (m < c0) ? t2 : m;
+                W.rbm[i1] = t2 > AMZ_CLIP ? ulimv(t2, cfa[i - M1], cfa[i + M1]) : t2;
+
+                t1 = cfa[i + P1]; t2 = cfa[i + P2];
+                float rbne = (t1 + t1) / (AMZ_EPS + c0 + t2);
+                rbne = ab(1.0f - rbne) < AMZ_ARTHRESH ? c0 * rbne : t1 + 0.5f * (c0 - t2);
+                t1 = cfa[i - P1]; t2 = cfa[i - P2];
+                float rbsw = (t1 + t1) / (AMZ_EPS + c0 + t2);
+                rbsw = ab(1.0f - rbsw) < AMZ_ARTHRESH ? c0 * rbsw : t1 + 0.5f * (c0 - t2);
+                t1 = AMZ_EPS + W.delp[i1];
+                const float wtne = t1 + W.delp[(i + P1) >> 1] + W.delp[(i + P2) >> 1], wtsw = t1 + W.delp[(i - P1) >> 1] + W.delp[(i - P2) >> 1];
+                const float p = (wtne * rbsw + wtsw * rbne) / (wtne + wtsw);
+                t1 = ulimv(p, cfa[i - P1], cfa[i + P1]);
+                w = 2.0f * (c0 - p) / (AMZ_EPS + p + c0);
+                t2 = w * p + (1.0f - w) * t1;
+                t2 = (p + p < c0) ? t1 : t2;
+                t2 = (p < c0) ? t2 : p;
+                W.rbp[i1] = t2 > AMZ_CLIP ? ulimv(t2, cfa[i - P1], cfa[i + P1]) : t2;
+#define AMZ_EVEN8(A) (gausseven[0] * (A[(i - V1) >> 1] + A[(i - 1) >> 1] + A[(i + 1) >> 1] + A[(i + V1) >> 1]) +                 \
+                      gausseven[1] * (A[(i - V2 - 1) >> 1] + A[(i - V2 + 1) >> 1] + A[(i - 2 - V1) >> 1] + A[(i + 2 - V1) >> 1] +  \
+                                      A[(i - 2 + V1) >> 1] + A[(i + 2 + V1) >> 1] + A[(i + V2 - 1) >> 1] + A[(i + V2 + 1) >> 1]))
+                const float rbvarm = AMZ_EPSSQ + AMZ_EVEN8(W.Dgrbsq1m);
+                pmwt[i1] = rbvarm / ((AMZ_EPSSQ + AMZ_EVEN8(W.Dgrbsq1p)) + rbvarm);
+#undef AMZ_EVEN8
+            }
+        }
+    }
+    C.sync();
+
+    // ---- variance-based choice + bounding, in place (:748-803): thread per column, rows in order ----
+    {
+        const int ncol = 4 * cdiv(cc1 - 8, 4);                            // columns 4 .. 4+ncol-1
+        const int cc = 4 + tid, lane = tid & 3;
+        const bool active = tid < ncol;
+        float vup[2] = {0.0f, 0.0f};                                      // updated vcd of rows rr-2 (same parity)
+        for (int rr = 4; rr < rr1 - 4; rr++) {
+            const int i = rr * TS + cc, buf = rr & 1;
+            float h = 0.0f, v = 0.0f, c0 = 0.0f, sgn = 1.0f, hm2 = 0.0f, h0 = 0.0f, hp2 = 0.0f, havar = 0.0f, ha = 0.0f;
+            if (active) {
+                sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
+                c0 = cfa[i];
+                h0 = W.hcd[i]; hm2 = W.hcd[i - 2]; hp2 = W.hcd[i + 2];
+                ha = W.hcdalt[i];
+                havar = var3(W.hcdalt[i - 2], ha, W.hcdalt[i + 2]);
+                h = (havar < var3(hm2, h0, hp2)) ? ha : h0;
+                h = bound_cd(h, c0, cfa[i - 1], cfa[i + 1], sgn);
+                const float v0 = W.vcd[i], vm2 = rr >= 6 ? vup[rr & 1] : W.vcd[i - V2], vp2 = W.vcd[i + V2];
+                const float va = W.vcdalt[i];
+                v = (var3(W.vcdalt[i - V2], va, W.vcdalt[i + V2]) < var3(vm2, v0, vp2)) ? va : v0;
+                v = bound_cd(v, c0, cfa[i - V1], cfa[i + V1], sgn);
+                vup[rr & 1] = v;
+                if (lane >= 2) S.row[buf][tid] = h;
+            }
+            C.sync();
+            if (active) {
+                if (lane < 2 && tid >= 2) {                               // left neighbour is lane 2/3 of the previous vector: updated
+                    const float hm2u = S.row[buf][tid - 2];
+                    h = (havar < var3(hm2u, h0, hp2)) ? ha : h0;
+                    h = bound_cd(h, c0, cfa[i - 1], cfa[i + 1], sgn);
+                }
+                W.hcd[i] = h; W.vcd[i] = v;
+                W.cddiffsq[i] = sq(v - h);
+            }
+        }
+    }
+    C.sync();
+
+    // ---- H/V weight (:876-920) and Nyquist texture test (:967-996) ----
+    for (int par = 0; par < 2; par++) {
+        const int ns = 4 * cdiv(cc1 - 12 - par, 8), nr = (rr1 - 12 + 1 - par) / 2;
+        for (int idx = tid; idx < nr * ns; idx += nthr) {
+            const int rr = 6 + par + 2 * (idx / ns), cc = 6 + par + 2 * (idx % ns), i = rr * TS + cc;
+            const float *vcd = W.vcd, *hcd = W.hcd, *d0 = W.dirwts0, *d1 = W.dirwts1;
+            float t = vcd[i];
+            const float uave = t + vcd[i - V1] + vcd[i - V2] + vcd[i - V3], dave = t + vcd[i + V1] + vcd[i + V2] + vcd[i + V3];
+            float Du = sq(t - uave) + sq(vcd[i - V1] - uave) + sq(vcd[i - V2] - uave) + sq(vcd[i - V3] - uave);
+            float Dd = sq(t - dave) + sq(vcd[i + V1] - dave) + sq(vcd[i + V2] - dave) + sq(vcd[i + V3] - dave);
+            const float hwt = d1[i - 1] / (d1[i - 1] + d1[i + 1]);
+            const float vwt = d0[i - V1] / (d0[i + V1] + d0[i - V1]);
+            t = hcd[i];
+            const float lave = t + hcd[i - 1] + hcd[i - 2] + hcd[i - 3], rave = t + hcd[i + 1] + hcd[i + 2] + hcd[i + 3];
+            float Dl = sq(t - lave) + sq(hcd[i - 1] - lave) + sq(hcd[i - 2] - lave) + sq(hcd[i - 3] - lave);
+            float Dr = sq(t - rave) + sq(hcd[i + 1] - rave) + sq(hcd[i + 2] - rave) + sq(hcd[i + 3] - rave);
+            const float vcdvar = AMZ_EPSSQ + vwt * Dd + (1.0f - vwt) * Du, hcdvar = AMZ_EPSSQ + hwt * Dr + (1.0f - hwt) * Dl;
+            Du = W.dgintv[i] + W.dgintv[i - V1] + W.dgintv[i - V2];
+            Dd = W.dgintv[i] + W.dgintv[i + V1] + W.dgintv[i + V2];
+            Dl = W.dginth[i] + W.dginth[i - 1] + W.dginth[i - 2];
+            Dr = W.dginth[i] + W.dginth[i + 1] + W.dginth[i + 2];
+            const float vcdvar1 = AMZ_EPSSQ + vwt * Dd + (1.0f - vwt) * Du, hcdvar1 = AMZ_EPSSQ + hwt * Dr + (1.0f - hwt) * Dl;
+            const float varwt = hcdvar / (vcdvar + hcdvar), diffwt = hcdvar1 / (vcdvar1 + hcdvar1);
+            const bool dec = ((0.5f - varwt) * (0.5f - diffwt) > 0.0f) & (ab(0.5f - diffwt) < ab(0.5f - varwt));
+            hvwt[i >> 1] = dec ? varwt : diffwt;
+        }
+        const int nq = cdiv(cc1 - 12 - par, 2);
+        for (int idx = tid; idx < nr * nq; idx += nthr) {
+            const int rr = 6 + par + 2 * (idx / nq), cc = 6 + par + 2 * (idx % nq), i = rr * TS + cc;
+            const float *q = W.cddiffsq, *d = W.delhvsqsum;
+            float nyqtest = (gaussodd[0] * q[i] + gaussodd[1] * (q[i - M1] + q[i + P1] + q[i - P1] + q[i + M1]) +
+                             gaussodd[2] * (q[i - V2] + q[i - 2] + q[i + 2] + q[i + V2]) +
+                             gaussodd[3] * (q[i - M2] + q[i + P2] + q[i - P2] + q[i + M2]));
+            nyqtest -= 0.5f * (gaussgrad[0] * d[i] + gaussgrad[1] * (d[i - V1] + d[i + 1] + d[i - 1] + d[i + V1]) +
+                               gaussgrad[2] * (d[i - M1] + d[i + P1] + d[i - P1] + d[i + M1]) +
+                               gaussgrad[3] * (d[i - V2] + d[i - 2] + d[i + 2] + d[i + V2]) +
+                               gaussgrad[4] * (d[i - 2 * TS - 1] + d[i - 2 * TS + 1] + d[i - TS - 2] + d[i - TS + 2] +
+                                               d[i + TS - 2] + d[i + TS + 2] + d[i + 2 * TS - 1] + d[i + 2 * TS + 1]) +
+                               gaussgrad[5] * (d[i - M2] + d[i + P2] + d[i - P2] + d[i + M2]));
+            if (nyqtest > 0) { nyquist[i >> 1] = 1; C.atomic_add(&S.rowcnt[rr], 1); C.atomic_add(&S.anynyq, 1); }
+        }
+    }
+    C.sync();
+    const bool anynyq = S.anynyq != 0;                                    // block-uniform
+
+    if (anynyq) {
+        // ---- 3x3 vote, raster-sequential and in place (:998-1010) ----
+        for (int rr = 8; rr < rr1 - 8; rr++) {
+            if (S.rowcnt[rr - 2] + S.rowcnt[rr - 1] + S.rowcnt[rr] + S.rowcnt[rr + 1] + S.rowcnt[rr + 2] == 0) continue;   // stays all zero
+            const int par = fc(rr, 2) & 1, ns = cdiv(cc1 - 16 - par, 2);
+            for (int k = tid; k < ns; k += nthr) {
+                const int i = rr * TS + 8 + par + 2 * k;
+                S.oth[k] = nyquist[(i - V2) >> 1] + nyquist[(i - M1) >> 1] + nyquist[(i + P1) >> 1] + nyquist[(i + 2) >> 1] +
+                           nyquist[(i - P1) >> 1] + nyquist[(i + M1) >> 1] + nyquist[(i + V2) >> 1];
+                S.old[k] = nyquist[i >> 1];
+            }
+            C.sync();
+            if (tid == 0) {
+                int x = nyquist[(rr * TS + 8 + par - 2) >> 1], cnt = 0;
+                for (int k = 0; k < ns; k++) {
+                    const int n = S.oth[k] + S.old[k] + x;
+                    x = n > 4 ? 1 : (n < 4 ? 0 : S.old[k]);
+                    nyquist[(rr * TS + 8 + par + 2 * k) >> 1] = (unsigned char)x;
+                    cnt += x;
+                }
+                // cells of this row outside the voted range keep their test result
+                const int i0 = rr * TS;
+                for (int c2 = 6 + par; c2 < 8 + par; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
+                for (int c2 = 8 + par + 2 * ns; c2 < cc1 - 6; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
+                S.rowcnt[rr] = cnt;
+            }
+            C.sync();
+        }
+        // ---- area interpolation inside Nyquist regions (:1016-1045) ----
+        for (int par = 0; par < 2; par++) {
+            const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
+            for (int idx = tid; idx < nr * ns; idx += nthr) {
+                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+                if (!nyquist[i >> 1]) continue;
+                float sumh = 0, sumv = 0, sumsqh = 0, sumsqv = 0, areawt = 0;
+                for (int a = -6; a < 7; a += 2)
+                    for (int b = -6; b < 7; b += 2) {
+                        const int j = (rr + a) * TS + cc + b;
+                        if (!nyquist[j >> 1]) continue;
+                        sumh += cfa[j] - expdec(cfa[j - 1] + cfa[j + 1], 1);
+                        sumv += cfa[j] - expdec(cfa[j - V1] + cfa[j + V1], 1);
+                        sumsqh += expdec(sq(cfa[j] - cfa[j - 1]) + sq(cfa[j] - cfa[j + 1]), 1);
+                        sumsqv += expdec(sq(cfa[j] - cfa[j - V1]) + sq(cfa[j] - cfa[j + V1]), 1);
+                        areawt += 1;
+                    }
+                const float hv = AMZ_EPSSQ + ab(areawt * sumsqh - sumh * sumh), vv = AMZ_EPSSQ + ab(areawt * sumsqv - sumv * sumv);
+                hvwt[i >> 1] = hv / (vv + hv);
+            }
+        }
+        C.sync();
+    }
+
+    // ---- hvwt refinement from the diagonal neighbours, row after row (:1054-1058), then
+    //      pmwt refinement + R+B estimate the same way (:1264-1274); both through the shared row buffer ----
+    for (int pass = 0; pass < 2; pass++) {
+        float *const P = pass ? pmwt : hvwt;
+        const int r0 = pass ? 10 : 8;
+        for (int k = tid; k < TSH; k += nthr) S.row[(r0 - 1) & 1][k] = P[(r0 - 1) * TSH + k];
+        C.sync();
+        for (int rr = r0; rr < rr1 - r0; rr++) {
+            const int par = fc(rr, 2) & 1;
+            // processed sites: scalar bound for hvwt, whole 4-site vectors for pmwt
+            const int ns = pass ? 4 * cdiv(cc1 - 20 - par, 8) : cdiv(cc1 - 16 - par, 2);
+            const int k0 = (r0 + par) >> 1;                                // half index of the first processed site
+            const float *prev = S.row[(rr - 1) & 1];
+            float *cur = S.row[rr & 1];
+            for (int k = tid; k < TSH; k += nthr) {
+                float t = P[rr * TSH + k];
+                if (k >= k0 && k < k0 + ns) {
+                    // diagonal neighbours: previous row (updated) at half indices k-1+par, k+par; next row (original)
+                    const float ul = prev[k - 1 + par], ur = prev[k + par];
+                    const float dl = P[(rr + 1) * TSH + k - 1 + par], dr = P[(rr + 1) * TSH + k + par];
+                    const float s4 = ul + ur + dl + dr;
+                    const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
+                    t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
+                    P[rr * TSH + k] = t;
+                    if (pass) {
+                        const int i = rr * TS + 2 * k + par;
+                        W.rbint[rr * TSH + k] = 0.5f * (cfa[i] + W.rbm[rr * TSH + k] * (1.0f - t) + W.rbp[rr * TSH + k] * t);
+                    }
+                }
+                cur[k] = t;
+            }
+            C.sync();
+        }
+        if (pass) break;
+        // ---- G at R/B sites with the final hvwt (:1063-1074) ----
+        for (int par = 0; par < 2; par++) {
+            const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
+            for (int idx = tid; idx < nr * ns; idx += nthr) {
+                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+                const float d = W.hcd[i] * (1.0f - hvwt[i1]) + W.vcd[i] * hvwt[i1];
+                W.Dgrb0[i1] = d;
+                const float g = cfa[i] + d;
+                rgbgreen[i] = g;
+                if (anynyq && nyquist[i1]) {
+                    W.Dgrb2[2 * i1] = sq(g - expdec(rgbgreen[i - 1] + rgbgreen[i + 1], 1));
+                    W.Dgrb2[2 * i1 + 1] = sq(g - expdec(rgbgreen[i - V1] + rgbgreen[i + V1], 1));
+                } else
+                    W.Dgrb2[2 * i1] = W.Dgrb2[2 * i1 + 1] = 0.0f;
+            }
+        }
+        C.sync();
+        // ---- refine Nyquist sites with the local G curvature (:1085-1102) ----
+        if (anynyq) {
+#define AMZ_D2H(k) W.Dgrb2[2 * ((k) >> 1)]
+#define AMZ_D2V(k) W.Dgrb2[2 * ((k) >> 1) + 1]
+            for (int par = 0; par < 2; par++) {
+                const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
+                for (int idx = tid; idx < nr * ns; idx += nthr) {
+                    const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+                    if (!nyquist[i >> 1]) continue;
+                    const float gvarh = AMZ_EPSSQ + (gquinc[0] * AMZ_D2H(i) + gquinc[1] * (AMZ_D2H(i - M1) + AMZ_D2H(i + P1) + AMZ_D2H(i - P1) + AMZ_D2H(i + M1)) +
+                                                     gquinc[2] * (AMZ_D2H(i - V2) + AMZ_D2H(i - 2) + AMZ_D2H(i + 2) + AMZ_D2H(i + V2)) +
+                                                     gquinc[3] * (AMZ_D2H(i - M2) + AMZ_D2H(i + P2) + AMZ_D2H(i - P2) + AMZ_D2H(i + M2)));
+                    const float gvarv = AMZ_EPSSQ + (gquinc[0] * AMZ_D2V(i) + gquinc[1] * (AMZ_D2V(i - M1) + AMZ_D2V(i + P1) + AMZ_D2V(i - P1) + AMZ_D2V(i + M1)) +
+                                                     gquinc[2] * (AMZ_D2V(i - V2) + AMZ_D2V(i - 2) + AMZ_D2V(i + 2) + AMZ_D2V(i + V2)) +
+                                                     gquinc[3] * (AMZ_D2V(i - M2) + AMZ_D2V(i + P2) + AMZ_D2V(i - P2) + AMZ_D2V(i + M2)));
+                    const float d = (W.hcd[i] * gvarv + W.vcd[i] * gvarh) / (gvarv + gvarh);
+                    W.Dgrb0[i >> 1] = d;
+                    rgbgreen[i] = cfa[i] + d;
+                }
+            }
+#undef AMZ_D2H
+#undef AMZ_D2V
+            C.sync();
+        }
+    }
+
+    // ---- where the diagonal estimate discriminates better, redo G from R+B (:1287-1352) ----
+    for (int par = 0; par < 2; par++) {
+        const int ns = cdiv(cc1 - 24 - par, 2), nr = (rr1 - 24 + 1 - par) / 2;
+        for (int idx = tid; idx < nr * ns; idx += nthr) {
+            const int rr = 12 + par + 2 * (idx / ns), cc = 12 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+            if (ab(0.5f - pmwt[i1]) < ab(0.5f - hvwt[i1])) continue;
+            const float *rbint = W.rbint, *d0 = W.dirwts0, *d1 = W.dirwts1;
+            const float rb = rbint[i1];
+            const float cru = (float)((double)cfa[i - V1] * 2.0 / (double)(AMZ_EPS + rb + rbint[i1 - V1]));
+            const float crd = (float)((double)cfa[i + V1] * 2.0 / (double)(AMZ_EPS + rb + rbint[i1 + V1]));
+            const float crl = (float)((double)cfa[i - 1] * 2.0 / (double)(AMZ_EPS + rb + rbint[i1 - 1]));
+            const float crr = (float)((double)cfa[i + 1] * 2.0 / (double)(AMZ_EPS + rb + rbint[i1 + 1]));
+            const float gu = ab(1.0f - cru) < AMZ_ARTHRESH ? rb * cru : cfa[i - V1] + expdec(rb - rbint[i1 - V1], 1);
+            const float gd = ab(1.0f - crd) < AMZ_ARTHRESH ? rb * crd : cfa[i + V1] + expdec(rb - rbint[i1 + V1], 1);
+            const float gl = ab(1.0f - crl) < AMZ_ARTHRESH ? rb * crl : cfa[i - 1] + expdec(rb - rbint[i1 - 1], 1);
+            const float gr = ab(1.0f - crr) < AMZ_ARTHRESH ? rb * crr : cfa[i + 1] + expdec(rb - rbint[i1 + 1], 1);
+            float Gintv = (d0[i - V1] * gd + d0[i + V1] * gu) / (d0[i + V1] + d0[i - V1]);
+            float Ginth = (d1[i - 1] * gr + d1[i + 1] * gl) / (d1[i - 1] + d1[i + 1]);
+            if (Gintv < rb) {
+                if (2 * Gintv < rb)
+                    Gintv = ulims(Gintv, cfa[i - V1], cfa[i + V1]);
+                else {
+                    const float vw = (float)(2.0 * (double)(rb - Gintv) / (double)(AMZ_EPS + Gintv + rb));
+                    Gintv = vw * Gintv + (1.0f - vw) * ulims(Gintv, cfa[i - V1], cfa[i + V1]);
+                }
+            }
+            if (Ginth < rb) {
+                if (2 * Ginth < rb)
+                    Ginth = ulims(Ginth, cfa[i - 1], cfa[i + 1]);
+                else {
+                    const float hw = (float)(2.0 * (double)(rb - Ginth) / (double)(AMZ_EPS + Ginth + rb));
+                    Ginth = hw * Ginth + (1.0f - hw) * ulims(Ginth, cfa[i - 1], cfa[i + 1]);
+                }
+            }
+            if (Ginth > AMZ_CLIP) Ginth = ulims(Ginth, cfa[i - 1], cfa[i + 1]);
+            if (Gintv > AMZ_CLIP) Gintv = ulims(Gintv, cfa[i - V1], cfa[i + V1]);
+            const float g = Ginth * (1.0f - hvwt[i1]) + Gintv * hvwt[i1];
+            rgbgreen[i] = g;
+            W.Dgrb0[i1] = g - cfa[i];
+        }
+    }
+    C.sync();
+
+    // ---- split G-B out of the G-R plane at the B sites (:1358-1362) ----
+    {
+        const int nr = cdiv(rr1 - 12 - 13, 2), ns = cdiv(cc1 - 12 - 13, 2);
+        for (int idx = tid; idx < nr * ns; idx += nthr) {
+            const int rr = 13 + 2 * (idx / ns), cc = 13 + 2 * (idx % ns), i1 = (rr * TS + cc) >> 1;
+            W.Dgrb1[i1] = W.Dgrb0[i1];
+            W.Dgrb0[i1] = 0.0f;
+        }
+    }
+    C.sync();
+
+    // ---- chroma at the opposite-colour sites from the four diagonal neighbours (:1369-1383) ----
+    for (int par = 0; par < 2; par++) {
+        const int ns = 4 * cdiv(cc1 - 28 - par, 8), nr = (rr1 - 28 + 1 - par) / 2;
+        float *const D = par ? W.Dgrb0 : W.Dgrb1;                          // c = 1 - FC/2: R rows fill G-B, B rows fill G-R
+        for (int idx = tid; idx < nr * ns; idx += nthr) {
+            const int rr = 14 + par + 2 * (idx / ns), cc = 14 + par + 2 * (idx % ns), i = rr * TS + cc;
+#define AMZ_G(o) D[(i + (o)) >> 1]
+            const float wtnw = 1.0f / (AMZ_EPS + ab(AMZ_G(-M1) - AMZ_G(M1)) + ab(AMZ_G(-M1) - AMZ_G(-M3)) + ab(AMZ_G(M1) - AMZ_G(-M3)));
+            const float wtne = 1.0f / (AMZ_EPS + ab(AMZ_G(P1) - AMZ_G(-P1)) + ab(AMZ_G(P1) - AMZ_G(P3)) + ab(AMZ_G(-P1) - AMZ_G(P3)));
+            const float wtsw = 1.0f / (AMZ_EPS + ab(AMZ_G(-P1) - AMZ_G(P1)) + ab(AMZ_G(-P1) - AMZ_G(M3)) + ab(AMZ_G(P1) - AMZ_G(-P3)));
+            const float wtse = 1.0f / (AMZ_EPS + ab(AMZ_G(M1) - AMZ_G(-M1)) + ab(AMZ_G(M1) - AMZ_G(-P3)) + ab(AMZ_G(-M1) - AMZ_G(M3)));
+            D[i >> 1] = (wtnw * (1.325f * AMZ_G(-M1) - 0.175f * AMZ_G(-M3) - 0.075f * AMZ_G(-M1 - 2) - 0.075f * AMZ_G(-M1 - V2)) +
+                         wtne * (1.325f * AMZ_G(P1) - 0.175f * AMZ_G(P3) - 0.075f * AMZ_G(P1 + 2) - 0.075f * AMZ_G(P1 + V2)) +
+                         wtsw * (1.325f * AMZ_G(-P1) - 0.175f * AMZ_G(-P3) - 0.075f * AMZ_G(-P1 - 2) - 0.075f * AMZ_G(-P1 - V2)) +
+                         wtse * (1.325f * AMZ_G(M1) - 0.175f * AMZ_G(M3) - 0.075f * AMZ_G(M1 + 2) - 0.075f * AMZ_G(M1 + V2))) /
+                        (wtnw + wtne + wtsw + wtse);
+#undef AMZ_G
+        }
+    }
+    C.sync();
+
+    // ---- write red, blue (:1400-1445) and green (:1451-1455) ----
+    {
+        const int nc = cc1 - 32, nrow = rr1 - 32;
+        for (int idx = tid; idx < nrow * nc; idx += nthr) {
+            const int rr = 16 + idx / nc, cc = 16 + idx % nc, i = rr * TS + cc;
+            const size_t o = (size_t)(rr + top) * stride + cc + left;
+            const bool is_green = ((rr + cc) & 1) != 0;
+            const float g = rgbgreen[i];
+            if (is_green) {
+                const float wu = hvwt[(i - V1) >> 1], wr = 1.0f - hvwt[(i + 1) >> 1], wl = 1.0f - hvwt[(i - 1) >> 1], wd = hvwt[(i + V1) >> 1];
+                const float temp = 1.0f / (wu + wr + wl + wd);
+                red[o] = 65535.0f * (g - (wu * W.Dgrb0[(i - V1) >> 1] + wr * W.Dgrb0[(i + 1) >> 1] + wl * W.Dgrb0[(i - 1) >> 1] + wd * W.Dgrb0[(i + V1) >> 1]) * temp);
+                blue[o] = 65535.0f * (g - (wu * W.Dgrb1[(i - V1) >> 1] + wr * W.Dgrb1[(i + 1) >> 1] + wl * W.Dgrb1[(i - 1) >> 1] + wd * W.Dgrb1[(i + V1) >> 1]) * temp);
+            } else {
+                red[o] = 65535.0f * (g - W.Dgrb0[i >> 1]);
+                blue[o] = 65535.0f * (g - W.Dgrb1[i >> 1]);
+            }
+        }
+        const int ng = 4 * cdiv(cc1 - 35, 4);
+        for (int idx = tid; idx < nrow * ng; idx += nthr) {
+            const int rr = 16 + idx / ng, cc = 16 + idx % ng;
+            green[(size_t)(rr + top) * stride + cc + left] = rgbgreen[rr * TS + cc] * 65535.0f;
+        }
+    }
+}
+
+}  // namespace amaze

@@ -142,7 +142,7 @@ int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, con
                          size_t frame_stride, int nframes, int skip_chroma, int skip_pixfix, cudaStream_t st);
 
 // dualiso.cu
-size_t dual_iso_scratch_bytes(int w, int h);
+size_t dual_iso_scratch_bytes(int w, int h, int interp_method);
 int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, int interp_method,
                  int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st);
 void dual_iso_reset_tables(mlvb_context *ctx);

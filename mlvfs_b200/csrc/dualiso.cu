@@ -1,4 +1,4 @@
-// dualiso.cu -- full dual-ISO conversion ("cr2hdr 20-bit"), mean23 interpolation path.
+// dualiso.cu -- full dual-ISO conversion ("cr2hdr 20-bit"), both interpolation methods.
 //
 // Replaces reference hdr.c:1932-1957 (cr2hdr20_convert_data) and hdr_interpolate hdr.c:1774-1930 with
 // its stages: hdr_check :407, identify_rggb_or_gbrg :441, identify_bright_and_dark_fields :497,
@@ -6,7 +6,8 @@
 // mean32_interpolate :1231 (mean2/mean3 :341-368), border_interpolate :1306, fullres_reconstruction
 // :1355, mix_images :1524, hdr_chroma_smooth :1502 (kernel in chroma.cu), build_alias_map :1382,
 // final_blend :1663, convert_20_to_16bit :1760.  The AMaZE + edge-directed interpolation
-// (hdr.c:917-1229, amaze_demosaic_RT.c) is NOT built yet: interp_method 0 fails loudly.
+// (amaze_interpolate hdr.c:954-1229, amaze_demosaic_RT.c) lives in amaze.cu / amaze_tile.cuh; its last
+// step (edge_interp :940-952, :1182-1210) is fused into this file's per-pixel interpolation kernel.
 //
 // Structure: three frame-global statistics barriers (row-field detection -> white levels -> exposure
 // matching), each a histogram / selection kernel plus a tiny scalar epilogue on the host (the same
@@ -21,6 +22,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "amaze.cuh"
 #include "context.cuh"
 
 namespace {
@@ -164,6 +166,8 @@ struct PixParams {
     const int *raw2ev;                                // 20-bit tables (hdr.c:839-874)
     const int *ev2raw;                                // pointer pre-offset by 10 EV
     int use_fullres, use_alias;
+    int method;                                       // 0 AMaZE + edge-directed, 1 mean23 (hdr.c:1888-1896)
+    AmazeView amz;
 };
 
 // 14 -> 20 bit (hdr.c:825-837) + exposure matching apply (hdr.c:784-808)
@@ -188,7 +192,8 @@ __device__ __forceinline__ int mean3_ev(int a, int b, int c, int white)
     return (a >= white || b >= white || c >= white) ? max(m, white) : m;
 }
 
-// mean32_interpolate + border_interpolate + fullres_reconstruction, one thread per pixel
+// mean32_interpolate (or the edge-directed interpolation of amaze_interpolate, hdr.c:1182-1210) +
+// border_interpolate + fullres_reconstruction, one thread per pixel
 __global__ void diso_interp_kernel(const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark, uint32_t *__restrict__ bright,
                                    uint32_t *__restrict__ fullres, const PixParams P)
 {
@@ -203,7 +208,16 @@ __global__ void diso_interp_kernel(const uint32_t *__restrict__ raw32, uint32_t 
     else if (y >= 2 && x >= w - 3) { interp = R(x - 2, y - 2); native = R(x - 2, y); }
     else if (y >= h - 4) { interp = R(x, y - 2); native = R(x, y); }
     else if (y < 3) { interp = R(x, y + 2); native = R(x, y); }
-    else {
+    else if (P.method == 0) {
+        // edge-directed: average three neighbouring directions in EV space (hdr.c:1198-1206)
+        const int s = (P.is_bright[y % 4] == P.is_bright[(y + 1) % 4]) ? -1 : 1;
+        const int dir = P.amz.edir[x + (size_t)y * w];
+        const int pi0 = amz_edge_interp(P.amz, P.raw2ev, dir, x, y, s, P.black);
+        const int pip = amz_edge_interp(P.amz, P.raw2ev, min(dir + 1, 10), x, y, s, P.black);
+        const int pim = amz_edge_interp(P.amz, P.raw2ev, max(dir - 1, 0), x, y, s, P.black);
+        interp = (uint32_t)__ldg(P.ev2raw + (2 * pi0 + pip + pim) / 4);
+        native = R(x, y);
+    } else {
         // mean23 interior (hdr.c:1255-1299); pairs start at even x
         const int white = !br ? P.white_darkened : P.white;
         const int wev = __ldg(P.raw2ev + white);
@@ -444,12 +458,14 @@ struct DisoScratch {        // carved out of the slot's aux buffer
     uint32_t *raw32, *dark, *bright, *fullres, *halfres, *frs, *hrs;
     uint16_t *over, *over2, *amap, *aux;
     uint8_t *skip;
+    AmazeScratch amz;
 };
 
 constexpr int HB = 65536 + 8;
 
-size_t carve(uint8_t *base, size_t npix, size_t ngrid, DisoScratch *S)
+size_t carve(uint8_t *base, int w, int h, int interp_method, DisoScratch *S)
 {
+    const size_t npix = (size_t)w * h, ngrid = (size_t)((w + 2) / 3 + 1) * ((h + 2) / 3 + 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { void *p = base ? base + o : nullptr; o += (bytes + 255) & ~(size_t)255; return p; };
     DisoScratch s;
@@ -466,16 +482,17 @@ size_t carve(uint8_t *base, size_t npix, size_t ngrid, DisoScratch *S)
     s.over = (uint16_t *)take(npix * 2); s.over2 = (uint16_t *)take(npix * 2);
     s.amap = (uint16_t *)take(npix * 2); s.aux = (uint16_t *)take(npix * 2);
     s.skip = (uint8_t *)take(npix);
+    memset(&s.amz, 0, sizeof(s.amz));
+    if (interp_method == 0) o += amaze_scratch_bytes(w, h, &s.amz, base ? base + o : nullptr);
     if (S) *S = s;
     return o;
 }
 
 }  // namespace
 
-size_t dual_iso_scratch_bytes(int w, int h)
+size_t dual_iso_scratch_bytes(int w, int h, int interp_method)
 {
-    const size_t ngrid = (size_t)((w + 2) / 3 + 1) * ((h + 2) / 3 + 1);
-    return carve(nullptr, (size_t)w * h, ngrid, nullptr);
+    return carve(nullptr, w, h, interp_method, nullptr);
 }
 
 // Per-context dual-ISO tables: the 20-bit EV LUTs keyed by black like the reference's statics (built
@@ -515,11 +532,11 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
                         int use_alias_map, int cs_method, void *d_aux, cudaStream_t st)
 {
     if (w <= 0 || h <= 0) return 0;
-    if (interp_method == 0) {
-        fprintf(stderr, "libmlvfs_b200: dual ISO --amaze-edge is not implemented yet (use --mean23)\n");
+    if (w < 16 || h < 16 || (w & 1)) return MLVB_ERR_UNSUPPORTED;
+    if (interp_method == 0 && (w & 3)) {
+        fprintf(stderr, "libmlvfs_b200: dual ISO --amaze-edge needs a width that is a multiple of 4 (use --mean23)\n");
         return MLVB_ERR_UNSUPPORTED;
     }
-    if (w < 16 || h < 16 || (w & 1)) return MLVB_ERR_UNSUPPORTED;
     DualIsoTables *T = tables_of(ctx);
     {
         std::lock_guard<std::mutex> lk(T->mu);
@@ -536,7 +553,8 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
 
     const size_t npix_full = (size_t)w * h;
     DisoScratch D;
-    carve((uint8_t *)d_aux, npix_full, (size_t)((w + 2) / 3 + 1) * ((h + 2) / 3 + 1), &D);
+    carve((uint8_t *)d_aux, w, h, interp_method, &D);
+    (void)npix_full;
 
     // ---------------- phase A
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
@@ -679,6 +697,19 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     const dim3 g2(ceil_div(w, 256), h);
     const int g1 = ceil_div(np, 256);
     diso_to20_kernel<<<g2, 256, 0, st>>>(d_img, D.raw32, P);
+    P.method = interp_method ? 1 : 0;
+    if (P.method == 0) {
+        // the GBRG row skip changed h after the scratch was carved for the full frame: re-carve the AMaZE part
+        // for this geometry inside the same region (never larger than the full-frame request)
+        AmazeScratch A;
+        amaze_scratch_bytes(w, h, &A, (uint8_t *)D.amz.rawf);
+        int nl = 0;
+        const int rc = launch_amaze_stage(D.raw32, w, h, black, white_darkened, F.is_bright, P.raw2ev, A, st, &nl);
+        if (rc) return rc;
+        ctx->launches += nl;
+        P.amz.red = A.red; P.amz.green = A.green; P.amz.blue = A.blue; P.amz.squeezed = A.squeezed; P.amz.edir = A.edir;
+        P.amz.ws = w + 16;
+    }
     diso_interp_kernel<<<g2, 256, 0, st>>>(D.raw32, D.dark, D.bright, D.fullres, P);
     diso_mix_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
     ctx->launches += 3;
@@ -718,15 +749,11 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
                  int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st)
 {
     if (g.black > MLVB_MAX_BLACK) return 0;
-    if (interp_method == 0) {
-        fprintf(stderr, "libmlvfs_b200: dual ISO --amaze-edge is not implemented yet (use --mean23)\n");
-        return MLVB_ERR_UNSUPPORTED;
-    }
     DualIsoTables *T = tables_of(ctx);
     (void)T;
     // hdr_check needs the statistics of the untouched frame: run phase A's reduction once here
     DisoScratch D;
-    carve((uint8_t *)d_aux, g.npix, (size_t)((g.w + 2) / 3 + 1) * ((g.h + 2) / 3 + 1), &D);
+    carve((uint8_t *)d_aux, g.w, g.h, interp_method, &D);
     {
         std::lock_guard<std::mutex> lk(T->mu);
         if (!T->d_raw2evf) {
@@ -819,7 +846,7 @@ int cr2hdr20_convert_data(struct frame_headers *frame_headers, uint16_t *image_d
     cudaSetDevice(ctx->device);
     int ret = 0;
     if (slot_reserve(*s, 16, g.npix * 2) == MLVB_OK &&
-        reserve_device(&s->d_aux, &s->aux_cap, dual_iso_scratch_bytes(g.w, g.h)) == MLVB_OK &&
+        reserve_device(&s->d_aux, &s->aux_cap, dual_iso_scratch_bytes(g.w, g.h, interp_method)) == MLVB_OK &&
         cudaMemcpyAsync(s->d_a, image_data, g.npix * 2, cudaMemcpyHostToDevice, s->stream) == cudaSuccess) {
         const int rc = run_cr2hdr20(ctx, frame_headers, g, s->d_a, interp_method, fullres, use_alias_map, chroma_smooth,
                                     fix_bad_pixels_mode, s->d_aux, s->stream);
