@@ -56,7 +56,7 @@ WORKLOADS = {
                kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)"),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,
                desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=64,
-               kernel="lj92_decode_kernel (serial Huffman per frame, one warp per frame)"),
+               kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + wavefront prediction + untile, 10 launches)"),
 }
 METRIC = "DNG frames/sec per B200 and at 1/2/4/8 GPUs; achieved HBM GB/s vs peak"   # BASELINE.json metric
 

@@ -92,15 +92,15 @@ namespace {
 // Decode the VIDF payload into unpacked 16-bit frames at d_frames (main.c:569-706 dispatch).
 int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, const void *d_payload,
                    size_t payload_stride, size_t payload_bytes, uint16_t *d_frames, size_t frame_stride, int nframes,
-                   int *d_status, cudaStream_t st)
+                   int *d_status, void *d_aux, size_t aux_cap, cudaStream_t st)
 {
     const int vc = hdr->file_hdr.videoClass;
     if (vc & MLVB_VIDEO_CLASS_FLAG_LZMA) return MLVB_ERR_UNSUPPORTED;      // legacy codec stays on the CPU side
     if (vc & MLVB_VIDEO_CLASS_FLAG_LJ92) {                                 // main.c:617-681
         StageTimer t(ctx, ST_LJ92, st);
         int rc = launch_lj92_decode(d_payload, payload_stride, payload_bytes, d_frames, frame_stride, g.w, g.h, nframes,
-                                    d_status, st);
-        if (rc == MLVB_OK) ctx->launches += 1;
+                                    d_status, d_aux, aux_cap, st);
+        if (rc > 0) { ctx->launches += rc; rc = MLVB_OK; }
         return rc;
     }
     if (payload_bytes < mlvb_packed_bytes((uint32_t)g.npix, g.bpp)) return MLVB_ERR_ARG;
@@ -115,7 +115,8 @@ int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const Fra
 // on device buffers.  Finished frames end up in d_out.
 int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options &opts, const char *mlv_filename,
                  const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_work, uint16_t *d_out,
-                 size_t frame_stride, int nframes, int *d_status, void *d_aux, cudaStream_t st, mlvb_frame_result *res)
+                 size_t frame_stride, int nframes, int *d_status, void *d_aux, size_t aux_cap, cudaStream_t st,
+                 mlvb_frame_result *res)
 {
     const FrameGeom g = geom_from_headers(hdr);
     if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
@@ -134,7 +135,8 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
                     g.black <= MLVB_MAX_BLACK;
     // without an out-of-place stage the chain can run directly in d_out
     uint16_t *d_a = cs ? d_work : d_out;
-    rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, st);
+    rc = decode_payload(ctx, hdr, g, d_payload, payload_stride, payload_bytes, d_a, frame_stride, nframes, d_status, d_aux,
+                        aux_cap, st);
     if (rc) return rc;
     if (opts.deflicker) {                                                           // main.c:943, 895-906
         int32_t bias[2];
@@ -386,10 +388,11 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
     s->result = mlvb_frame_result();
     *s->h_status = 0;
     const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
-    rc = reserve_device(&s->d_aux, &s->aux_cap, aux_bytes_for(g, *opts));
+    rc = reserve_device(&s->d_aux, &s->aux_cap,
+                        std::max(aux_bytes_for(g, *opts), coded ? lj92_scratch_bytes(payload_bytes, g.npix, 1) : (size_t)0));
     if (rc) return fail(rc);
     rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->d_status,
-                      s->d_aux, s->stream, &s->result);
+                      s->d_aux, s->aux_cap, s->stream, &s->result);
     if (rc == MLVB_OK && coded &&
         cudaMemcpyAsync(s->h_status, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
         rc = MLVB_ERR_CUDA;
@@ -467,10 +470,11 @@ int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr
         MLVB_CUDA_OK(cudaMalloc(&ctx->d_batch_status, sizeof(int) * nframes));
         ctx->batch_status_cap = nframes;
     }
-    rc = reserve_device(&ctx->d_batch_aux, &ctx->batch_aux_cap, aux_bytes_for(g, *opts));
+    rc = reserve_device(&ctx->d_batch_aux, &ctx->batch_aux_cap,
+                        std::max(aux_bytes_for(g, *opts), coded ? lj92_scratch_bytes(payload_bytes, g.npix, nframes) : (size_t)0));
     if (rc) return rc;
     rc = run_pipeline(ctx, hdr, *opts, mlv_filename, d_payload, payload_stride, payload_bytes, (uint16_t *)ctx->d_scratch,
-                      d_out, out_stride_px, nframes, ctx->d_batch_status, ctx->d_batch_aux, st, &res);
+                      d_out, out_stride_px, nframes, ctx->d_batch_status, ctx->d_batch_aux, ctx->batch_aux_cap, st, &res);
     if (rc == MLVB_OK && coded) {
         // a compressed batch reports corrupt streams synchronously (the decode dwarfs the sync)
         std::vector<int> status(nframes);

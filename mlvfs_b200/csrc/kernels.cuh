@@ -46,8 +46,11 @@ int launch_stripes_hist(const uint16_t *d_img, int w, int h, int black, int whit
                         const uint16_t *d_dither, unsigned *d_hist, unsigned *d_num, int *d_median_bin, cudaStream_t st);
 
 // ---- lj92.cu ----
+size_t lj92_scratch_bytes(size_t payload_bytes, size_t npix, int nframes);
+// returns the number of kernels launched (> 0) or a negative MLVB_ERR_* code
 int launch_lj92_decode(const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_out,
-                       size_t out_stride_px, int w, int h, int nframes, int *d_status, cudaStream_t st);
+                       size_t out_stride_px, int w, int h, int nframes, int *d_status, void *d_scratch,
+                       size_t scratch_bytes, cudaStream_t st);
 
 // ---- patternnoise.cu ----
 size_t pattern_noise_scratch_bytes(int w, int h);

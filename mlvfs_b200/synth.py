@@ -174,7 +174,7 @@ def _lj_table():
     return codes, counts, order
 
 
-def lj92_encode_tiled(tiled, depth=14):
+def lj92_encode_tiled(tiled, depth=14, predictor=6):
     """Encode an (already interleaved) uint16 [h, w] image; returns the JPEG stream as uint8."""
     t = np.ascontiguousarray(tiled, dtype=np.int64)
     h, w = t.shape
@@ -182,7 +182,9 @@ def lj92_encode_tiled(tiled, depth=14):
     pred[0, 0] = 1 << (depth - 1)
     pred[0, 1:] = t[0, :-1]
     pred[1:, 0] = t[:-1, 0]
-    pred[1:, 1:] = t[:-1, 1:] + ((t[1:, :-1] - t[:-1, :-1]) >> 1)          # predictor 6
+    a, b, c = t[1:, :-1], t[:-1, 1:], t[:-1, :-1]                           # left, above, above-left
+    pred[1:, 1:] = {1: a, 2: b, 3: c, 4: a + b - c, 5: a + ((b - c) >> 1), 6: b + ((a - c) >> 1),
+                    7: (a + b) >> 1}[predictor]
     diff = (t - pred).reshape(-1)
     mag = np.abs(diff)
     ssss = np.zeros(diff.shape, dtype=np.int64)
@@ -207,14 +209,14 @@ def lj92_encode_tiled(tiled, depth=14):
     if ff.size:                                                             # byte stuffing: 0xFF -> 0xFF 0x00
         body = np.insert(body, ff + 1, 0)
     head = bytearray([0xFF, 0xD8, 0xFF, 0xC3, 0, 11, depth, h >> 8, h & 255, w >> 8, w & 255, 1, 0, 0x11, 0,
-                      0xFF, 0xC4, 0, 19 + 17, 0] + counts + order + [0xFF, 0xDA, 0, 8, 1, 0, 0, 6, 0, 0])
+                      0xFF, 0xC4, 0, 19 + 17, 0] + counts + order + [0xFF, 0xDA, 0, 8, 1, 0, 0, predictor, 0, 0])
     return np.concatenate([np.frombuffer(bytes(head), np.uint8), body, np.array([0xFF, 0xD9], np.uint8)])
 
 
-def lj92_payload(img, depth=14):
+def lj92_payload(img, depth=14, predictor=6):
     """VIDF payload of an LJ92 MLV frame: uint32 decoded size + stream of the interleaved frame."""
     h, w = img.shape
-    stream = lj92_encode_tiled(quadrant_interleave(img), depth)
+    stream = lj92_encode_tiled(quadrant_interleave(img), depth, predictor)
     return np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), stream])
 
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 LJ92 = F.VIDEO_CLASS_RAW | F.VIDEO_CLASS_FLAG_LJ92
 
 
-@pytest.mark.parametrize("w,h", [(640, 360), (352, 98), (64, 34)])
+@pytest.mark.parametrize("w,h", [(640, 360), (352, 98), (64, 34), (72, 38), (1920, 1080)])
 def test_lj92_frame_matches_oracle(fresh_ctx, oracle, w, h):
     hdr = F.make_frame_headers(w, h, video_class=LJ92)
     img = synth.make_frame(w, h, 2, hot_cold=True, bad_density=1e-3)
@@ -22,6 +22,20 @@ def test_lj92_frame_matches_oracle(fresh_ctx, oracle, w, h):
     out, res = fresh_ctx.process_frame(hdr, payload, M.Options(), "lj92.MLV")
     assert res.status == 0
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("predictor,w,h", [(1, 640, 360), (2, 96, 70), (3, 96, 70), (4, 352, 98), (5, 96, 70), (7, 640, 360),
+                                           (6, 70, 38)])
+def test_lj92_wavefront_predictors(fresh_ctx, oracle, predictor, w, h):
+    """Predictors other than 6 (and rasters the separated form does not take: width % 4 != 0) go through the
+    skewed-wavefront kernel; 640x360 spans two blocks of 8 strips, so strips hand over across blocks."""
+    hdr = F.make_frame_headers(w, h, video_class=LJ92)
+    img = synth.make_frame(w, h, predictor, hot_cold=True, bad_density=1e-3)
+    payload = synth.lj92_payload(img, predictor=predictor)
+    want = oracle.lj92_decode_payload(payload, w, h)
+    assert np.array_equal(want, img)
+    out, res = fresh_ctx.process_frame(hdr, payload, M.Options(), "lj92pred.MLV")
+    assert res.status == 0 and np.array_equal(out, want)
 
 
 def test_lj92_reference_encoder_stream(fresh_ctx, oracle, ref):
@@ -79,6 +93,28 @@ def test_lj92_then_corrections_and_batch(fresh_ctx, oracle):
     got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
     for i in range(n):
         assert np.array_equal(got[i], want[i]), i
+
+
+def test_lj92_fixed_length_symbols_still_converge(fresh_ctx, oracle):
+    """Rows of identical +-2 steps: almost every symbol is 5 bits long, so wrong starts re-synchronise late
+    or never; the boundary resolver must still reach the true parse (same case as tests/test_lj92_emu.py)."""
+    w, h = 640, 360
+    hdr = F.make_frame_headers(w, h, video_class=LJ92)
+    row = 8192 + np.cumsum(np.where(np.arange(w) % 2 == 0, 2, -2))
+    tiled = np.tile(row.astype(np.uint16), (h, 1))
+    tiled[::37, ::53] += 3
+    payload = np.concatenate([np.array([w * h * 2], dtype="<u4").view(np.uint8), synth.lj92_encode_tiled(tiled)])
+    want = oracle.lj92_decode_payload(payload, w, h)
+    out, res = fresh_ctx.process_frame(hdr, payload, M.Options(), "lj92fixed.MLV")
+    assert res.status == 0 and np.array_equal(out, want)
+
+
+def test_lj92_truncated_stream_fails_cleanly(fresh_ctx, oracle):
+    w, h = 128, 64
+    hdr = F.make_frame_headers(w, h, video_class=LJ92)
+    payload = oracle.lj92_payload(synth.make_frame(w, h, 0))
+    with pytest.raises(RuntimeError):
+        fresh_ctx.process_frame(hdr, payload[: payload.size // 2].copy(), M.Options(), "cut.MLV")
 
 
 def test_lj92_corrupt_stream_fails_cleanly(fresh_ctx, oracle):
