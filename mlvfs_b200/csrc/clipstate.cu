@@ -71,6 +71,8 @@ PixelList::~PixelList()
 {
     if (d_by_level) cudaFree(d_by_level);
     if (d_level_start) cudaFree(d_level_start);
+    if (d_by_row) cudaFree(d_by_row);
+    if (d_seg_start) cudaFree(d_seg_start);
 }
 
 int PixelList::upload()
@@ -112,7 +114,54 @@ int PixelList::upload()
     MLVB_CUDA_OK(cudaMemcpy(d_by_level, sorted.data(), n * sizeof(PixelXY), cudaMemcpyHostToDevice));
     MLVB_CUDA_OK(cudaMemcpy(d_level_start, level_start.data(), level_start.size() * sizeof(unsigned),
                             cudaMemcpyHostToDevice));
+
+    // Row-wise form for the horizontal interpolator (dual ISO, cs.c:321-328 / 470-478 with dual_iso set):
+    // an entry then reads and writes its own row only, so rows are independent and, inside a row whose
+    // entries come in increasing x, so are runs further than 3 columns apart.  Stable counting sort by y.
+    int ylo = host[0].y, yhi = host[0].y;
+    for (size_t m = 0; m < n; m++) { ylo = std::min(ylo, host[m].y); yhi = std::max(yhi, host[m].y); }
+    const size_t nrows = (size_t)(yhi - ylo) + 1;
+    std::vector<unsigned> row_start(nrows + 1, 0);
+    for (size_t m = 0; m < n; m++) row_start[(size_t)(host[m].y - ylo) + 1]++;
+    for (size_t r = 0; r < nrows; r++) row_start[r + 1] += row_start[r];
+    std::vector<PixelXY> by_row(n);
+    {
+        std::vector<unsigned> cur(row_start.begin(), row_start.end() - 1);
+        for (size_t m = 0; m < n; m++) by_row[cur[(size_t)(host[m].y - ylo)]++] = host[m];
+    }
+    std::vector<unsigned> seg;
+    seg.reserve(n + 1);
+    for (size_t r = 0; r < nrows; r++) {
+        const unsigned lo = row_start[r], hi = row_start[r + 1];
+        if (lo == hi) continue;
+        bool monotone = true;
+        for (unsigned m = lo + 1; m < hi; m++) monotone &= by_row[m].x >= by_row[m - 1].x;
+        seg.push_back(lo);
+        if (monotone)
+            for (unsigned m = lo + 1; m < hi; m++)
+                if (by_row[m].x - by_row[m - 1].x > 3) seg.push_back(m);
+    }
+    nseg = (unsigned)seg.size();
+    seg.push_back((unsigned)n);
+    MLVB_CUDA_OK(cudaMalloc(&d_by_row, n * sizeof(PixelXY)));
+    MLVB_CUDA_OK(cudaMalloc(&d_seg_start, seg.size() * sizeof(unsigned)));
+    MLVB_CUDA_OK(cudaMemcpy(d_by_row, by_row.data(), n * sizeof(PixelXY), cudaMemcpyHostToDevice));
+    MLVB_CUDA_OK(cudaMemcpy(d_seg_start, seg.data(), seg.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     return MLVB_OK;
+}
+
+int apply_pixel_list(mlvb_context *ctx, const PixelList &L, uint16_t *d_img, const FrameGeom &g, size_t frame_stride, int nframes,
+                     int dual_iso, int edge_rules, cudaStream_t st)
+{
+    if (!L.nlevels) return MLVB_OK;
+    if (dual_iso) {
+        ctx->launches += 1;
+        return launch_pixel_fix_rows(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, edge_rules, L.d_by_row,
+                                     L.d_seg_start, L.nseg, ctx->luts, st);
+    }
+    ctx->launches += 1 + (L.nlevels > 1);
+    return launch_pixel_fix(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, 0, edge_rules, L.d_by_level,
+                            L.d_level_start, L.level_start.data(), L.nlevels, ctx->luts, st);
 }
 
 // ------------------------------------------------------------------ geometry

@@ -27,6 +27,11 @@ struct PixelList {
     std::vector<PixelXY> host;             // original (reference) order
     PixelXY *d_by_level = nullptr;         // sorted by level, stable
     unsigned *d_level_start = nullptr;
+    // dual-ISO (horizontal-only) application: entries grouped by row in list order and cut into segments
+    // that cannot see each other (x gap > 3); one thread walks one segment sequentially
+    PixelXY *d_by_row = nullptr;
+    unsigned *d_seg_start = nullptr;
+    unsigned nseg = 0;
     std::vector<unsigned> level_start;     // nlevels + 1 entries
     unsigned nlevels = 0;
     ~PixelList();
@@ -165,6 +170,11 @@ int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const 
                       const uint16_t *d_img, cudaStream_t st, std::shared_ptr<PixelList> *out);
 int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, std::shared_ptr<PixelList> *out);
 int compute_stripes(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, cudaStream_t st, StripeCoef *out);
+
+// apply a pixel list to device frames: level schedule for the 2-D interpolator, independent row segments for
+// the horizontal one (dual ISO); counts the launches
+int apply_pixel_list(mlvb_context *ctx, const PixelList &L, uint16_t *d_img, const FrameGeom &g, size_t frame_stride, int nframes,
+                     int dual_iso, int edge_rules, cudaStream_t st);
 
 // slot lease for the synchronous drop-in entry points (dropin.cu)
 Slot *acquire_slot(mlvb_context *ctx);

@@ -164,10 +164,7 @@ void fix_bad_pixels(struct frame_headers *frame_headers, uint16_t *image_data, i
                              }
                              *res = d_a;
                              if (!bad || !bad->nlevels) { *res = nullptr; return (int)MLVB_OK; }
-                             ctx->launches += 1 + (bad->nlevels > 1);
-                             return launch_pixel_fix(d_a, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, dual_iso != 0, 0,
-                                                     bad->d_by_level, bad->d_level_start, bad->level_start.data(),
-                                                     bad->nlevels, ctx->luts, st);
+                             return apply_pixel_list(ctx, *bad, d_a, g, g.npix, 1, dual_iso != 0, 0, st);
                          });
 }
 
@@ -186,10 +183,7 @@ void fix_focus_pixels(struct frame_headers *frame_headers, uint16_t *image_data,
     with_frame_on_device("fix_focus_pixels", image_data, g.npix,
                          [&](mlvb_context *ctx, uint16_t *d_a, uint16_t *, cudaStream_t st, uint16_t **res) {
                              *res = d_a;
-                             ctx->launches += 1 + (focus->nlevels > 1);
-                             return launch_pixel_fix(d_a, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, dual_iso != 0, 1,
-                                                     focus->d_by_level, focus->d_level_start, focus->level_start.data(),
-                                                     focus->nlevels, ctx->luts, st);
+                             return apply_pixel_list(ctx, *focus, d_a, g, g.npix, 1, dual_iso != 0, 1, st);
                          });
 }
 

@@ -43,6 +43,8 @@ struct StatsA {
     unsigned hist_field[2][4][16384];   // identify_bright_and_dark_fields for row offset 0 (RGGB) and 1 (GBRG)
 };
 
+// HIST = false: only the hdr_check sum (the histograms are taken later, from the pixel-fixed frame)
+template <bool HIST>
 __global__ void __launch_bounds__(256)
 diso_stats_a_kernel(const uint16_t *__restrict__ img, int w, int h, int black, int white, const double *__restrict__ raw2evf,
                     StatsA *__restrict__ S)
@@ -52,10 +54,12 @@ diso_stats_a_kernel(const uint16_t *__restrict__ img, int w, int h, int black, i
     unsigned num = 0;
     if (x < w) {
         const int p = img[x + (size_t)y * w];
-        if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
-        if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
-        const int ys = y - 1;                                                                          // GBRG: frame starts one row lower
-        if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
+        if (HIST) {
+            if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
+            if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
+            const int ys = y - 1;                                                                      // GBRG: frame starts one row lower
+            if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
+        }
         if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {                                              // hdr.c:419-433
             const int p2 = img[x + (size_t)(y + 2) * w];
             if ((p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
@@ -500,6 +504,7 @@ size_t dual_iso_scratch_bytes(int w, int h, int interp_method)
 // the 3000 candidate slopes of match_exposures.
 struct DualIsoTables {
     std::mutex mu;
+    std::vector<void *> pinned_free;    // host staging for the statistics read-backs (pinned: async, full PCIe rate)
     int lut_black = -1;
     int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
     double *d_raw2evf = nullptr;        // 16384 + MAX_BLACK doubles
@@ -518,6 +523,28 @@ static DualIsoTables *tables_of(mlvb_context *ctx)
     g_tabs[ctx] = t;
     return t;
 }
+
+constexpr size_t PINNED_STAGE_BYTES = sizeof(StatsA) + 2 * 65536 * sizeof(unsigned) + 2 * (65536 + 8) * sizeof(unsigned) +
+                                      4096 * sizeof(unsigned) + 256;
+
+struct PinnedLease {
+    DualIsoTables *T;
+    void *p = nullptr;
+    explicit PinnedLease(DualIsoTables *t) : T(t)
+    {
+        {
+            std::lock_guard<std::mutex> lk(T->mu);
+            if (!T->pinned_free.empty()) { p = T->pinned_free.back(); T->pinned_free.pop_back(); }
+        }
+        if (!p && cudaHostAlloc(&p, PINNED_STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
+    }
+    ~PinnedLease()
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(T->mu);
+        T->pinned_free.push_back(p);
+    }
+};
 
 void dual_iso_reset_tables(mlvb_context *ctx)
 {
@@ -558,12 +585,15 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
 
     // ---------------- phase A
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<<<dim3(ceil_div(w, 256), h), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
+    diso_stats_a_kernel<true><<<dim3(ceil_div(w, 256), h), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
     ctx->launches += 1;
-    std::vector<uint8_t> hostA(sizeof(StatsA));
-    MLVB_CUDA_OK(cudaMemcpyAsync(hostA.data(), D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
+    PinnedLease stage(T);
+    if (!stage.p) return MLVB_ERR_CUDA;
+    uint8_t *hostA = (uint8_t *)stage.p;
+    unsigned *hw = (unsigned *)(hostA + sizeof(StatsA)), *he = hw + 2 * 65536, *scores = he + 2 * HB;
+    MLVB_CUDA_OK(cudaMemcpyAsync(hostA, D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaStreamSynchronize(st));
-    const StatsA *A = (const StatsA *)hostA.data();
+    const StatsA *A = (const StatsA *)hostA;
 
     // identify_rggb_or_gbrg (hdr.c:467-494)
     double d_rggb = 0, d_gbrg = 0;
@@ -591,8 +621,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     const int ny_w = (h - F.y1 + 2) / 3;
     if (ny_w > 0) diso_white_kernel<<<dim3(ceil_div(nx, 128), ny_w), 128, 0, st>>>(d_img, w, h, F, max_pix, n_class[0], n_class[1], D.hist_white);
     ctx->launches += 1;
-    std::vector<unsigned> hw(2 * 65536);
-    MLVB_CUDA_OK(cudaMemcpyAsync(hw.data(), D.hist_white, hw.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(hw, D.hist_white, 2 * 65536 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaStreamSynchronize(st));
     int whites[2];
     for (int c = 0; c < 2; c++) {
@@ -622,18 +651,17 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     MLVB_CUDA_OK(cudaMemsetAsync(D.hist_expo, 0, 2 * HB * sizeof(unsigned), st));
     if (ngrid) diso_expo_pairs_kernel<<<dim3(ceil_div(nx, 128), ny_e), 128, 0, st>>>(d_img, w, h, F, E, D.pairs, D.hist_expo, HB);
     ctx->launches += 1;
-    std::vector<unsigned> he(2 * HB);
-    MLVB_CUDA_OK(cudaMemcpyAsync(he.data(), D.hist_expo, he.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(he, D.hist_expo, 2 * HB * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaStreamSynchronize(st));
     long long n = 0;
     for (int i = 0; i < HB; i++) n += he[i];
     auto med_idx = [](long long m) { return (m & 1) ? m / 2 : m / 2 - 1; };
     int bmed = 0, b_lo = 0, b_hi = 0, dmed = 0;
     if (n > 0) {
-        bmed = kth_from_hist(he.data(), HB, med_idx(n), E.black16);
-        b_lo = kth_from_hist(he.data(), HB, n * 98 / 100, E.black16);
-        b_hi = kth_from_hist(he.data(), HB, (long long)(int)(n * 99.9 / 100), E.black16);
-        dmed = kth_from_hist(he.data() + HB, HB, med_idx(n), E.black16);
+        bmed = kth_from_hist(he, HB, med_idx(n), E.black16);
+        b_lo = kth_from_hist(he, HB, n * 98 / 100, E.black16);
+        b_hi = kth_from_hist(he, HB, (long long)(int)(n * 99.9 / 100), E.black16);
+        dmed = kth_from_hist(he + HB, HB, med_idx(n), E.black16);
     }
     const int nmax = (w + 2) * (h + 2) / 9;
     const unsigned hi_cap = (unsigned)std::max(nmax / 50, 0);
@@ -642,11 +670,11 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     if (ngrid) diso_highlights_kernel<<<ceil_div(ngrid, 256), 256, 0, st>>>(D.pairs, ngrid, b_lo, b_hi, D.sel, D.nsel, ngrid);
     diso_score_kernel<<<ncand, 256, 0, st>>>(D.sel, D.nsel, ngrid, T->d_test_a, dmed, bmed, D.scores);
     ctx->launches += 2;
-    std::vector<unsigned> scores(ncand);
-    unsigned nsel = 0;
-    MLVB_CUDA_OK(cudaMemcpyAsync(scores.data(), D.scores, ncand * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaMemcpyAsync(&nsel, D.nsel, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (ncand > 4095) return MLVB_ERR_ARG;
+    MLVB_CUDA_OK(cudaMemcpyAsync(scores, D.scores, ncand * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MLVB_CUDA_OK(cudaMemcpyAsync(scores + ncand, D.nsel, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    const unsigned nsel = scores[ncand];
     if (nsel >= hi_cap && hi_cap > 0) {
         // the reference truncates its highlight list in raster order here (hdr.c:727-745); not reproduced
         fprintf(stderr, "libmlvfs_b200: dual ISO: highlight sample cap reached (%u >= %u), frame not converted\n", nsel, hi_cap);
@@ -766,7 +794,7 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
         }
     }
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<<<dim3(ceil_div(g.w, 256), g.h), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
+    diso_stats_a_kernel<false><<<dim3(ceil_div(g.w, 256), g.h), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
                                                                       T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA);
     ctx->launches += 1;
     double ev_sum = 0;
@@ -786,10 +814,8 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
         if (rc) return rc;
     }
     if (focus && focus->nlevels) {
-        rc = launch_pixel_fix(d_img, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, 1, 1, focus->d_by_level, focus->d_level_start,
-                              focus->level_start.data(), focus->nlevels, ctx->luts, st);
+        rc = apply_pixel_list(ctx, *focus, d_img, g, g.npix, 1, 1, 1, st);
         if (rc) return rc;
-        ctx->launches += 1 + (focus->nlevels > 1);
     }
     if (fix_bad_pixels_mode) {
         {
@@ -798,10 +824,8 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
             if (rc) return rc;
         }
         if (bad && bad->nlevels) {
-            rc = launch_pixel_fix(d_img, g.w, g.h, g.npix, 1, g.black, g.crop_x, g.crop_y, 1, 0, bad->d_by_level, bad->d_level_start,
-                                  bad->level_start.data(), bad->nlevels, ctx->luts, st);
+            rc = apply_pixel_list(ctx, *bad, d_img, g, g.npix, 1, 1, 0, st);
             if (rc) return rc;
-            ctx->launches += 1 + (bad->nlevels > 1);
         }
     }
     return run_hdr_interpolate(ctx, d_img, g.w, g.h, g.black, interp_method, use_fullres, use_alias_map, cs_method, d_aux, st);

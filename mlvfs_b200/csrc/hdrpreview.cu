@@ -127,10 +127,10 @@ int run_hdr_preview(mlvb_context *ctx, const struct frame_headers *hdr, const Fr
         if (rc) return rc;
     }
     if (focus && focus->nlevels && g.black <= MLVB_MAX_BLACK) {
-        int rc = launch_pixel_fix(d_img, w, h, g.npix, 1, g.black, g.crop_x, g.crop_y, 1, 1, focus->d_by_level, focus->d_level_start,
-                                  focus->level_start.data(), focus->nlevels, ctx->luts, st);
+        FrameGeom gw = g;
+        gw.w = w; gw.h = h;
+        int rc = apply_pixel_list(ctx, *focus, d_img, gw, g.npix, 1, 1, 1, st);
         if (rc) return rc;
-        ctx->launches += 1 + (focus->nlevels > 1);
     }
 
     // histogram matching + weighted least squares (hdr.c:119-182), same fp64 operation order

@@ -37,6 +37,11 @@ int launch_pixel_fix(uint16_t *d_img, int w, int h, size_t frame_stride, int nfr
                      int dual_iso, int edge_rules, const PixelXY *d_list_by_level, const unsigned *d_level_start,
                      const unsigned *h_level_start, unsigned nlevels, const EvLuts &luts, cudaStream_t st);
 
+// horizontal-only (dual ISO) form: independent row segments, one thread each
+int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, int nframes, int black, int crop_x, int crop_y,
+                          int edge_rules, const PixelXY *d_list_by_row, const unsigned *d_seg_start, unsigned nseg,
+                          const EvLuts &luts, cudaStream_t st);
+
 // ---- stripes.cu ----
 int stripes_blocks_per_row(int w);
 int stripes_count_ctas(int w, int h);

@@ -111,6 +111,20 @@ __global__ void fix_deep_levels_kernel(const FixArgs A, const unsigned *__restri
     }
 }
 
+// dual-ISO form: every entry uses the horizontal interpolator (or a same-row copy), so a thread applies one
+// independent run of a row's entries in list order (PixelList::upload builds the runs)
+__global__ void __launch_bounds__(128)
+fix_row_segments_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, unsigned nseg)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    uint16_t *im = A.img + (size_t)blockIdx.y * A.frame_stride;
+    for (unsigned m = seg_start[s], hi = seg_start[s + 1]; m < hi; m++) {
+        const PixelXY p = A.list[m];
+        fix_entry(im, A.w, A.h, p.x - A.crop_x, p.y - A.crop_y, 1, A.edge_rules, A.lut);
+    }
+}
+
 // ---------------------------------------------------------------- detection (cs.c:257-306) ----
 
 constexpr int DET_THREADS = 256;
@@ -233,6 +247,23 @@ int launch_pixel_fix(uint16_t *d_img, int w, int h, size_t frame_stride, int nfr
     const unsigned n0 = h_level_start[1];
     if (n0) fix_level0_kernel<<<dim3(ceil_div(n0, 128), nframes), 128, 0, st>>>(A, n0);
     if (nlevels > 1) fix_deep_levels_kernel<<<dim3(1, nframes), 1024, 0, st>>>(A, d_level_start, nlevels);
+    MLVB_CUDA_OK(cudaGetLastError());
+    return MLVB_OK;
+}
+
+int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, int nframes, int black, int crop_x, int crop_y,
+                          int edge_rules, const PixelXY *d_list_by_row, const unsigned *d_seg_start, unsigned nseg,
+                          const EvLuts &luts, cudaStream_t st)
+{
+    if (nseg == 0) return MLVB_OK;
+    if (black > MLVB_MAX_BLACK) return MLVB_ERR_ARG;
+    FixArgs A;
+    A.img = d_img; A.frame_stride = frame_stride; A.w = w; A.h = h; A.crop_x = crop_x; A.crop_y = crop_y;
+    A.dual_iso = 1; A.edge_rules = edge_rules; A.list = d_list_by_row;
+    A.lut.raw2ev = luts.raw2ev_base + (MLVB_MAX_BLACK - black);
+    A.lut.ev2raw = luts.ev2raw_pos;
+    A.lut.black = black;
+    fix_row_segments_kernel<<<dim3(ceil_div(nseg, 128), nframes), 128, 0, st>>>(A, d_seg_start, nseg);
     MLVB_CUDA_OK(cudaGetLastError());
     return MLVB_OK;
 }
