@@ -45,7 +45,7 @@ WORKLOADS = {
     "C2": dict(w=1920, h=1080, opts=dict(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=1),
                variant=dict(hot_cold=True, stripes=True), codec="raw", chain_bpp=3.75, stage="chroma", stage_bpp=4.0,
                desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256,
-               kernel="chroma3_strip_kernel (3x3 median chroma smoothing + fused stripes store)"),
+               kernel="fused3_strip_kernel (unpack + bad-pixel patches + 3x3 median chroma smoothing + stripes, one pass)"),
     "C3": dict(w=3840, h=1536, opts=dict(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5),
                variant=dict(dual_iso=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
                desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=8,
@@ -56,9 +56,19 @@ WORKLOADS = {
                kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)"),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,
                desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=64,
-               kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + wavefront prediction + untile, 10 launches)"),
+               kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + wavefront prediction + untile, 14 launches)"),
 }
 METRIC = "DNG frames/sec per B200 and at 1/2/4/8 GPUs; achieved HBM GB/s vs peak"   # BASELINE.json metric
+
+
+def measured_traffic(workload, frames):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get(workload)
+        return float(t["dram_bytes_per_frame"]) * frames if t else None
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -369,7 +379,7 @@ def run_ours(args, wl):
             stage_bytes = (wl["stage_bpp"] * npix if wl["codec"] == "raw" else in_bytes + 2 * npix) * B
             achieved = stage_bytes / per_launch_s / 1e9
             roof = {"bound": "hbm", "kernel": wl["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launch_ms": per_launch_s * 1e3,
+                    "frac": achieved / peak, "traffic": measured_traffic(args.workload, B), "peak_source": peak_src, "launch_ms": per_launch_s * 1e3,
                     "algorithmic_bytes_per_launch": stage_bytes,
                     "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                     "chain_achieved_gbs": chain_bytes * value / world / 1e9,
