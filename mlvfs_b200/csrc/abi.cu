@@ -224,6 +224,12 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
     std::vector<uint16_t> pos(14 * MLVB_EV_RES);
     const int *ev2raw = host_ev2raw_base();
     for (int e = 0; e < 14 * MLVB_EV_RES; e++) pos[e] = (uint16_t)ev2raw[e + 10 * MLVB_EV_RES];
+    // 2^(e/EV) = 2^k * 2^(f/EV): every octave of the table is the top octave shifted right (exact, not assumed:
+    // checked here against the libm-built table; fused.cu keeps only the 64 KiB top octave in shared memory)
+    ctx->ev2raw_octaves_ok = true;
+    for (int e = 0; e < 14 * MLVB_EV_RES && ctx->ev2raw_octaves_ok; e++)
+        ctx->ev2raw_octaves_ok = pos[e] == (pos[13 * MLVB_EV_RES + (e & (MLVB_EV_RES - 1))] >> (13 - (e >> 15)));
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) ctx->sm_count = 148;
     MLVB_CUDA_OK(cudaMalloc(&ctx->d_raw2ev_base, n1));
     MLVB_CUDA_OK(cudaMalloc(&ctx->d_ev2raw_pos, n2));
     MLVB_CUDA_OK(cudaMalloc(&ctx->d_ev2raw_full, n3));

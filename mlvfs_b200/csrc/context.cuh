@@ -80,6 +80,8 @@ struct mlvb_context {
     int *d_raw2ev_base = nullptr;
     uint16_t *d_ev2raw_pos = nullptr;
     int *d_ev2raw_full = nullptr;
+    bool ev2raw_octaves_ok = false;        // ev2raw[e] == ev2raw[13 EV + (e mod EV)] >> (13 - e / EV) for all e (checked at creation)
+    int sm_count = 0;
 
     std::mutex mu;                         // slots + tickets
     std::condition_variable cv;

@@ -193,3 +193,20 @@ def test_batch_device_matches_per_frame(fresh_ctx, oracle):
         got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
         for i in range(n):
             assert np.array_equal(got[i], want[i]), (rep, i)
+
+
+@pytest.mark.parametrize("w,h,stripes", [(1920, 1080, 1), (656, 362, 1), (1040, 94, 0)])
+def test_fused_kernel_odd_geometries(fresh_ctx, oracle, w, h, stripes):
+    """The steady-state C2 chain runs in one fused kernel (fused.cu); it must give the oracle's frames also at
+    segment / strip edges of odd geometries and with a dense bad-pixel list."""
+    hdr = _hdr(w, h)
+    ri = hdr.rawi_hdr.raw_info
+    frames = [synth.make_frame(w, h, i, hot_cold=True, stripes=bool(stripes), bad_density=3e-4) for i in range(4)]
+    want, _ = oracle.single_iso_chain(frames, ri.black_level, ri.white_level, ri.frame_size,
+                                      chroma_smooth_method=3, fix_bad_pixels=1, fix_stripes=stripes)
+    o = M.Options(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=stripes)
+    name = f"fusedgeo_{w}x{h}.MLV"
+    for i, fr in enumerate(frames):              # frames 0, 1 build the per-clip state / take the general path
+        out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(fr), o, name)
+        assert res.status == 0
+        assert np.array_equal(out, want[i]), (i, int(np.count_nonzero(out != want[i])))
