@@ -73,6 +73,7 @@ PixelList::~PixelList()
     if (d_level_start) cudaFree(d_level_start);
     if (d_by_row) cudaFree(d_by_row);
     if (d_seg_start) cudaFree(d_seg_start);
+    if (d_long_rows) cudaFree(d_long_rows);
 }
 
 int PixelList::upload()
@@ -129,24 +130,29 @@ int PixelList::upload()
         std::vector<unsigned> cur(row_start.begin(), row_start.end() - 1);
         for (size_t m = 0; m < n; m++) by_row[cur[(size_t)(host[m].y - ylo)]++] = host[m];
     }
-    std::vector<unsigned> seg;
-    seg.reserve(n + 1);
+    // rows with >= 128 entries (dual ISO with --really-bad-pix lists every bright-row pixel: one serial chain per
+    // row) are walked by a warp in shared memory; the others are cut into independent segments, one thread each
+    std::vector<unsigned> seg, longr;
     for (size_t r = 0; r < nrows; r++) {
         const unsigned lo = row_start[r], hi = row_start[r + 1];
         if (lo == hi) continue;
+        if (hi - lo >= 128) { longr.push_back(lo); longr.push_back(hi); continue; }
         bool monotone = true;
         for (unsigned m = lo + 1; m < hi; m++) monotone &= by_row[m].x >= by_row[m - 1].x;
-        seg.push_back(lo);
+        unsigned first = lo;
         if (monotone)
             for (unsigned m = lo + 1; m < hi; m++)
-                if (by_row[m].x - by_row[m - 1].x > 3) seg.push_back(m);
+                if (by_row[m].x - by_row[m - 1].x > 3) { seg.push_back(first); seg.push_back(m); first = m; }
+        seg.push_back(first); seg.push_back(hi);
     }
-    nseg = (unsigned)seg.size();
-    seg.push_back((unsigned)n);
+    nseg = (unsigned)(seg.size() / 2);
+    nlong = (unsigned)(longr.size() / 2);
     MLVB_CUDA_OK(cudaMalloc(&d_by_row, n * sizeof(PixelXY)));
-    MLVB_CUDA_OK(cudaMalloc(&d_seg_start, seg.size() * sizeof(unsigned)));
+    MLVB_CUDA_OK(cudaMalloc(&d_seg_start, std::max<size_t>(seg.size(), 2) * sizeof(unsigned)));
+    MLVB_CUDA_OK(cudaMalloc(&d_long_rows, std::max<size_t>(longr.size(), 2) * sizeof(unsigned)));
     MLVB_CUDA_OK(cudaMemcpy(d_by_row, by_row.data(), n * sizeof(PixelXY), cudaMemcpyHostToDevice));
-    MLVB_CUDA_OK(cudaMemcpy(d_seg_start, seg.data(), seg.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (!seg.empty()) MLVB_CUDA_OK(cudaMemcpy(d_seg_start, seg.data(), seg.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (!longr.empty()) MLVB_CUDA_OK(cudaMemcpy(d_long_rows, longr.data(), longr.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     return MLVB_OK;
 }
 
@@ -155,9 +161,9 @@ int apply_pixel_list(mlvb_context *ctx, const PixelList &L, uint16_t *d_img, con
 {
     if (!L.nlevels) return MLVB_OK;
     if (dual_iso) {
-        ctx->launches += 1;
+        ctx->launches += (L.nseg > 0) + (L.nlong > 0);
         return launch_pixel_fix_rows(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, edge_rules, L.d_by_row,
-                                     L.d_seg_start, L.nseg, ctx->luts, st);
+                                     L.d_seg_start, L.nseg, L.d_long_rows, L.nlong, ctx->luts, ctx->ev2raw_octaves_ok, ctx->sm_count, st);
     }
     ctx->launches += 1 + (L.nlevels > 1);
     return launch_pixel_fix(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, 0, edge_rules, L.d_by_level,

@@ -30,8 +30,10 @@ struct PixelList {
     // dual-ISO (horizontal-only) application: entries grouped by row in list order and cut into segments
     // that cannot see each other (x gap > 3); one thread walks one segment sequentially
     PixelXY *d_by_row = nullptr;
-    unsigned *d_seg_start = nullptr;
+    unsigned *d_seg_start = nullptr;       // segments of the sparse rows: [2 * s], [2 * s + 1] = first, end entry
     unsigned nseg = 0;
+    unsigned *d_long_rows = nullptr;       // rows with many entries (one warp walks the whole row in shared memory)
+    unsigned nlong = 0;
     std::vector<unsigned> level_start;     // nlevels + 1 entries
     unsigned nlevels = 0;
     ~PixelList();

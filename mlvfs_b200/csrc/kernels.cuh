@@ -40,7 +40,8 @@ int launch_pixel_fix(uint16_t *d_img, int w, int h, size_t frame_stride, int nfr
 // horizontal-only (dual ISO) form: independent row segments, one thread each
 int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, int nframes, int black, int crop_x, int crop_y,
                           int edge_rules, const PixelXY *d_list_by_row, const unsigned *d_seg_start, unsigned nseg,
-                          const EvLuts &luts, cudaStream_t st);
+                          const unsigned *d_long_rows, unsigned nlong, const EvLuts &luts, int ev2raw_octaves_ok, int sm_count,
+                          cudaStream_t st);
 
 // ---- stripes.cu ----
 int stripes_blocks_per_row(int w);

@@ -10,6 +10,8 @@
 // running levels in order, in place, reads exactly what the sequential loop would have read.
 // Level 0 (virtually everything on real sensors) runs grid-wide; deeper levels run in one CTA that
 // walks the levels with a barrier in between.
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "scan.cuh"
 
@@ -112,16 +114,180 @@ __global__ void fix_deep_levels_kernel(const FixArgs A, const unsigned *__restri
 }
 
 // dual-ISO form: every entry uses the horizontal interpolator (or a same-row copy), so a thread applies one
-// independent run of a row's entries in list order (PixelList::upload builds the runs)
-__global__ void __launch_bounds__(128)
-fix_row_segments_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, unsigned nseg)
+// independent run of a row's entries in list order (PixelList::upload builds the runs).  With --really-bad-pix
+// every bright-row pixel of a dual-ISO frame is in the list (its third-largest same-colour neighbour sits in a
+// dark row, cs.c:289-304), so a run is a whole row and each entry reads the three values just written before
+// it: a serial chain of thousands of steps.  The chain is kept short per step: both EV tables in shared memory
+// (persistent blocks), and a 7-pixel window of raw values and their EVs carried in registers, so that a step
+// loads only the pixels that enter the window and never waits for its own stores.
+constexpr int RUN_THREADS = 256;
+constexpr size_t RUN_SMEM = 16384 * sizeof(int) + 32768 * sizeof(uint16_t);
+
+template <bool SMEM_EV2RAW>
+__global__ void __launch_bounds__(RUN_THREADS)
+fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, unsigned nseg, int nframes)
 {
-    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    uint16_t *im = A.img + (size_t)blockIdx.y * A.frame_stride;
-    for (unsigned m = seg_start[s], hi = seg_start[s + 1]; m < hi; m++) {
-        const PixelXY p = A.list[m];
-        fix_entry(im, A.w, A.h, p.x - A.crop_x, p.y - A.crop_y, 1, A.edge_rules, A.lut);
+    extern __shared__ __align__(16) unsigned char run_smem[];
+    int *s_r2e = reinterpret_cast<int *>(run_smem);
+    uint16_t *s_m13 = reinterpret_cast<uint16_t *>(run_smem + 16384 * sizeof(int));
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) s_r2e[i] = __ldg(A.lut.raw2ev + i);
+    if (SMEM_EV2RAW) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.lut.ev2raw + 13 * MLVB_EV_RES);
+        for (int i = threadIdx.x; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t *>(s_m13)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int w = A.w, h = A.h, black = A.lut.black;
+    auto ev_of_raw = [&](int v) { return v < 16384 ? s_r2e[v] : __ldg(A.lut.raw2ev + v); };
+    auto raw_of_ev = [&](int e) {
+        const int c = clamp_ev(e);
+        return SMEM_EV2RAW ? (int)(s_m13[c & (MLVB_EV_RES - 1)] >> (13 - (c >> 15))) : (int)__ldg(A.lut.ev2raw + c);
+    };
+    const unsigned total = nseg * (unsigned)nframes;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned sidx = t % nseg, frame = t / nseg;
+        uint16_t *im = A.img + (size_t)frame * A.frame_stride;
+        int R[7], E[7];                    // raw values and EVs at x-3 .. x+3 of the previous entry (same row)
+        int lastx = -100, lasty = -1;
+        for (unsigned m = seg_start[2 * sidx], hi = seg_start[2 * sidx + 1]; m < hi; m++) {
+            const PixelXY p = A.list[m];
+            const int x = p.x - A.crop_x, y = p.y - A.crop_y;
+            if (!(x > 2 && x < w - 3 && y > 2 && y < h - 3)) {                  // border rules: generic path
+                fix_entry(im, w, h, x, y, 1, A.edge_rules, A.lut);
+                lastx = -100;
+                continue;
+            }
+            uint16_t *row = im + (size_t)y * w;
+            const int dx = x - lastx;
+            if (y == lasty && dx >= 1 && dx <= 3) {
+                for (int sft = 0; sft < dx; sft++) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { R[k] = R[k + 1]; E[k] = E[k + 1]; }
+                    R[6] = row[lastx + sft + 4];
+                    E[6] = ev_of_raw(R[6]);
+                }
+            } else if (!(y == lasty && dx == 0)) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) { R[k] = row[x - 3 + k]; E[k] = ev_of_raw(R[k]); }
+            }
+            lastx = x; lasty = y;
+            // cs.c:87-109 (interpolate_horizontal), same expressions as interp_line
+            const int d1 = wabs(wsub(E[6], E[4])), d2 = wabs(wsub(E[2], E[0]));
+            const int sum = wadd(d1, d2);
+            int v;
+            if (sum == 0) v = R[5];
+            else {
+                const int c1 = ((sum - d1) << 8) / sum, c2 = ((sum - d2) << 8) / sum;
+                const int ev = (wmul(E[5], c1) >> 8) + (wmul(E[1], c2) >> 8);
+                v = (raw_of_ev(ev) + black) & 0xFFFF;
+            }
+            row[x] = (uint16_t)v;
+            R[3] = v;
+            E[3] = ev_of_raw(v);
+        }
+    }
+}
+
+// Rows with many entries: one warp stages the whole image row in shared memory, lane 0 applies the row's entries
+// in list order there (every dual-ISO-mode rule of fix_entry stays inside the row: horizontal interpolation or a
+// copy from x +- 2), then the warp writes the row back.  The chain never waits for global memory.
+constexpr int LONG_WARPS_MAX = 16;
+
+template <bool SMEM_EV2RAW>
+__global__ void __launch_bounds__(LONG_WARPS_MAX * 32)
+fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, unsigned nlong, int nframes, int warps_per_block)
+{
+    extern __shared__ __align__(16) unsigned char run_smem[];
+    int *s_r2e = reinterpret_cast<int *>(run_smem);
+    // with SMEM_EV2RAW the exp table's top octave follows (64 KiB), else the row buffers start right here and the
+    // exp table is read through L1: more rows per SM, so that every long row of a frame is walked concurrently
+    uint16_t *s_m13 = reinterpret_cast<uint16_t *>(run_smem + 16384 * sizeof(int));
+    uint16_t *s_rows = reinterpret_cast<uint16_t *>(run_smem + (SMEM_EV2RAW ? RUN_SMEM : 16384 * sizeof(int)));
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) s_r2e[i] = __ldg(A.lut.raw2ev + i);
+    if (SMEM_EV2RAW) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(A.lut.ev2raw + 13 * MLVB_EV_RES);
+        for (int i = threadIdx.x; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t *>(s_m13)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int w = A.w, h = A.h, black = A.lut.black;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= warps_per_block) return;
+    uint16_t *row = s_rows + (size_t)warp * ((w + 7) & ~7);
+    auto ev_of_raw = [&](int v) { return v < 16384 ? s_r2e[v] : __ldg(A.lut.raw2ev + v); };
+    auto raw_of_ev = [&](int e) {
+        const int c = clamp_ev(e);
+        return SMEM_EV2RAW ? (int)(s_m13[c & (MLVB_EV_RES - 1)] >> (13 - (c >> 15))) : (int)__ldg(A.lut.ev2raw + c);
+    };
+    // (num << 8) / sum for 0 <= num <= sum < 2^22 (quotient 0..256): float estimate + exact correction, ~10
+    // dependent instructions instead of the ~35 of a 32-bit integer division
+    auto div8 = [&](int num, int sum) {
+        const int n8 = num << 8;
+        int q = __float2int_rz(__fdividef((float)n8, (float)sum));
+        const int r = n8 - q * sum;
+        q += (r >= sum) - (r < 0);
+        return q;
+    };
+    // window of EVs at x-3 .. x+3 around the previous entry (valid while entries advance by 1..3 columns)
+    int E[7];
+    int lastx = -100;
+    auto interp_h = [&](int x) {                                                // cs.c:87-109, as interp_line(step 1)
+        const int dx = x - lastx;
+        if (dx >= 1 && dx <= 3) {
+            for (int sft = 0; sft < dx; sft++) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) E[k] = E[k + 1];
+                E[6] = ev_of_raw(row[lastx + sft + 4]);
+            }
+        } else if (dx != 0) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) E[k] = ev_of_raw(row[x - 3 + k]);
+        }
+        lastx = x;
+        const int d1 = wabs(wsub(E[6], E[4])), d2 = wabs(wsub(E[2], E[0]));
+        const int sum = wadd(d1, d2);
+        int v;
+        if (sum == 0) v = row[x + 2];
+        else {
+            int c1, c2;
+            if (d1 >= 0 && d2 >= 0 && sum > 0 && sum < (1 << 22)) { c1 = div8(sum - d1, sum); c2 = div8(sum - d2, sum); }
+            else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }   // wrap-around cases (pixels at black)
+            const int ev = (wmul(E[5], c1) >> 8) + (wmul(E[1], c2) >> 8);
+            v = (raw_of_ev(ev) + black) & 0xFFFF;
+        }
+        row[x] = (uint16_t)v;
+        E[3] = ev_of_raw(v);
+    };
+    const unsigned total = nlong * (unsigned)nframes;
+    for (unsigned t = blockIdx.x * warps_per_block + warp; t < total; t += gridDim.x * warps_per_block) {
+        const unsigned ridx = t % nlong, frame = t / nlong;
+        const unsigned m0 = long_rows[2 * ridx], m1 = long_rows[2 * ridx + 1];
+        const int y = A.list[m0].y - A.crop_y;
+        if (y <= 3 || y >= h - 3) {
+            // top / bottom edge rows (and rows outside the frame): the reference's edge rules address pixels by
+            // linear index there (cs.c:467, 479-500), which can leave the row; apply them in place, entry by entry
+            if (lane == 0)
+                for (unsigned m = m0; m < m1; m++)
+                    fix_entry(A.img + (size_t)frame * A.frame_stride, w, h, A.list[m].x - A.crop_x, y, 1, A.edge_rules, A.lut);
+            __syncwarp();
+            continue;
+        }
+        uint16_t *grow = A.img + (size_t)frame * A.frame_stride + (size_t)y * w;
+        for (int x = lane; x < w; x += 32) row[x] = grow[x];
+        __syncwarp();
+        lastx = -100;
+        if (lane == 0) {
+            for (unsigned m = m0; m < m1; m++) {                                // rows 4 .. h-4: fix_entry with dual_iso = 1
+                const int x = A.list[m].x - A.crop_x;
+                if (x > 2 && x < w - 3) interp_h(x);
+                else if (A.edge_rules && x >= 0 && x < w) {
+                    if (x <= 3) row[x] = row[x + 2];
+                    else row[x] = row[x - 2];
+                    lastx = -100;
+                }
+            }
+        }
+        __syncwarp();
+        for (int x = lane; x < w; x += 32) grow[x] = row[x];
+        __syncwarp();
     }
 }
 
@@ -253,9 +419,10 @@ int launch_pixel_fix(uint16_t *d_img, int w, int h, size_t frame_stride, int nfr
 
 int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, int nframes, int black, int crop_x, int crop_y,
                           int edge_rules, const PixelXY *d_list_by_row, const unsigned *d_seg_start, unsigned nseg,
-                          const EvLuts &luts, cudaStream_t st)
+                          const unsigned *d_long_rows, unsigned nlong, const EvLuts &luts, int ev2raw_octaves_ok, int sm_count,
+                          cudaStream_t st)
 {
-    if (nseg == 0) return MLVB_OK;
+    if (nseg == 0 && nlong == 0) return MLVB_OK;
     if (black > MLVB_MAX_BLACK) return MLVB_ERR_ARG;
     FixArgs A;
     A.img = d_img; A.frame_stride = frame_stride; A.w = w; A.h = h; A.crop_x = crop_x; A.crop_y = crop_y;
@@ -263,7 +430,47 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
     A.lut.raw2ev = luts.raw2ev_base + (MLVB_MAX_BLACK - black);
     A.lut.ev2raw = luts.ev2raw_pos;
     A.lut.black = black;
-    fix_row_segments_kernel<<<dim3(ceil_div(nseg, 128), nframes), 128, 0, st>>>(A, d_seg_start, nseg);
+    const int sms = sm_count > 0 ? sm_count : 148;
+    // long rows first?  No: rows are independent of each other in this mode, any order is the reference's result
+    const size_t row_bytes = (size_t)((w + 7) & ~7) * sizeof(uint16_t);
+    // rows per SM with both tables in shared memory; if that cannot hold all long rows of the batch at once, keep
+    // only the log table there (the exp table is then read through L1) to avoid a second round of serial chains
+    int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / row_bytes);
+    bool long_ev2raw_smem = ev2raw_octaves_ok != 0;
+    if ((long long)nlong * nframes > (long long)long_warps * sms || long_warps < 1) {
+        const int alt = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - 16384 * sizeof(int) - 1024) / row_bytes);
+        if (alt > long_warps) { long_warps = alt; long_ev2raw_smem = false; }
+    }
+    const unsigned *segs = d_seg_start;
+    unsigned nshort = nseg;
+    if (nlong && long_warps < 1) {                                            // rows too wide to stage: thread-per-row walk
+        segs = d_long_rows; nshort = nlong;
+        if (nseg) {
+            const int b0 = (int)std::min<long long>(sms, ceil_div((long long)nseg * nframes, RUN_THREADS));
+            MLVB_CUDA_OK(cudaFuncSetAttribute(fix_row_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM));
+            fix_row_runs_kernel<false><<<b0, RUN_THREADS, RUN_SMEM, st>>>(A, d_seg_start, nseg, nframes);
+        }
+    } else if (nlong) {
+        const size_t smem = (long_ev2raw_smem ? RUN_SMEM : 16384 * sizeof(int)) + (size_t)long_warps * row_bytes;
+        const int blocks = (int)std::min<long long>(sms, ceil_div((long long)nlong * nframes, long_warps));
+        if (long_ev2raw_smem) {
+            MLVB_CUDA_OK(cudaFuncSetAttribute(fix_long_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fix_long_rows_kernel<true><<<blocks, LONG_WARPS_MAX * 32, smem, st>>>(A, d_long_rows, nlong, nframes, long_warps);
+        } else {
+            MLVB_CUDA_OK(cudaFuncSetAttribute(fix_long_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fix_long_rows_kernel<false><<<blocks, LONG_WARPS_MAX * 32, smem, st>>>(A, d_long_rows, nlong, nframes, long_warps);
+        }
+    }
+    if (nshort) {
+        const int blocks = (int)std::min<long long>(sms, ceil_div((long long)nshort * nframes, RUN_THREADS));
+        if (ev2raw_octaves_ok) {
+            MLVB_CUDA_OK(cudaFuncSetAttribute(fix_row_runs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM));
+            fix_row_runs_kernel<true><<<blocks, RUN_THREADS, RUN_SMEM, st>>>(A, segs, nshort, nframes);
+        } else {
+            MLVB_CUDA_OK(cudaFuncSetAttribute(fix_row_runs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RUN_SMEM));
+            fix_row_runs_kernel<false><<<blocks, RUN_THREADS, RUN_SMEM, st>>>(A, segs, nshort, nframes);
+        }
+    }
     MLVB_CUDA_OK(cudaGetLastError());
     return MLVB_OK;
 }
