@@ -12,10 +12,32 @@
 //   amz_edge_dir_kernel    hdr.c:1094-1175  11 directions x 11 offsets of |EV| differences where high accuracy is needed
 // The interpolation itself (hdr.c:1182-1210, edge_interp :940-952) is done inside dualiso.cu's per-pixel kernel
 // through amz_edge_interp().
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "amaze.cuh"
 
 #include "amaze_tile.cuh"
 #include "context.cuh"
+
+int amz_threads()
+{
+    static const int v = [] { const char *e = getenv("MLVB_AMZ_THREADS"); int t = e ? atoi(e) : 512; return t >= 64 && t <= 1024 && t % 32 == 0 ? t : 512; }();
+    return v;
+}
+
+int amz_blocks()
+{
+    static const int v = [] {
+        const char *e = getenv("MLVB_AMZ_BLOCKS_PER_SM");
+        int b = e ? atoi(e) : 2, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        b = b >= 1 && b <= 6 ? b : 2;
+        return std::min(b * sms, (int)AMZ_MAX_BLOCKS);
+    }();
+    return v;
+}
 
 namespace {
 
@@ -37,7 +59,7 @@ __global__ void amz_squeeze_kernel(const uint32_t *__restrict__ raw32, float *__
     rawf[(size_t)yh * ws + x] = (float)p;
 }
 
-__global__ void __launch_bounds__(AMZ_THREADS)
+__global__ void __launch_bounds__(AMZ_THREADS_MAX)
 amz_tiles_kernel(const float *__restrict__ raw, float *__restrict__ red, float *__restrict__ green, float *__restrict__ blue,
                  int stride, int width, int height, int ntx, int nty, char *__restrict__ ws_base, unsigned *__restrict__ counter)
 {
@@ -126,7 +148,7 @@ size_t amaze_scratch_bytes(int w, int h, AmazeScratch *S, uint8_t *base)
     s.squeezed = (int *)take((size_t)h * 4); s.sq_dst = (int *)take((size_t)h * 4);
     s.counter = (unsigned *)take(256);
     const int ntiles = amaze::tiles_along(w) * amaze::tiles_along(h);
-    s.nblocks = ntiles < AMZ_MAX_BLOCKS ? ntiles : AMZ_MAX_BLOCKS;
+    s.nblocks = ntiles < amz_blocks() ? ntiles : amz_blocks();
     s.ws = (char *)take((size_t)s.nblocks * amaze::WS_BYTES);
     if (S) *S = s;
     return o;
@@ -166,7 +188,7 @@ int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int whi
     const dim3 g2(ceil_div(w, 256), h);
     amz_squeeze_kernel<<<g2, 256, 0, st>>>(d_raw32, A.rawf, A.sq_dst, w, h, ws, black);
     const int ntx = amaze::tiles_along(w), nty = amaze::tiles_along(h);
-    amz_tiles_kernel<<<A.nblocks, AMZ_THREADS, 0, st>>>(A.rawf, A.red, A.green, A.blue, ws, w, h, ntx, nty, A.ws, A.counter);
+    amz_tiles_kernel<<<A.nblocks, amz_threads(), 0, st>>>(A.rawf, A.red, A.green, A.blue, ws, w, h, ntx, nty, A.ws, A.counter);
     amz_gray_kernel<<<g2, 256, 0, st>>>(A.red, A.green, A.blue, A.squeezed, d_raw2ev, A.grayev, w, h, ws, black);
     amz_edge_dir_kernel<<<dim3(ceil_div(w, 128), h), 128, 0, st>>>(d_raw32, A.grayev, A.edir, w, h, black, white_darkened,
                                                                   is_bright[0], is_bright[1], is_bright[2], is_bright[3]);
@@ -181,7 +203,7 @@ int launch_amaze_planes(const float *d_raw, float *d_red, float *d_green, float 
 {
     if (w & 3) return MLVB_ERR_UNSUPPORTED;
     MLVB_CUDA_OK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned), st));
-    amz_tiles_kernel<<<nblocks, AMZ_THREADS, 0, st>>>(d_raw, d_red, d_green, d_blue, stride, w, h, amaze::tiles_along(w),
+    amz_tiles_kernel<<<nblocks, amz_threads(), 0, st>>>(d_raw, d_red, d_green, d_blue, stride, w, h, amaze::tiles_along(w),
                                                      amaze::tiles_along(h), d_ws, d_counter);
     MLVB_CUDA_OK(cudaGetLastError());
     return MLVB_OK;
@@ -203,7 +225,7 @@ extern "C" void amaze_demosaic_RT(float **rawData, float **red, float **green, f
     }
     const int ws = winw + 16;
     const size_t plane = (size_t)ws * winh;
-    const int ntiles = amaze_tile_count(winw, winh), nblocks = ntiles < AMZ_MAX_BLOCKS ? ntiles : AMZ_MAX_BLOCKS;
+    const int ntiles = amaze_tile_count(winw, winh), nblocks = ntiles < amz_blocks() ? ntiles : amz_blocks();
     const size_t need = 4 * plane * sizeof(float) + 256 + (size_t)nblocks * amaze::WS_BYTES;
     Slot *s = acquire_slot(ctx);
     cudaSetDevice(ctx->device);

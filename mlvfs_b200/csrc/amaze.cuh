@@ -4,8 +4,10 @@
 
 #include "common.cuh"
 
-#define AMZ_THREADS 256
-#define AMZ_MAX_BLOCKS (148 * 3)      // persistent tile blocks; each owns a 2.3 MB workspace
+#define AMZ_THREADS_MAX 1024
+#define AMZ_MAX_BLOCKS (148 * 6)      // upper bound of persistent tile blocks; each owns a 2.3 MB workspace
+int amz_threads();                    // threads per tile block and tile blocks per SM (tunable: MLVB_AMZ_THREADS,
+int amz_blocks();                     // MLVB_AMZ_BLOCKS_PER_SM), chosen for latency hiding on the global workspace
 
 struct AmazeScratch {
     float *rawf, *red, *green, *blue;  // h rows of w+16 floats (hdr.c:967-975)
