@@ -115,6 +115,9 @@ int mlvb_get_stripes(mlvb_context *ctx, const char *mlv_filename, int *needed, i
 int mlvb_get_bad_pixels(mlvb_context *ctx, uint64_t file_guid, int aggressive, int *xy, int cap);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t mlvb_launch_count(mlvb_context *ctx);
+/* Introspection for tests: how often a given kernel path was taken.  which: 0 = fused single-ISO strip kernel
+ * (per-frame and small batches), 1 = fused single-ISO wide kernel (large batches). */
+uint64_t mlvb_path_count(mlvb_context *ctx, int which);
 /* Per-stage device timing for the roofline report: between begin and end every stage of the
  * batch / per-frame pipeline is bracketed by CUDA events on its own stream.  Stage ids:
  * 0 unpack, 1 bad/focus-pixel fix, 2 chroma smoothing (+fused stripes), 3 stripes apply,

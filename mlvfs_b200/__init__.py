@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "mlvb_context_create", "mlvb_context_destroy", "mlvb_default_context", "mlvb_device_count",
     "mlvb_host_alloc", "mlvb_host_free", "mlvb_process_frame", "mlvb_submit", "mlvb_wait",
     "mlvb_process_batch_device", "mlvb_reset_clip_state", "mlvb_seed_dither", "mlvb_get_stripes",
-    "mlvb_get_bad_pixels", "mlvb_launch_count", "mlvb_profile_begin", "mlvb_profile_end",
+    "mlvb_get_bad_pixels", "mlvb_launch_count", "mlvb_path_count", "mlvb_profile_begin", "mlvb_profile_end",
     "dng_get_image_data", "dng_get_image_size", "get_image_data", "get_raw2evf", "get_raw2ev", "get_ev2raw",
     "chroma_smooth", "fix_bad_pixels", "fix_focus_pixels", "free_focus_pixel_maps",
     "stripes_get_correction", "stripes_new_correction", "stripes_free_corrections",
@@ -108,6 +108,8 @@ def lib():
         L.mlvb_get_bad_pixels.argtypes = [vp, C.c_uint64, C.c_int, vp, C.c_int]
         L.mlvb_launch_count.restype = C.c_uint64
         L.mlvb_launch_count.argtypes = [vp]
+        L.mlvb_path_count.restype = C.c_uint64
+        L.mlvb_path_count.argtypes = [vp, C.c_int]
         L.mlvb_profile_begin.argtypes = [vp]
         L.mlvb_profile_end.argtypes = [vp, vp, vp, C.c_int]
         L.dng_get_image_data.restype = sz
@@ -213,6 +215,9 @@ class Context:
 
     def launch_count(self):
         return int(lib().mlvb_launch_count(self._h))
+
+    def path_count(self, which):
+        return int(lib().mlvb_path_count(self._h, int(which)))
 
     STAGES = ["unpack", "pixfix", "chroma", "stripes", "pattern", "dualiso", "lj92", "other"]
 

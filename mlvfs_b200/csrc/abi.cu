@@ -369,6 +369,7 @@ int mlvb_profile_end(mlvb_context *ctx, float *ms_per_stage, int *spans_per_stag
 }
 
 uint64_t mlvb_launch_count(mlvb_context *ctx) { return ctx ? (uint64_t)ctx->launches : 0; }
+uint64_t mlvb_path_count(mlvb_context *ctx, int which) { return (ctx && which >= 0 && which < 2) ? (uint64_t)ctx->path_count[which] : 0; }
 
 // ------------------------------------------------------------------ host-buffer pipeline
 

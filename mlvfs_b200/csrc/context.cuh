@@ -105,6 +105,7 @@ struct mlvb_context {
     void *d_batch_aux = nullptr; size_t batch_aux_cap = 0;        // per-frame codec status of a batch
 
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> path_count[2] = {{0}, {0}};   // fused strip kernel, fused wide kernel (mlvb_path_count)
 
     // optional per-stage device timing (mlvb_profile_begin / mlvb_profile_end), bench.py's roofline leg
     bool profiling = false;

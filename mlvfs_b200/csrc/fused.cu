@@ -20,6 +20,8 @@
 // other bit depths or smoothing sizes use the general multi-kernel path.
 #include <algorithm>
 #include <map>
+#include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "context.cuh"
@@ -213,18 +215,24 @@ fused3_strip_kernel(const FusedParams P)
 
 }  // namespace
 
-// Per-clip patch buckets for the fused kernel (built once, with the bad-pixel map).
+#include "fused_wide.cuh"
+
+// Per-clip patch buckets for the fused kernels (built once, with the bad-pixel map).
 struct FusedPatchPlan {
     int w = 0, h = 0, crop_x = 0, crop_y = 0;
     unsigned n_entries = 0;
     PatchItem *d_items = nullptr;
     unsigned *d_bucket_start = nullptr;
+    WideItem *d_wide_items = nullptr;           // wide kernel: entries by (strip, quad row)
+    unsigned *d_wide_row_start = nullptr;
     struct Vals { uint16_t *d = nullptr; size_t cap = 0; };
     std::map<cudaStream_t, Vals> vals;          // repaired values of the frames in flight, one buffer per stream
     ~FusedPatchPlan()
     {
         if (d_items) cudaFree(d_items);
         if (d_bucket_start) cudaFree(d_bucket_start);
+        if (d_wide_items) cudaFree(d_wide_items);
+        if (d_wide_row_start) cudaFree(d_wide_row_start);
         for (auto &kv : vals) if (kv.second.d) cudaFree(kv.second.d);
     }
 };
@@ -262,7 +270,61 @@ static int build_patch_plan(const PixelList &list, int w, int h, int crop_x, int
     MLVB_CUDA_OK(cudaMalloc(&plan->d_bucket_start, start.size() * sizeof(unsigned)));
     if (!items.empty()) MLVB_CUDA_OK(cudaMemcpy(plan->d_items, items.data(), items.size() * sizeof(PatchItem), cudaMemcpyHostToDevice));
     MLVB_CUDA_OK(cudaMemcpy(plan->d_bucket_start, start.data(), start.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+
+    // wide kernel: a strip is a 512-pixel window starting at pixel 480 * s - 16 (lanes 0 and 31 are halo)
+    const int wstrips = ceil_div(w, 480);
+    std::vector<std::vector<WideItem>> wb((size_t)wstrips * ph);
+    for (size_t m = 0; m < list.host.size(); m++) {
+        const int x = list.host[m].x - crop_x, y = list.host[m].y - crop_y;
+        if (!(x > 2 && x < w - 3 && y > 2 && y < h - 3)) continue;
+        for (int s = 0; s < wstrips; s++) {
+            const int px = x - (480 * s - 16);
+            if (px < 0 || px >= 512) continue;
+            wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)px, (unsigned short)((y & 1) * 2 + (x & 1)), (unsigned)m});
+        }
+    }
+    std::vector<unsigned> wstart((size_t)wstrips * (ph + 1), 0);
+    std::vector<WideItem> witems;
+    for (int s = 0; s < wstrips; s++) {
+        for (int q = 0; q < ph; q++) {
+            wstart[(size_t)s * (ph + 1) + q] = (unsigned)witems.size();
+            auto &v = wb[(size_t)s * ph + q];
+            witems.insert(witems.end(), v.begin(), v.end());
+        }
+        wstart[(size_t)s * (ph + 1) + ph] = (unsigned)witems.size();
+    }
+    MLVB_CUDA_OK(cudaMalloc(&plan->d_wide_items, std::max<size_t>(witems.size(), 1) * sizeof(WideItem)));
+    MLVB_CUDA_OK(cudaMalloc(&plan->d_wide_row_start, wstart.size() * sizeof(unsigned)));
+    if (!witems.empty()) MLVB_CUDA_OK(cudaMemcpy(plan->d_wide_items, witems.data(), witems.size() * sizeof(WideItem), cudaMemcpyHostToDevice));
+    MLVB_CUDA_OK(cudaMemcpy(plan->d_wide_row_start, wstart.data(), wstart.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     return MLVB_OK;
+}
+
+// The wide kernel needs enough warp rows (frames x strips x quad rows) to occupy one persistent CTA per SM;
+// MLVB_WIDE_MIN_ROWS overrides the threshold (tests run it on small batches).
+static long long wide_min_rows(const mlvb_context *ctx)
+{
+    const char *e = getenv("MLVB_WIDE_MIN_ROWS");
+    if (e && *e) return atoll(e);
+    return 8LL * ctx->sm_count * FW_WARPS;
+}
+
+// Segment length of the wide kernel: items = frames x strips x segments are dealt round-robin to
+// sm_count x 16 persistent warps; pick the split that loses least to the last partial round and to the two
+// halo rows every segment re-reads.
+static int wide_pick_segments(int nframes, int nstrips, int ph, int nwarps)
+{
+    int best = 1;
+    double best_eff = 0.0;
+    for (int nseg = 1; nseg <= std::max(1, ph / 8); nseg++) {
+        const int rows = ceil_div(ph, nseg);
+        if (ceil_div(ph, rows) != nseg) continue;
+        const long long items = (long long)nframes * nstrips * nseg;
+        const long long rounds = (items + nwarps - 1) / nwarps;
+        const double eff = (double)items / (double)(rounds * nwarps) * rows / (rows + 2.0);
+        if (eff > best_eff) { best_eff = eff; best = nseg; }
+    }
+    return best;
 }
 
 // Returns MLVB_OK when the fused kernel was enqueued, 1 when this call is not eligible (use the general
@@ -350,12 +412,39 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         ctx->launches += 1;
         P.items = plan->d_items; P.bucket_start = plan->d_bucket_start; P.vals = d_vals; P.n_entries = plan->n_entries;
     }
-    {
+    // batches large enough to keep one persistent CTA per SM busy take the wide kernel (fused_wide.cuh)
+    bool wide = ctx->ev2raw_octaves_ok && ctx->sm_count > 0 && (g.w % 64) == 0 && ((uintptr_t)d_out % 16) == 0 &&
+                (out_stride_px % 8) == 0 && (payload_stride % 16) == 0 && getenv("MLVB_NO_WIDE") == nullptr &&
+                (long long)nframes * ceil_div(g.w, 480) * (g.h / 2) >= wide_min_rows(ctx);
+    for (int i = 0; i < 8 && P.stripes; i++) wide = wide && P.coef[i] < (1 << 18);
+    if (wide) {
+        WideParams Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.packed = P.packed; Q.payload_stride = payload_stride; Q.out = d_out; Q.out_stride = out_stride_px;
+        Q.w = g.w; Q.h = g.h; Q.black = g.black; Q.raw2ev = P.raw2ev; Q.ev2raw13 = ctx->luts.ev2raw_pos + 13 * MLVB_EV_RES;
+        Q.black16 = P.black16; Q.white16 = P.white16;
+        for (int i = 0; i < 8; i++) Q.coef[i] = (unsigned)P.coef[i];
+        if (plan) { Q.items = plan->d_wide_items; Q.row_start = plan->d_wide_row_start; Q.vals = P.vals; Q.n_entries = plan->n_entries; }
+        Q.nstrips = ceil_div(g.w, 480); Q.nframes = nframes;
+        Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, ctx->sm_count * FW_WARPS);
+        Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
+        static std::once_flag once;
+        std::call_once(once, [] {
+            cudaFuncSetAttribute(fused3_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+            cudaFuncSetAttribute(fused3_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+        });
+        StageTimer t(ctx, ST_CHROMA, st);
+        if (P.stripes) fused3_wide_kernel<true><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        else fused3_wide_kernel<false><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        ctx->launches += 1;
+        ctx->path_count[1] += 1;
+    } else {
         StageTimer t(ctx, ST_CHROMA, st);
         dim3 grid(ceil_div(P.nstrips, FS_WARPS), ceil_div(g.h / 2, FS_ROWS), nframes);
         if (P.stripes) fused3_strip_kernel<true><<<grid, FS_WARPS * 32, 0, st>>>(P);
         else fused3_strip_kernel<false><<<grid, FS_WARPS * 32, 0, st>>>(P);
         ctx->launches += 1;
+        ctx->path_count[0] += 1;
     }
     MLVB_CUDA_OK(cudaGetLastError());
     return MLVB_OK;

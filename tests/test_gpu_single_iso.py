@@ -210,3 +210,35 @@ def test_fused_kernel_odd_geometries(fresh_ctx, oracle, w, h, stripes):
         out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(fr), o, name)
         assert res.status == 0
         assert np.array_equal(out, want[i]), (i, int(np.count_nonzero(out != want[i])))
+
+
+@pytest.mark.parametrize("w,h,n,stripes,density", [(1920, 1080, 8, 1, 3e-5), (640, 362, 5, 1, 3e-4), (1088, 94, 3, 0, 3e-4),
+                                                   (3840, 160, 3, 1, 1e-4)])
+def test_wide_fused_kernel_batches(fresh_ctx, oracle, monkeypatch, w, h, n, stripes, density):
+    """Large device batches of the C2 chain take the persistent wide kernel (fused_wide.cuh: shared-memory EV
+    tables, 8 quad columns per lane, cp.async row staging, patches written into the staged bytes).  Same frames
+    as the oracle, bit for bit, including strip / segment seams, image borders and a dense bad-pixel list."""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("MLVB_WIDE_MIN_ROWS", "1")
+    hdr = _hdr(w, h)
+    ri = hdr.rawi_hdr.raw_info
+    frames = [synth.make_frame(w, h, i, hot_cold=True, stripes=bool(stripes), bad_density=density) for i in range(n)]
+    want, _ = oracle.single_iso_chain(frames, ri.black_level, ri.white_level, ri.frame_size,
+                                      chroma_smooth_method=3, fix_bad_pixels=1, fix_stripes=stripes)
+    packed = np.stack([synth.pack_bits(f) for f in frames])
+    stride = packed.shape[1] * 2
+    assert stride % 16 == 0
+    d_in = torch.from_numpy(packed.view(np.int16)).cuda()
+    d_out = torch.empty((n, h * w), dtype=torch.int16, device="cuda")
+    o = M.Options(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=stripes)
+    name = f"wide_{w}x{h}.MLV"
+    for rep in range(3):        # pass 0 builds the per-clip state on the general path
+        d_out.zero_()
+        fresh_ctx.process_batch_device(hdr, o, name, d_in.data_ptr(), stride, stride, d_out.data_ptr(), h * w, n,
+                                       torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), (rep, i, int(np.count_nonzero(got[i] != want[i])),
+                                                     np.argwhere(got[i] != want[i])[:8].tolist())
+    assert fresh_ctx.path_count(1) >= 2, "the wide kernel did not run"
