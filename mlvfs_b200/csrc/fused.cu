@@ -271,15 +271,15 @@ static int build_patch_plan(const PixelList &list, int w, int h, int crop_x, int
     if (!items.empty()) MLVB_CUDA_OK(cudaMemcpy(plan->d_items, items.data(), items.size() * sizeof(PatchItem), cudaMemcpyHostToDevice));
     MLVB_CUDA_OK(cudaMemcpy(plan->d_bucket_start, start.data(), start.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
 
-    // wide kernel: a strip is a 512-pixel window starting at pixel 480 * s - 16 (lanes 0 and 31 are halo)
-    const int wstrips = ceil_div(w, 480);
+    // wide kernel: a strip is a window of 32 lanes starting one lane left of pixel FW_STRIP_PX * s (lanes 0 and 31 are halo)
+    const int wstrips = ceil_div(w, FW_STRIP_PX);
     std::vector<std::vector<WideItem>> wb((size_t)wstrips * ph);
     for (size_t m = 0; m < list.host.size(); m++) {
         const int x = list.host[m].x - crop_x, y = list.host[m].y - crop_y;
         if (!(x > 2 && x < w - 3 && y > 2 && y < h - 3)) continue;
         for (int s = 0; s < wstrips; s++) {
-            const int px = x - (480 * s - 16);
-            if (px < 0 || px >= 512) continue;
+            const int px = x - (FW_STRIP_PX * s - FW_LANE_PX);
+            if (px < 0 || px >= FW_WINDOW_PX) continue;
             wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)px, (unsigned short)((y & 1) * 2 + (x & 1)), (unsigned)m});
         }
     }
@@ -415,7 +415,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
     // batches large enough to keep one persistent CTA per SM busy take the wide kernel (fused_wide.cuh)
     bool wide = ctx->ev2raw_octaves_ok && ctx->sm_count > 0 && (g.w % 64) == 0 && ((uintptr_t)d_out % 16) == 0 &&
                 (out_stride_px % 8) == 0 && (payload_stride % 16) == 0 && getenv("MLVB_NO_WIDE") == nullptr &&
-                (long long)nframes * ceil_div(g.w, 480) * (g.h / 2) >= wide_min_rows(ctx);
+                (long long)nframes * ceil_div(g.w, FW_STRIP_PX) * (g.h / 2) >= wide_min_rows(ctx);
     for (int i = 0; i < 8 && P.stripes; i++) wide = wide && P.coef[i] < (1 << 18);
     if (wide) {
         WideParams Q;
@@ -425,7 +425,8 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         Q.black16 = P.black16; Q.white16 = P.white16;
         for (int i = 0; i < 8; i++) Q.coef[i] = (unsigned)P.coef[i];
         if (plan) { Q.items = plan->d_wide_items; Q.row_start = plan->d_wide_row_start; Q.vals = P.vals; Q.n_entries = plan->n_entries; }
-        Q.nstrips = ceil_div(g.w, 480); Q.nframes = nframes;
+        Q.nstrips = ceil_div(g.w, FW_STRIP_PX); Q.nframes = nframes;
+        Q.one = 1; Q.mone = -1;
         Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, ctx->sm_count * FW_WARPS);
         Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
         static std::once_flag once;

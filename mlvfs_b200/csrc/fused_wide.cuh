@@ -2,18 +2,18 @@
 // chroma smoothing + stripe gains, one pass over HBM), written for the instruction roofline that bounds
 // the strip kernel in fused.cu (profiles/r01d_fused3_ncu.md):
 //
-//   * one persistent 512-thread CTA per SM; both EV tables live in shared memory: raw2ev for this black
-//     level (16384 x int32, 64 KB) and the top octave of ev2raw (32768 x uint16, 64 KB) from which every
-//     other octave is a right shift (ev2raw[e] == ev2raw[13 EV + e mod EV] >> (13 - e / EV), verified
-//     entry by entry when the context is created) -- no table gather goes through the L1 tag stage;
-//   * a lane owns EIGHT adjacent RGGB quad columns (16 pixels = 28 stream bytes per row), so every bit
-//     offset is a compile-time constant (one shift + one mask per pixel), neighbouring sorted columns are
-//     already in the lane's registers (12 shuffles per 8 quads instead of per quad) and the stripe gains
-//     are constant-bank operands;
+//   * one persistent CTA per SM; both EV tables live in shared memory: raw2ev for this black level
+//     (16384 x int32, 64 KB) and the top octave of ev2raw (32768 x uint16, 64 KB) from which every other
+//     octave is a right shift (ev2raw[e] == ev2raw[13 EV + e mod EV] >> (13 - e / EV), verified entry by
+//     entry when the context is created) -- no table gather goes through the L1 tag stage;
+//   * a lane owns FW_COLS adjacent RGGB quad columns (2 * FW_COLS pixels of a row), so every bit offset is a
+//     compile-time constant (one shift + one mask per pixel), neighbouring sorted columns are mostly in the
+//     lane's own registers (12 shuffles per FW_COLS quads instead of per quad) and every stripe gain has a
+//     fixed column;
 //   * the packed rows are staged by cp.async (16-byte chunks, L2 only) into a per-warp double buffer, one
 //     quad row ahead; bad-pixel patches are written into the staged bytes before extraction;
-//   * sort3 / med3 are evaluated as (min3, max3, a + b + c - min3 - max3): the additions can issue on the
-//     FMA pipe (IMAD) while the min/max run on the ALU pipe, instead of 6 / 4 ALU-pipe min/max.
+//   * sort3 / med3 are evaluated as (min3, max3, a + b + c - min3 - max3): the additions issue on the FMA
+//     pipe (IMAD) while the min/max run on the ALU pipe, instead of 6 / 4 ALU-pipe min/max.
 //
 // Arithmetic is the same 32-bit wrap-around integer arithmetic as fused3_strip_kernel / the reference
 // (cs.c:49-84, chroma_smooth.c:22-71, stripes.c:250-266); results are bit-identical.
@@ -21,20 +21,32 @@
 
 namespace {
 
-constexpr int FW_WARPS = 12;
+#ifndef FW_COLS_CFG
+#define FW_COLS_CFG 4
+#endif
+#ifndef FW_WARPS_CFG
+#define FW_WARPS_CFG 16
+#endif
+constexpr int FW_COLS = FW_COLS_CFG;             // quad columns per lane (4 or 8)
+constexpr int FW_WARPS = FW_WARPS_CFG;
 constexpr int FW_THREADS = FW_WARPS * 32;
-constexpr int FW_COLS = 8;                       // quad columns per lane
-constexpr int FW_ROWBYTES = 960;                 // staged bytes per pixel row and warp (60 chunks of 16 B)
-constexpr int FW_STAGE_PER_WARP = 4 * FW_ROWBYTES;   // 2 slots x 2 pixel rows
+constexpr int FW_LANE_PX = 2 * FW_COLS;          // pixels of a row per lane
+constexpr int FW_LANE_BYTES = FW_LANE_PX * 14 / 8;   // 14 or 28 stream bytes
+constexpr int FW_STRIP_PX = 30 * FW_LANE_PX;     // pixels a warp finishes per row (lanes 0 and 31 are halo)
+constexpr int FW_WINDOW_PX = 32 * FW_LANE_PX;
+constexpr int FW_NW = FW_LANE_PX * 14 / 32 + ((FW_LANE_PX * 14) % 32 ? 1 : 0);   // stream words holding a lane's pixels (4 or 7)
+constexpr int FW_ROWBYTES = FW_COLS == 4 ? 480 : 960;   // staged bytes per pixel row and warp (16-byte chunks)
+constexpr int FW_STAGE_PER_WARP = 4 * FW_ROWBYTES;       // 2 slots x 2 pixel rows
 constexpr int FW_SMEM_R2E = 16384 * 4;
 constexpr int FW_SMEM_T13 = 32768 * 2;
 constexpr int FW_SMEM_BYTES = FW_SMEM_R2E + FW_SMEM_T13 + FW_WARPS * FW_STAGE_PER_WARP;
+static_assert(FW_COLS == 4 || FW_COLS == 8, "a lane owns 8 or 16 pixels of a row");
 
 extern __shared__ __align__(16) uint8_t fw_smem[];
 #define FW_R2E(v) (reinterpret_cast<const int *>(fw_smem)[(v)])
 #define FW_T13(f) (reinterpret_cast<const uint16_t *>(fw_smem + FW_SMEM_R2E)[(f)])
 
-struct WideItem { unsigned short px; unsigned short sub; unsigned entry; };   // px: pixel column inside the strip's 512-pixel window
+struct WideItem { unsigned short px; unsigned short sub; unsigned entry; };   // px: pixel column inside the strip's window
 
 struct WideParams {
     const uint8_t *packed; size_t payload_stride;
@@ -44,6 +56,7 @@ struct WideParams {
     const uint16_t *ev2raw13;         // ev2raw[13 EV ...], 32768 entries
     int black16, white16;
     unsigned coef[8];
+    int one, mone;                    // +1 / -1: multipliers of the FMA-pipe additions (opaque to the compiler)
     const WideItem *items; const unsigned *row_start; const uint16_t *vals; unsigned n_entries;
     int nstrips, nseg, seg_rows, nframes;
 };
@@ -59,30 +72,49 @@ __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_g
 
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
-// exact in wrap-around arithmetic: the three values are a permutation of (min, med, max)
-__device__ __forceinline__ int imed3(int a, int b, int c)
+
+struct WideConst { uint32_t black, thr, white; uint32_t coef[8]; int one, mone; };
+
+// a * m + b on the FMA pipe (IMAD with a register multiplier the compiler cannot fold): the min/max network
+// keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
+__device__ __forceinline__ int fma_add(int a, int m, int b)
 {
-    const unsigned s = (unsigned)a + (unsigned)b + (unsigned)c;
-    return (int)(s - (unsigned)imin3(a, b, c) - (unsigned)imax3(a, b, c));
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
+    return d;
+}
+// the middle of three = a + b + c - min - max; exact in wrap-around arithmetic (a permutation of the three)
+__device__ __forceinline__ int mid_of(int a, int b, int c, int lo, int hi, const WideConst &K)
+{
+#ifndef FW_SUMS_ON_FMA
+    return (int)((unsigned)a + (unsigned)b + (unsigned)c - (unsigned)lo - (unsigned)hi);
+#else
+    return fma_add(hi, K.mone, fma_add(lo, K.mone, fma_add(c, K.one, fma_add(a, K.one, b))));
+#endif
+}
+__device__ __forceinline__ int imed3(int a, int b, int c, const WideConst &K)
+{
+    return mid_of(a, b, c, imin3(a, b, c), imax3(a, b, c), K);
 }
 
-// pixel I (0..15) of a lane's 16-pixel group; W[] are the group's seven 32-bit words in stream order
+// pixel I of a lane's pixel group; W[] are the group's 32-bit words in stream order
 template <int I>
-__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[7])
+__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW])
 {
     constexpr int bit = 14 * I, j = bit >> 5, s = bit & 31;
-    if constexpr (s <= 18) return (W[j] >> (18 - s)) & 0x3FFFu;
-    else return __funnelshift_l(W[j + 1], W[j], s) >> 18;
+    uint32_t v;
+    if constexpr (s <= 18) v = (W[j] >> (18 - s)) & 0x3FFFu;
+    else v = __funnelshift_l(W[j + 1], W[j], s) >> 18;
+    asm("" : "+r"(v));          // keep the table address a plain v * 4 (one IMAD) instead of a second shift + mask of W
+    return v;
 }
 
-struct WideRow {                                  // per-lane state of one quad row (8 quad columns)
+struct WideRow {                                  // per-lane state of one quad row
     int dr[FW_COLS], db[FW_COLS];                 // ev(r) - ge, ev(b) - ge
     int ge[FW_COLS];
     uint32_t r[FW_COLS], b[FW_COLS];              // raw R / B samples
     uint32_t g1s[FW_COLS], g2[FW_COLS];           // finished G1 << 16, finished G2
 };
-
-struct WideConst { uint32_t black, thr, white; uint32_t coef[8]; };
 
 template <bool STRIPES, int IDX>
 __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
@@ -97,8 +129,7 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
 }
 
 template <bool STRIPES, int C>
-__device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[7], const uint32_t (&B)[7], const int *s_r2e,
-                                                const WideConst &P, WideRow &R)
+__device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[FW_NW], const uint32_t (&B)[FW_NW], const WideConst &K, WideRow &R)
 {
     const uint32_t r = wide_px<2 * C>(T), g1 = wide_px<2 * C + 1>(T);
     const uint32_t g2 = wide_px<2 * C>(B), b = wide_px<2 * C + 1>(B);
@@ -108,23 +139,23 @@ __device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[7], const ui
     R.db[C] = wsub(FW_R2E(b), ge);
     R.r[C] = r;
     R.b[C] = b;
-    R.g1s[C] = wide_gain<STRIPES, (2 * C + 1) & 7>(g1, P) << 16;
-    R.g2[C] = wide_gain<STRIPES, (2 * C) & 7>(g2, P);
+    R.g1s[C] = wide_gain<STRIPES, (2 * C + 1) & 7>(g1, K) << 16;
+    R.g2[C] = wide_gain<STRIPES, (2 * C) & 7>(g2, K);
 }
 
 struct Tri { int lo, mid, hi; };
 
-__device__ __forceinline__ Tri wide_sort3(int a, int b, int c)
+__device__ __forceinline__ Tri wide_sort3(int a, int b, int c, const WideConst &K)
 {
     Tri t;
     t.lo = imin3(a, b, c);
     t.hi = imax3(a, b, c);
-    t.mid = (int)((unsigned)a + (unsigned)b + (unsigned)c - (unsigned)t.lo - (unsigned)t.hi);
+    t.mid = mid_of(a, b, c, t.lo, t.hi, K);
     return t;
 }
-__device__ __forceinline__ int wide_med9(const Tri &l, const Tri &m, const Tri &r)
+__device__ __forceinline__ int wide_med9(const Tri &l, const Tri &m, const Tri &r, const WideConst &K)
 {
-    return imed3(imax3(l.lo, m.lo, r.lo), imed3(l.mid, m.mid, r.mid), imin3(l.hi, m.hi, r.hi));
+    return imed3(imax3(l.lo, m.lo, r.lo), imed3(l.mid, m.mid, r.mid, K), imin3(l.hi, m.hi, r.hi), K);
 }
 __device__ __forceinline__ Tri tri_shfl_up(const Tri &t)
 {
@@ -142,7 +173,7 @@ __device__ __forceinline__ Tri tri_shfl_down(const Tri &t)
 // finish quad column C of the middle row: smoothed R/B (chroma_smooth.c:30-68), stripe gains, packed words
 template <bool STRIPES, int C>
 __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb, int ge_thr, bool edge_first, bool edge_last,
-                                                const uint16_t *s_t13, const WideConst &P, uint32_t &top, uint32_t &bot)
+                                                const WideConst &K, uint32_t &top, uint32_t &bot)
 {
     uint32_t r = M.r[C], b = M.b[C];
     const int ge = M.ge[C];
@@ -152,68 +183,84 @@ __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb
     const int er = wadd(ge, mr), eb = wadd(ge, mb);
     if (go && er > MLVB_EV_RES && eb > MLVB_EV_RES) {
         const int cr = min(er, MLVB_EV_MAX), cb = min(eb, MLVB_EV_MAX);
-        r = ((uint32_t)FW_T13(cr & (MLVB_EV_RES - 1)) >> (13 - (cr >> 15))) + P.black;
-        b = ((uint32_t)FW_T13(cb & (MLVB_EV_RES - 1)) >> (13 - (cb >> 15))) + P.black;
+        r = ((uint32_t)FW_T13(cr & (MLVB_EV_RES - 1)) >> (13 - (cr >> 15))) + K.black;
+        b = ((uint32_t)FW_T13(cb & (MLVB_EV_RES - 1)) >> (13 - (cb >> 15))) + K.black;
     }
-    r = wide_gain<STRIPES, (2 * C) & 7>(r, P);
-    b = wide_gain<STRIPES, (2 * C + 1) & 7>(b, P);
+    r = wide_gain<STRIPES, (2 * C) & 7>(r, K);
+    b = wide_gain<STRIPES, (2 * C + 1) & 7>(b, K);
     top = r | M.g1s[C];
     bot = M.g2[C] | (b << 16);
 }
 
-// One row step: take quad row `qr_new` from the staged bytes into N (overwriting the row two above), and
-// write the finished middle row M (quad row qr_new - 1) when `emit`.
+template <int C> struct ColTag { static constexpr int value = C; };
+
+// One row step: take a new quad row from the staged bytes into N (overwriting the row two above, whose
+// dr / db are still read for the column sorts), and write the finished middle row M when `emit`.
+//   lane_off : byte offset of the lane's first word inside a staged row (4-byte aligned)
+//   perm     : byte-permute selector turning two loaded words into one stream-order word
 template <bool STRIPES>
-__device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const uint8_t *stage_rows, int lane_off, bool have_new,
+__device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const uint8_t *stage_rows, int lane_off, uint32_t perm,
                                           bool emit, int ge_thr, bool edge_first, bool edge_last, bool writer, uint16_t *orow, int w,
-                                          const int *s_r2e, const uint16_t *s_t13, const WideConst &P)
+                                          const WideConst &K)
 {
-    uint32_t T[7], B[7];
-    if (have_new) {
+    uint32_t T[FW_NW], B[FW_NW];
+    if constexpr (FW_COLS == 8) {                   // 28 bytes per lane: always word aligned
 #pragma unroll
-        for (int j = 0; j < 7; j++) {
+        for (int j = 0; j < FW_NW; j++) {
             T[j] = __byte_perm(*reinterpret_cast<const uint32_t *>(stage_rows + lane_off + 4 * j), 0, 0x1032);
             B[j] = __byte_perm(*reinterpret_cast<const uint32_t *>(stage_rows + FW_ROWBYTES + lane_off + 4 * j), 0, 0x1032);
         }
-    } else {
+    } else {                                        // 14 bytes per lane: every other lane starts in the middle of a word
+        uint32_t lt[FW_NW + 1], lb[FW_NW + 1];
 #pragma unroll
-        for (int j = 0; j < 7; j++) T[j] = B[j] = 0u;
+        for (int j = 0; j <= FW_NW; j++) {
+            lt[j] = *reinterpret_cast<const uint32_t *>(stage_rows + lane_off + 4 * j);
+            lb[j] = *reinterpret_cast<const uint32_t *>(stage_rows + FW_ROWBYTES + lane_off + 4 * j);
+        }
+#pragma unroll
+        for (int j = 0; j < FW_NW; j++) {
+            T[j] = __byte_perm(lt[j], lt[j + 1], perm);
+            B[j] = __byte_perm(lb[j], lb[j + 1], perm);
+        }
     }
     // sorted columns of (row above = N's old contents, M, new row); N is replaced column by column
     Tri tr[FW_COLS + 2], tb[FW_COLS + 2];            // index c + 1
     auto do_col = [&](auto cc) {
         constexpr int C = decltype(cc)::value;
         const int adr = N.dr[C], adb = N.db[C];
-        wide_ingest_col<STRIPES, C>(T, B, s_r2e, P, N);
-        tr[C + 1] = wide_sort3(adr, M.dr[C], N.dr[C]);
-        tb[C + 1] = wide_sort3(adb, M.db[C], N.db[C]);
+        wide_ingest_col<STRIPES, C>(T, B, K, N);
+        tr[C + 1] = wide_sort3(adr, M.dr[C], N.dr[C], K);
+        tb[C + 1] = wide_sort3(adb, M.db[C], N.db[C], K);
     };
-    do_col(std::integral_constant<int, 0>{});
-    do_col(std::integral_constant<int, 7>{});
-    tr[0] = tri_shfl_up(tr[8]);   tb[0] = tri_shfl_up(tb[8]);
-    tr[9] = tri_shfl_down(tr[1]); tb[9] = tri_shfl_down(tb[1]);
     uint32_t top[FW_COLS], bot[FW_COLS];
     auto fin_col = [&](auto cc) {
         constexpr int C = decltype(cc)::value;
-        const int mr = wide_med9(tr[C], tr[C + 1], tr[C + 2]);
-        const int mb = wide_med9(tb[C], tb[C + 1], tb[C + 2]);
-        wide_finish_col<STRIPES, C>(M, mr, mb, ge_thr, edge_first, edge_last, s_t13, P, top[C], bot[C]);
+        const int mr = wide_med9(tr[C], tr[C + 1], tr[C + 2], K);
+        const int mb = wide_med9(tb[C], tb[C + 1], tb[C + 2], K);
+        wide_finish_col<STRIPES, C>(M, mr, mb, ge_thr, edge_first, edge_last, K, top[C], bot[C]);
     };
-    do_col(std::integral_constant<int, 1>{}); fin_col(std::integral_constant<int, 0>{});
-    do_col(std::integral_constant<int, 2>{}); fin_col(std::integral_constant<int, 1>{});
-    do_col(std::integral_constant<int, 3>{}); fin_col(std::integral_constant<int, 2>{});
-    do_col(std::integral_constant<int, 4>{}); fin_col(std::integral_constant<int, 3>{});
-    if (emit && writer) {
-        __stcs(reinterpret_cast<uint4 *>(orow), make_uint4(top[0], top[1], top[2], top[3]));
-        __stcs(reinterpret_cast<uint4 *>(orow + w), make_uint4(bot[0], bot[1], bot[2], bot[3]));
+    do_col(ColTag<0>{});
+    do_col(ColTag<FW_COLS - 1>{});
+    tr[0] = tri_shfl_up(tr[FW_COLS]);           tb[0] = tri_shfl_up(tb[FW_COLS]);
+    tr[FW_COLS + 1] = tri_shfl_down(tr[1]);     tb[FW_COLS + 1] = tri_shfl_down(tb[1]);
+    do_col(ColTag<1>{}); fin_col(ColTag<0>{});
+    do_col(ColTag<2>{}); fin_col(ColTag<1>{});
+    if constexpr (FW_COLS == 8) {
+        do_col(ColTag<3>{}); fin_col(ColTag<2>{});
+        do_col(ColTag<4>{}); fin_col(ColTag<3>{});
+        if (emit && writer) {
+            __stcs(reinterpret_cast<uint4 *>(orow), make_uint4(top[0], top[1], top[2], top[3]));
+            __stcs(reinterpret_cast<uint4 *>(orow + w), make_uint4(bot[0], bot[1], bot[2], bot[3]));
+        }
+        do_col(ColTag<5>{}); fin_col(ColTag<4>{});
+        do_col(ColTag<6>{}); fin_col(ColTag<5>{});
     }
-    do_col(std::integral_constant<int, 5>{}); fin_col(std::integral_constant<int, 4>{});
-    do_col(std::integral_constant<int, 6>{}); fin_col(std::integral_constant<int, 5>{});
-    fin_col(std::integral_constant<int, 6>{});
-    fin_col(std::integral_constant<int, 7>{});
+    fin_col(ColTag<FW_COLS - 2>{});
+    fin_col(ColTag<FW_COLS - 1>{});
     if (emit && writer) {
-        __stcs(reinterpret_cast<uint4 *>(orow) + 1, make_uint4(top[4], top[5], top[6], top[7]));
-        __stcs(reinterpret_cast<uint4 *>(orow + w) + 1, make_uint4(bot[4], bot[5], bot[6], bot[7]));
+        constexpr int o = FW_COLS - 4;
+        __stcs(reinterpret_cast<uint4 *>(orow + 2 * o), make_uint4(top[o], top[o + 1], top[o + 2], top[o + 3]));
+        __stcs(reinterpret_cast<uint4 *>(orow + w + 2 * o), make_uint4(bot[o], bot[o + 1], bot[o + 2], bot[o + 3]));
     }
 }
 
@@ -256,6 +303,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
     K.black = (uint32_t)P.black16; K.thr = (uint32_t)P.black16 + 64u; K.white = (uint32_t)P.white16;
 #pragma unroll
     for (int i = 0; i < 8; i++) K.coef[i] = P.coef[i];
+    K.one = P.one; K.mone = P.mone;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = fw_smem + FW_SMEM_R2E + FW_SMEM_T13 + warp * FW_STAGE_PER_WARP;
     const int w = P.w, ph = P.h >> 1;
@@ -268,13 +316,15 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         const int strip = t0 % P.nstrips, frame_i = t0 / P.nstrips;
         const uint8_t *frame = P.packed + (size_t)frame_i * P.payload_stride;
         uint16_t *out = P.out + (size_t)frame_i * P.out_stride;
-        const int xl = strip * 480 - 16 + 16 * lane;                       // first pixel column of this lane
+        const int xl = strip * FW_STRIP_PX - FW_LANE_PX + FW_LANE_PX * lane;   // first pixel column of this lane
         const bool lane_ok = xl >= 0 && xl < w;
         const bool writer = lane_ok && lane >= 1 && lane <= 30;
-        const bool edge_first = xl == 0, edge_last = xl + 16 == w;
-        const int byte0 = strip * 840 - 28;                                // lane 0's first stream byte inside a row
+        const bool edge_first = xl == 0, edge_last = xl + FW_LANE_PX == w;
+        const int byte0 = (strip * FW_STRIP_PX - FW_LANE_PX) * 14 / 8;      // lane 0's first stream byte inside a row
         const int base16 = byte0 & ~15;
-        const int lane_off = (byte0 - base16) + 28 * lane;
+        const int lane_byte = (byte0 - base16) + FW_LANE_BYTES * lane;
+        const int lane_off = lane_byte & ~3;
+        const uint32_t perm = (lane_byte & 2) ? 0x3254u : 0x1032u;
         const int qr0 = seg * P.seg_rows, qr1 = min(qr0 + P.seg_rows, ph);
         const unsigned *row_start = P.items ? P.row_start + (size_t)strip * (ph + 1) : nullptr;
         const uint16_t *vals = P.vals + (size_t)frame_i * P.n_entries;
@@ -284,7 +334,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
                 const uint8_t *src_row = frame + (size_t)(2 * qr) * rowbytes;
                 uint8_t *dst = stage + slot * 2 * FW_ROWBYTES;
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
+                for (int k = 0; k < (FW_ROWBYTES / 16 + 31) / 32; k++) {
                     const int ch = lane + 32 * k;
                     const int src = base16 + 16 * ch;
                     if (ch < FW_ROWBYTES / 16 && src >= 0 && src + 16 <= rowbytes) {
@@ -315,16 +365,15 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         uint16_t *orow = out + (size_t)(2 * qr0) * w + xl;
         // rows enter in the order qr0-1, qr0, ..., qr1; row q is finished when row q+1 has entered
         int q = qr0 - 1;
-        // prologue: two rows without output
         arrive(q, 0);
-        wide_step<STRIPES>(R0, R1, stage, lane_off, q >= 0, false, 0, false, false, false, orow, w, s_r2e, s_t13, K);
+        wide_step<STRIPES>(R0, R1, stage, lane_off, perm, false, 0, false, false, false, orow, w, K);
         __syncwarp();
-        prefetch(q + 2, 0);
+        prefetch(q + 2 <= qr1 ? q + 2 : -1, 0);
         q++;
         arrive(q, 1);
-        wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, true, false, 0, false, false, false, orow, w, s_r2e, s_t13, K);
+        wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, perm, false, 0, false, false, false, orow, w, K);
         __syncwarp();
-        prefetch(q + 2, 1);
+        prefetch(q + 2 <= qr1 ? q + 2 : -1, 1);
         q++;
         // steady state: row q enters, row q-1 is written
         while (q <= qr1) {
@@ -332,7 +381,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
                 const int y = 2 * (q - 1);
                 const int thr = (y >= 4 && y < P.h - 5) ? 2 * MLVB_EV_RES : 0x7FFFFFFF;
                 arrive(q, 0);
-                wide_step<STRIPES>(R0, R1, stage, lane_off, q < ph, true, thr, edge_first, edge_last, writer, orow, w, s_r2e, s_t13, K);
+                wide_step<STRIPES>(R0, R1, stage, lane_off, perm, true, thr, edge_first, edge_last, writer, orow, w, K);
                 __syncwarp();
                 prefetch(q + 2 <= qr1 ? q + 2 : -1, 0);
                 orow += 2 * w;
@@ -343,8 +392,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
                 const int y = 2 * (q - 1);
                 const int thr = (y >= 4 && y < P.h - 5) ? 2 * MLVB_EV_RES : 0x7FFFFFFF;
                 arrive(q, 1);
-                wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, q < ph, true, thr, edge_first, edge_last, writer, orow, w, s_r2e,
-                                   s_t13, K);
+                wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, perm, true, thr, edge_first, edge_last, writer, orow, w, K);
                 __syncwarp();
                 prefetch(q + 2 <= qr1 ? q + 2 : -1, 1);
                 orow += 2 * w;
