@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "context.cuh"
 
@@ -175,21 +177,58 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
         return MLVB_OK;
     }
     if (opts.dual_iso == 2) {                                                       // main.c:956-973
-        for (int f = 0; f < nframes; f++) {
+        auto one_frame = [&](int f, void *aux, cudaStream_t s) -> int {
             uint16_t *fa = d_a + (size_t)f * frame_stride, *fo = d_out + (size_t)f * frame_stride;
-            StageTimer *t = new StageTimer(ctx, ST_DUALISO, st);
-            rc = run_cr2hdr20(ctx, hdr, g, fa, opts.hdr_interpolation_method, !opts.hdr_no_fullres, !opts.hdr_no_alias_map,
-                              opts.chroma_smooth, opts.fix_bad_pixels, d_aux, st);
-            delete t;
-            if (rc < 0) return rc;
+            int r = run_cr2hdr20(ctx, hdr, g, fa, opts.hdr_interpolation_method, !opts.hdr_no_fullres, !opts.hdr_no_alias_map,
+                                 opts.chroma_smooth, opts.fix_bad_pixels, aux, s);
+            if (r < 0) return r;
             FrameGeom gf = g;
-            if (rc == 1) { gf.black *= 4; gf.white *= 4; }                         // hdr.c:1951-1952
-            if (f == 0) { res->is_dual_iso = rc; res->black_level = gf.black; res->white_level = gf.white; }
+            if (r == 1) { gf.black *= 4; gf.white *= 4; }                          // hdr.c:1951-1952
+            if (f == 0) { res->is_dual_iso = r; res->black_level = gf.black; res->white_level = gf.white; }
             // converted: only stripes remain; not converted: the usual chain minus chroma smoothing (main.c:975)
-            rc = run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, 1, rc == 1, st);
+            return run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, 1, r == 1, s);
+        };
+        StageTimer t(ctx, ST_DUALISO, st);
+        // frame 0 first, on the caller's stream: it creates the per-clip state (bad-pixel map, EV tables, stripes)
+        rc = one_frame(0, d_aux, st);
+        if (rc || nframes == 1) return rc;
+        // the other frames are independent: a few host threads, each with its own stream and scratch, so that one
+        // frame's statistics read-backs and scalar epilogues overlap the kernels of the others
+        const int nlanes = std::min(nframes - 1, getenv("MLVB_BATCH_LANES") ? std::max(atoi(getenv("MLVB_BATCH_LANES")), 1) : 4);
+        const size_t need = aux_bytes_for(g, opts);
+        if (!ctx->batch_fork) MLVB_CUDA_OK(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
+        while ((int)ctx->batch_lanes.size() < nlanes) {
+            mlvb_context::BatchLane l;
+            MLVB_CUDA_OK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            MLVB_CUDA_OK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+            ctx->batch_lanes.push_back(l);
+        }
+        for (int l = 0; l < nlanes; l++) {
+            rc = reserve_device(&ctx->batch_lanes[l].d_aux, &ctx->batch_lanes[l].aux_cap, need);
             if (rc) return rc;
         }
-        return MLVB_OK;
+        MLVB_CUDA_OK(cudaEventRecord(ctx->batch_fork, st));
+        std::vector<int> lane_rc(nlanes, MLVB_OK);
+        std::vector<std::thread> workers;
+        const bool was_profiling = ctx->profiling;
+        ctx->profiling = false;                                                     // the span list is single-threaded; this stage is timed as a whole
+        for (int l = 0; l < nlanes; l++)
+            workers.emplace_back([&, l] {
+                mlvb_context::BatchLane &L = ctx->batch_lanes[l];
+                if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamWaitEvent(L.stream, ctx->batch_fork, 0) != cudaSuccess) {
+                    lane_rc[l] = MLVB_ERR_CUDA;
+                    return;
+                }
+                for (int f = 1 + l; f < nframes && lane_rc[l] == MLVB_OK; f += nlanes) lane_rc[l] = one_frame(f, L.d_aux, L.stream);
+                if (cudaEventRecord(L.done, L.stream) != cudaSuccess) lane_rc[l] = MLVB_ERR_CUDA;
+            });
+        for (auto &th : workers) th.join();
+        ctx->profiling = was_profiling;
+        for (int l = 0; l < nlanes; l++) {
+            MLVB_CUDA_OK(cudaStreamWaitEvent(st, ctx->batch_lanes[l].done, 0));
+            if (lane_rc[l]) rc = lane_rc[l];
+        }
+        return rc;
     }
     return run_single_iso_chain(ctx, hdr, g, opts, mlv_filename, d_a, d_out, frame_stride, nframes, 0, 0, st);
 }
@@ -273,6 +312,12 @@ void mlvb_context_destroy(mlvb_context *ctx)
     }
     if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
     if (ctx->d_batch_aux) cudaFree(ctx->d_batch_aux);
+    for (auto &l : ctx->batch_lanes) {
+        if (l.d_aux) cudaFree(l.d_aux);
+        if (l.done) cudaEventDestroy(l.done);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    if (ctx->batch_fork) cudaEventDestroy(ctx->batch_fork);
     if (ctx->batch_stream) cudaStreamDestroy(ctx->batch_stream);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_stat) cudaFree(ctx->d_stat);

@@ -104,6 +104,12 @@ struct mlvb_context {
     int *d_batch_status = nullptr; size_t batch_status_cap = 0;
     void *d_batch_aux = nullptr; size_t batch_aux_cap = 0;        // per-frame codec status of a batch
 
+    // batch lanes: extra streams + scratch so that independent dual-ISO frames of one device batch overlap their
+    // statistics read-backs and host epilogues with each other's kernels (abi.cu: run_pipeline)
+    struct BatchLane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; void *d_aux = nullptr; size_t aux_cap = 0; };
+    std::vector<BatchLane> batch_lanes;
+    cudaEvent_t batch_fork = nullptr;
+
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> path_count[2] = {{0}, {0}};   // fused strip kernel, fused wide kernel (mlvb_path_count)
 

@@ -43,28 +43,33 @@ struct StatsA {
     unsigned hist_field[2][4][16384];   // identify_bright_and_dark_fields for row offset 0 (RGGB) and 1 (GBRG)
 };
 
-// HIST = false: only the hdr_check sum (the histograms are taken later, from the pixel-fixed frame)
+// HIST = false: only the hdr_check sum (the histograms are taken later, from the pixel-fixed frame).
+// A block walks rows blockIdx.y, blockIdx.y + gridDim.y, ... and adds its hdr_check partial sums once.
+constexpr int STATS_A_ROWS = 64;        // gridDim.y of the statistics pass
+
 template <bool HIST>
 __global__ void __launch_bounds__(256)
 diso_stats_a_kernel(const uint16_t *__restrict__ img, int w, int h, int black, int white, const double *__restrict__ raw2evf,
                     StatsA *__restrict__ S)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     double ev = 0.0;
     unsigned num = 0;
     if (x < w) {
-        const int p = img[x + (size_t)y * w];
-        if (HIST) {
-            if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
-            if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
-            const int ys = y - 1;                                                                      // GBRG: frame starts one row lower
-            if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
-        }
-        if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {                                              // hdr.c:419-433
-            const int p2 = img[x + (size_t)(y + 2) * w];
-            if ((p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
-                ev = fabs(raw2evf[p2] - raw2evf[p]);
-                num = 1;
+        for (int y = blockIdx.y; y < h; y += gridDim.y) {
+            const int p = img[x + (size_t)y * w];
+            if (HIST) {
+                if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
+                if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
+                const int ys = y - 1;                                                                      // GBRG: frame starts one row lower
+                if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
+            }
+            if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {                                              // hdr.c:419-433
+                const int p2 = img[x + (size_t)(y + 2) * w];
+                if ((p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
+                    ev += fabs(raw2evf[p2] - raw2evf[p]);
+                    num++;
+                }
             }
         }
     }
@@ -169,6 +174,8 @@ struct PixParams {
     double corr_ev, overlap, max_ev;                  // mixing curve (hdr.c:1540-1571)
     const int *raw2ev;                                // 20-bit tables (hdr.c:839-874)
     const int *ev2raw;                                // pointer pre-offset by 10 EV
+    const double *fullres_curve;                      // [2^20], keyed by black (hdr.c:890-913: the reference keeps the same table)
+    const double *mix_curve;                          // [2^20], rebuilt for every frame (hdr.c:1562-1571)
     int use_fullres, use_alias;
     int method;                                       // 0 AMaZE + edge-directed, 1 mean23 (hdr.c:1888-1896)
     AmazeView amz;
@@ -258,6 +265,23 @@ __device__ __forceinline__ double fullres_curve_at(int i, int black)         // 
     return (c2 + 1.0) / 2.0;
 }
 
+// the two blending curves as tables over the 20-bit bright sample, like the reference's own mix_curve /
+// fullres_curve arrays: fullres_curve depends on black only, mix_curve on this frame's exposure match
+__global__ void diso_fullres_curve_kernel(double *__restrict__ curve, int black)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N20) curve[i] = fullres_curve_at(i, black);
+}
+__global__ void diso_mix_curve_kernel(double *__restrict__ curve, int black, double corr_ev, double max_ev, double overlap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N20) return;
+    const double ev = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0)) + corr_ev;
+    const double c = -cos(fmax(fmin(ev - (max_ev - overlap), overlap), 0.0) * M_PI / overlap);
+    const double k = (c + 1.0) / 2.0;
+    curve[i] = fmax(fmin(k, 1.0), 0.0);
+}
+
 // half-res blend (hdr.c:1562-1611) + overexposure flags (hdr.c:1627-1633) + alias-map skip mask
 __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, uint32_t *__restrict__ halfres,
                                 uint16_t *__restrict__ over, uint8_t *__restrict__ skip, const PixParams P)
@@ -265,14 +289,11 @@ __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
     if (i >= np) return;
     const int b = (int)bright[i], d = (int)dark[i];
-    const double ev = log2(fmax((double)(b & 0xFFFFF) / 64.0 - (double)P.black / 64.0, 1.0)) + P.corr_ev;
-    const double c = -cos(fmax(fmin(ev - (P.max_ev - P.overlap), P.overlap), 0.0) * M_PI / P.overlap);
-    double k = (c + 1.0) / 2.0;
-    k = fmax(fmin(k, 1.0), 0.0);
+    const double k = __ldg(P.mix_curve + (b & 0xFFFFF));
     const int mixed = (int)((double)__ldg(P.raw2ev + b) * (1.0 - k) + (double)__ldg(P.raw2ev + d) * k);
     halfres[i] = (uint32_t)__ldg(P.ev2raw + mixed);
     over[i] = (b >= P.white_darkened || d >= P.white) ? 100 : 0;
-    skip[i] = fullres_curve_at(b & 0xFFFFF, P.black) > FULLRES_THR;
+    skip[i] = __ldg(P.fullres_curve + (b & 0xFFFFF)) > FULLRES_THR;
 }
 
 // alias map, pass 1 (hdr.c:1397-1415)
@@ -364,7 +385,7 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
     if (i >= np) return;
     const int b = (int)bright[i];
     const int hrev = __ldg(P.raw2ev + hrs[i]), frev = __ldg(P.raw2ev + fullres[i]), frsev = __ldg(P.raw2ev + frs[i]);
-    double f = fullres_curve_at(b & 0xFFFFF, P.black), c = 0.0;
+    double f = __ldg(P.fullres_curve + (b & 0xFFFFF)), c = 0.0;
     if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
     const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
     c = fmax(c, ovf);
@@ -462,6 +483,7 @@ struct DisoScratch {        // carved out of the slot's aux buffer
     uint32_t *raw32, *dark, *bright, *fullres, *halfres, *frs, *hrs;
     uint16_t *over, *over2, *amap, *aux;
     uint8_t *skip;
+    double *mix_curve;      // [2^20]
     AmazeScratch amz;
 };
 
@@ -486,6 +508,7 @@ size_t carve(uint8_t *base, int w, int h, int interp_method, DisoScratch *S)
     s.over = (uint16_t *)take(npix * 2); s.over2 = (uint16_t *)take(npix * 2);
     s.amap = (uint16_t *)take(npix * 2); s.aux = (uint16_t *)take(npix * 2);
     s.skip = (uint8_t *)take(npix);
+    s.mix_curve = (double *)take((size_t)N20 * sizeof(double));
     memset(&s.amz, 0, sizeof(s.amz));
     if (interp_method == 0) o += amaze_scratch_bytes(w, h, &s.amz, base ? base + o : nullptr);
     if (S) *S = s;
@@ -508,6 +531,7 @@ struct DualIsoTables {
     int lut_black = -1;
     int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
     double *d_raw2evf = nullptr;        // 16384 + MAX_BLACK doubles
+    double *d_fullres_curve = nullptr;  // 2^20 doubles, keyed by lut_black
     double *d_test_a = nullptr;
     std::vector<double> test_a;
 };
@@ -585,7 +609,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
 
     // ---------------- phase A
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<true><<<dim3(ceil_div(w, 256), h), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
+    diso_stats_a_kernel<true><<<dim3(ceil_div(w, 256), std::min(h, STATS_A_ROWS)), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
     ctx->launches += 1;
     PinnedLease stage(T);
     if (!stage.p) return MLVB_ERR_CUDA;
@@ -714,11 +738,19 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
             if (!T->d_ev2raw_0) MLVB_CUDA_OK(cudaMalloc(&T->d_ev2raw_0, 24 * EVR * sizeof(int)));
             MLVB_CUDA_OK(cudaMemcpy(T->d_raw2ev, r2e.data(), N20 * sizeof(int), cudaMemcpyHostToDevice));
             MLVB_CUDA_OK(cudaMemcpy(T->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
+            if (!T->d_fullres_curve) MLVB_CUDA_OK(cudaMalloc(&T->d_fullres_curve, (size_t)N20 * sizeof(double)));
+            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(T->d_fullres_curve, black);
+            MLVB_CUDA_OK(cudaStreamSynchronize(st));                    // other streams read the table from now on
+            ctx->launches += 1;
             T->lut_black = black;
         }
         P.raw2ev = T->d_raw2ev;
         P.ev2raw = T->d_ev2raw_0 + 10 * EVR;
+        P.fullres_curve = T->d_fullres_curve;
     }
+    P.mix_curve = D.mix_curve;
+    diso_mix_curve_kernel<<<N20 / 256, 256, 0, st>>>(D.mix_curve, black, P.corr_ev, P.max_ev, P.overlap);
+    ctx->launches += 1;
 
     // ---------------- phase D: per-pixel pipeline
     const size_t np = (size_t)w * h;
@@ -794,7 +826,7 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
         }
     }
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<false><<<dim3(ceil_div(g.w, 256), g.h), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
+    diso_stats_a_kernel<false><<<dim3(ceil_div(g.w, 256), std::min(g.h, STATS_A_ROWS)), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
                                                                       T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA);
     ctx->launches += 1;
     double ev_sum = 0;

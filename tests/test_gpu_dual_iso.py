@@ -87,3 +87,32 @@ def test_dual_iso_through_process_frame(fresh_ctx, oracle):
         out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(img), o, "c3.MLV")
         assert rc == 1 and res.is_dual_iso == 1 and res.black_level == 8192 and res.white_level == 60000
         _check(out, want, f"process_frame dual ISO frame {i}")
+
+
+@pytest.mark.parametrize("method,cs", [(1, 5), (0, 0)])
+def test_dual_iso_device_batch_matches_per_frame(fresh_ctx, method, cs):
+    """The device-resident batch entry runs the frames after the first on a few worker lanes (own stream, own
+    scratch, own host thread); every frame must equal what the per-frame call gives (bit for bit: same kernels,
+    same statistics), in any interleaving."""
+    torch = pytest.importorskip("torch")
+    w, h, n = 640, 384, 7
+    hdr = F.make_frame_headers(w, h)
+    frames = [synth.make_frame(w, h, i, dual_iso=True, hot_cold=True) for i in range(n)]
+    o = M.Options(dual_iso=2, hdr_interpolation_method=method, chroma_smooth=cs, fix_bad_pixels=1)
+    want = []
+    for i, img in enumerate(frames):
+        out, res = fresh_ctx.process_frame(hdr, synth.pack_bits(img), o, "dbatch.MLV")
+        assert res.status == 0 and res.is_dual_iso == 1
+        want.append(out.copy())
+    packed = np.stack([synth.pack_bits(f) for f in frames])
+    stride = packed.shape[1] * 2
+    d_in = torch.from_numpy(packed.view(np.int16)).cuda()
+    d_out = torch.zeros((n, h * w), dtype=torch.int16, device="cuda")
+    for rep in range(2):
+        d_out.zero_()
+        fresh_ctx.process_batch_device(hdr, o, "dbatch.MLV", d_in.data_ptr(), stride, stride, d_out.data_ptr(), h * w, n,
+                                       torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), (rep, i, int(np.count_nonzero(got[i] != want[i])))
