@@ -431,12 +431,15 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
         static std::once_flag once;
         std::call_once(once, [] {
-            cudaFuncSetAttribute(fused3_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
-            cudaFuncSetAttribute(fused3_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+            cudaFuncSetAttribute(fused3_wide_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+            cudaFuncSetAttribute(fused3_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+            cudaFuncSetAttribute(fused3_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
         });
         StageTimer t(ctx, ST_CHROMA, st);
-        if (P.stripes) fused3_wide_kernel<true><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
-        else fused3_wide_kernel<false><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        const bool unit01 = P.coef[0] == 65536 && P.coef[1] == 65536 && P.white16 > P.black16 + 64;
+        if (P.stripes && unit01) fused3_wide_kernel<2><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        else if (P.stripes) fused3_wide_kernel<1><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        else fused3_wide_kernel<0><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
         ctx->launches += 1;
         ctx->path_count[1] += 1;
     } else {

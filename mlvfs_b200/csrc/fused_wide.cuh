@@ -116,9 +116,13 @@ struct WideRow {                                  // per-lane state of one quad 
     uint32_t g1s[FW_COLS], g2[FW_COLS];           // finished G1 << 16, finished G2
 };
 
-template <bool STRIPES, int IDX>
+// STRIPES: 0 = no stripe correction, 1 = eight general gains, 2 = gains 0 and 1 are exactly 1.0 (what
+// stripes_compute_correction always produces, stripes.c:236-237) and white > black + 64: those two columns
+// only need the clamp to white
+template <int STRIPES, int IDX>
 __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
 {
+    if (STRIPES == 2 && IDX < 2) return min(v, K.white);
     if (STRIPES) {
         if (v > K.thr) {                                                       // stripes.c:258: v > black + 64
             const uint32_t t = (((v - K.black) * K.coef[IDX]) >> 16) + K.black;   // product < 2^32: coef < 2^18 (host check)
@@ -128,7 +132,7 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
     return v;
 }
 
-template <bool STRIPES, int C>
+template <int STRIPES, int C>
 __device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[FW_NW], const uint32_t (&B)[FW_NW], const WideConst &K, WideRow &R)
 {
     const uint32_t r = wide_px<2 * C>(T), g1 = wide_px<2 * C + 1>(T);
@@ -171,7 +175,7 @@ __device__ __forceinline__ Tri tri_shfl_down(const Tri &t)
 }
 
 // finish quad column C of the middle row: smoothed R/B (chroma_smooth.c:30-68), stripe gains, packed words
-template <bool STRIPES, int C>
+template <int STRIPES, int C>
 __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb, int ge_thr, bool edge_first, bool edge_last,
                                                 const WideConst &K, uint32_t &top, uint32_t &bot)
 {
@@ -181,11 +185,14 @@ __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb
     if (C < 2) go = go && !edge_first;
     if (C >= FW_COLS - 2) go = go && !edge_last;
     const int er = wadd(ge, mr), eb = wadd(ge, mb);
-    if (go && er > MLVB_EV_RES && eb > MLVB_EV_RES) {
-        const int cr = min(er, MLVB_EV_MAX), cb = min(eb, MLVB_EV_MAX);
-        r = ((uint32_t)FW_T13(cr & (MLVB_EV_RES - 1)) >> (13 - (cr >> 15))) + K.black;
-        b = ((uint32_t)FW_T13(cb & (MLVB_EV_RES - 1)) >> (13 - (cb >> 15))) + K.black;
-    }
+    go = go && er > MLVB_EV_RES && eb > MLVB_EV_RES;
+    // branch-free: both lookups always run (indices clamped into the table), the result is selected -- no
+    // reconvergence barrier between the columns of a lane, so their instruction streams interleave freely
+    const uint32_t cr = min((uint32_t)er, (uint32_t)MLVB_EV_MAX), cb = min((uint32_t)eb, (uint32_t)MLVB_EV_MAX);
+    const uint32_t nr = ((uint32_t)FW_T13(cr & (MLVB_EV_RES - 1)) >> ((13 - (cr >> 15)) & 31)) + K.black;
+    const uint32_t nb = ((uint32_t)FW_T13(cb & (MLVB_EV_RES - 1)) >> ((13 - (cb >> 15)) & 31)) + K.black;
+    r = go ? nr : r;
+    b = go ? nb : b;
     r = wide_gain<STRIPES, (2 * C) & 7>(r, K);
     b = wide_gain<STRIPES, (2 * C + 1) & 7>(b, K);
     top = r | M.g1s[C];
@@ -198,7 +205,7 @@ template <int C> struct ColTag { static constexpr int value = C; };
 // dr / db are still read for the column sorts), and write the finished middle row M when `emit`.
 //   lane_off : byte offset of the lane's first word inside a staged row (4-byte aligned)
 //   perm     : byte-permute selector turning two loaded words into one stream-order word
-template <bool STRIPES>
+template <int STRIPES>
 __device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const uint8_t *stage_rows, int lane_off, uint32_t perm,
                                           bool emit, int ge_thr, bool edge_first, bool edge_last, bool writer, uint16_t *orow, int w,
                                           const WideConst &K)
@@ -288,7 +295,7 @@ __device__ __noinline__ void wide_apply_patches(const WideItem *items, unsigned 
     }
 }
 
-template <bool STRIPES>
+template <int STRIPES>
 __global__ void __launch_bounds__(FW_THREADS, 1)
 fused3_wide_kernel(const __grid_constant__ WideParams P)
 {
