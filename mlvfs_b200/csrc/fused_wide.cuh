@@ -11,7 +11,10 @@
 //     lane's own registers (12 shuffles per FW_COLS quads instead of per quad) and every stripe gain has a
 //     fixed column;
 //   * the packed rows are staged by cp.async (16-byte chunks, L2 only) into a per-warp double buffer, one
-//     quad row ahead; bad-pixel patches are written into the staged bytes before extraction;
+//     quad row ahead; bad-pixel patches are written into the staged bytes before extraction.  -DFW_STAGE_TMA
+//     stages the same bytes with cp.async.bulk + one mbarrier per warp and slot instead (bit-identical, measured
+//     325 k against 360 k frames/s on C2: the single issuing lane's address / uniform-register code costs more
+//     issue slots than the 32-lane LDGSTS it replaces, and issue slots are what this kernel is short of);
 //   * sort3 / med3 are evaluated as (min3, max3, a + b + c - min3 - max3): the additions issue on the FMA
 //     pipe (IMAD) while the min/max run on the ALU pipe, instead of 6 / 4 ALU-pipe min/max.
 //
@@ -39,7 +42,8 @@ constexpr int FW_ROWBYTES = FW_COLS == 4 ? 480 : 960;   // staged bytes per pixe
 constexpr int FW_STAGE_PER_WARP = 4 * FW_ROWBYTES;       // 2 slots x 2 pixel rows
 constexpr int FW_SMEM_R2E = 16384 * 4;
 constexpr int FW_SMEM_T13 = 32768 * 2;
-constexpr int FW_SMEM_BYTES = FW_SMEM_R2E + FW_SMEM_T13 + FW_WARPS * FW_STAGE_PER_WARP;
+constexpr int FW_SMEM_STAGE = FW_WARPS * FW_STAGE_PER_WARP;
+constexpr int FW_SMEM_BYTES = FW_SMEM_R2E + FW_SMEM_T13 + FW_SMEM_STAGE + FW_WARPS * 2 * 8;   // + one mbarrier per warp and slot
 static_assert(FW_COLS == 4 || FW_COLS == 8, "a lane owns 8 or 16 pixels of a row");
 
 extern __shared__ __align__(16) uint8_t fw_smem[];
@@ -69,6 +73,28 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// TMA (bulk async copy) row staging: one elected lane arms the slot's mbarrier with the byte count and issues
+// the copies; every lane of the warp waits on the barrier's phase before reading the staged bytes.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
@@ -174,6 +200,16 @@ __device__ __forceinline__ Tri tri_shfl_down(const Tri &t)
     return o;
 }
 
+// ev2raw[min(e, 14 EV - 1)] for e > 0 from the top-octave table.  With t = (14 EV - 1) - e clamped at 0:
+// octave shift 13 - (e >> 15) == t >> 15 and the table index e & (EV - 1) == ~t & (EV - 1).
+__device__ __forceinline__ uint32_t wide_ev2raw(int e)
+{
+    const int t = max(MLVB_EV_MAX - e, 0);
+    uint32_t f = ~(uint32_t)t & (uint32_t)(MLVB_EV_RES - 1);
+    asm("" : "+r"(f));          // index * 2 + table base as one IMAD
+    return (uint32_t)FW_T13(f) >> (((uint32_t)t >> 15) & 31);
+}
+
 // finish quad column C of the middle row: smoothed R/B (chroma_smooth.c:30-68), stripe gains, packed words
 template <int STRIPES, int C>
 __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb, int ge_thr, bool edge_first, bool edge_last,
@@ -188,9 +224,7 @@ __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb
     go = go && er > MLVB_EV_RES && eb > MLVB_EV_RES;
     // branch-free: both lookups always run (indices clamped into the table), the result is selected -- no
     // reconvergence barrier between the columns of a lane, so their instruction streams interleave freely
-    const uint32_t cr = min((uint32_t)er, (uint32_t)MLVB_EV_MAX), cb = min((uint32_t)eb, (uint32_t)MLVB_EV_MAX);
-    const uint32_t nr = ((uint32_t)FW_T13(cr & (MLVB_EV_RES - 1)) >> ((13 - (cr >> 15)) & 31)) + K.black;
-    const uint32_t nb = ((uint32_t)FW_T13(cb & (MLVB_EV_RES - 1)) >> ((13 - (cb >> 15)) & 31)) + K.black;
+    const uint32_t nr = wide_ev2raw(er) + K.black, nb = wide_ev2raw(eb) + K.black;
     r = go ? nr : r;
     b = go ? nb : b;
     r = wide_gain<STRIPES, (2 * C) & 7>(r, K);
@@ -304,6 +338,12 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
     for (int i = threadIdx.x; i < 16384; i += FW_THREADS) s_r2e[i] = __ldg(P.raw2ev + i);
     for (int i = threadIdx.x; i < FW_SMEM_T13 / 16; i += FW_THREADS)
         reinterpret_cast<uint4 *>(s_t13)[i] = __ldg(reinterpret_cast<const uint4 *>(P.ev2raw13) + i);
+#ifdef FW_STAGE_TMA
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(fw_smem + FW_SMEM_R2E + FW_SMEM_T13 + FW_SMEM_STAGE) + (threadIdx.x >> 5) * 16;
+    if ((threadIdx.x & 31) == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    uint32_t phase = 0;                            // bit s = parity the next wait on slot s expects
+#endif
     __syncthreads();
 
     WideConst K;
@@ -336,6 +376,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         const unsigned *row_start = P.items ? P.row_start + (size_t)strip * (ph + 1) : nullptr;
         const uint16_t *vals = P.vals + (size_t)frame_i * P.n_entries;
 
+#ifndef FW_STAGE_TMA
         auto prefetch = [&](int qr, int slot) {
             if (qr >= 0 && qr < ph) {
                 const uint8_t *src_row = frame + (size_t)(2 * qr) * rowbytes;
@@ -352,13 +393,36 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
             }
             cp_async_commit();
         };
+        auto landed = [&](int qr, int slot) { cp_async_wait1(); __syncwarp(); };
+#else
+        // the strip's bytes of a row, cut to the row: [lo, hi) in 16-byte units relative to base16
+        const int lo = max(-base16, 0), hi = min(FW_ROWBYTES, rowbytes - base16);
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+        auto prefetch = [&](int qr, int slot) {
+            if (qr >= 0 && qr < ph && lane == 0) {
+                const uint8_t *src = frame + (size_t)(2 * qr) * rowbytes + base16 + lo;
+                const uint32_t dst = stage_s + slot * 2 * FW_ROWBYTES + lo, bar = bar0 + 8 * slot;
+                mbar_expect_tx(bar, 2u * (uint32_t)(hi - lo));
+                tma_bulk_g2s(dst, src, (uint32_t)(hi - lo), bar);
+                tma_bulk_g2s(dst + FW_ROWBYTES, src + rowbytes, (uint32_t)(hi - lo), bar);
+            }
+        };
+        auto landed = [&](int qr, int slot) {
+            if (qr >= 0 && qr < ph) {
+                mbar_wait(bar0 + 8 * slot, (phase >> slot) & 1u);
+                phase ^= 1u << slot;
+            }
+        };
+#endif
         auto arrive = [&](int qr, int slot) {                                // staged bytes of quad row qr are visible after this
-            cp_async_wait1();
-            __syncwarp();
+            landed(qr, slot);
             if (row_start && qr >= 0 && qr < ph) {
                 const unsigned a = __ldg(row_start + qr), e = __ldg(row_start + qr + 1);
                 if (a < e) {
-                    if (lane == 0) wide_apply_patches(P.items, a, e, vals, stage + slot * 2 * FW_ROWBYTES, (byte0 - base16) * 8);
+                    if (lane == 0) {
+                        wide_apply_patches(P.items, a, e, vals, stage + slot * 2 * FW_ROWBYTES, (byte0 - base16) * 8);
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes before the next bulk copy into this slot
+                    }
                     __syncwarp();
                 }
             }
@@ -406,7 +470,9 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
                 q++;
             }
         }
+#ifndef FW_STAGE_TMA
         cp_async_wait0();
+#endif
         __syncwarp();
     }
 }
