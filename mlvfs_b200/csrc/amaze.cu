@@ -100,7 +100,8 @@ __device__ __forceinline__ double amz_fullres_curve_at(int i, int black)        
 
 __global__ void __launch_bounds__(128)
 amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ grayev, uint8_t *__restrict__ edir,
-                    int w, int h, int black, int white_darkened, int b0, int b1, int b2, int b3)
+                    int w, int h, int black, int white_darkened, int b0, int b1, int b2, int b3,
+                    const double *__restrict__ fullres_curve, const int *__restrict__ fullres_lim)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
@@ -109,7 +110,12 @@ amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ 
     if (x >= 5 && x < w - 5 && y >= 5 && y < h - 5) {
         const uint32_t p = raw32[x + (size_t)y * w];
         bool search;
-        if (!isb[y & 3]) search = !(amz_fullres_curve_at((int)p, black) > 0.8);   // deep shadows of the dark exposure (hdr.c:1106-1120)
+        if (!isb[y & 3]) {                                                         // deep shadows of the dark exposure (hdr.c:1106-1120)
+            // fullres_curve[p] > 0.8 from the per-black table of dualiso.cu (same function as amz_fullres_curve_at);
+            // where the table's crossing is a single index the test is a comparison
+            const int lo = __ldg(fullres_lim + 2), hi = __ldg(fullres_lim + 3);
+            search = lo == hi ? !((int)(p & 0xFFFFF) >= lo) : !(__ldg(fullres_curve + (p & 0xFFFFF)) > 0.8);
+        }
         else search = !(p < (uint32_t)white_darkened);                             // bright exposure clipped (hdr.c:1122-1133)
         if (search) {
             const int s = (isb[y & 3] == isb[(y + 1) & 3]) ? -1 : 1;
@@ -157,7 +163,8 @@ size_t amaze_scratch_bytes(int w, int h, AmazeScratch *S, uint8_t *base)
 // Everything of amaze_interpolate up to (and including) the direction map; the caller's per-pixel kernel
 // then interpolates with amz_edge_interp().
 int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int white_darkened, const int is_bright[4],
-                       const int *d_raw2ev, const AmazeScratch &A, cudaStream_t st, int *launches)
+                       const int *d_raw2ev, const double *d_fullres_curve, const int *d_fullres_lim, const AmazeScratch &A,
+                       cudaStream_t st, int *launches)
 {
     if (w & 3) {
         fprintf(stderr, "libmlvfs_b200: --amaze-edge needs a frame width that is a multiple of 4 (got %d)\n", w);
@@ -191,7 +198,8 @@ int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int whi
     amz_tiles_kernel<<<A.nblocks, amz_threads(), 0, st>>>(A.rawf, A.red, A.green, A.blue, ws, w, h, ntx, nty, A.ws, A.counter);
     amz_gray_kernel<<<g2, 256, 0, st>>>(A.red, A.green, A.blue, A.squeezed, d_raw2ev, A.grayev, w, h, ws, black);
     amz_edge_dir_kernel<<<dim3(ceil_div(w, 128), h), 128, 0, st>>>(d_raw32, A.grayev, A.edir, w, h, black, white_darkened,
-                                                                  is_bright[0], is_bright[1], is_bright[2], is_bright[3]);
+                                                                  is_bright[0], is_bright[1], is_bright[2], is_bright[3], d_fullres_curve,
+                                                                  d_fullres_lim);
     if (launches) *launches += 4;
     MLVB_CUDA_OK(cudaGetLastError());
     return MLVB_OK;

@@ -22,7 +22,8 @@ struct AmazeScratch {
 // carves `base` (may be null: size query); returns the bytes needed
 size_t amaze_scratch_bytes(int w, int h, AmazeScratch *S, uint8_t *base);
 int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int white_darkened, const int is_bright[4],
-                       const int *d_raw2ev, const AmazeScratch &A, cudaStream_t st, int *launches);
+                       const int *d_raw2ev, const double *d_fullres_curve, const int *d_fullres_lim, const AmazeScratch &A,
+                       cudaStream_t st, int *launches);
 int launch_amaze_planes(const float *d_raw, float *d_red, float *d_green, float *d_blue, int stride, int w, int h,
                         char *d_ws, int nblocks, unsigned *d_counter, cudaStream_t st);
 size_t amaze_ws_bytes_per_block();

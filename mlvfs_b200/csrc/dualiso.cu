@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "amaze.cuh"
@@ -43,47 +44,96 @@ struct StatsA {
     unsigned hist_field[2][4][16384];   // identify_bright_and_dark_fields for row offset 0 (RGGB) and 1 (GBRG)
 };
 
+// hdr_check (hdr.c:407-439) and, with HIST, the CFA / row-field histograms (hdr.c:441-636) in one pass.
 // HIST = false: only the hdr_check sum (the histograms are taken later, from the pixel-fixed frame).
-// A block walks rows blockIdx.y, blockIdx.y + gridDim.y, ... and adds its hdr_check partial sums once.
-constexpr int STATS_A_ROWS = 64;        // gridDim.y of the statistics pass
+//
+// One 1024-thread block per SM; block b takes the rows of one class c = b % 4 (y % 4 == c), every thread two
+// adjacent pixels.  The rows of one class feed only three histograms, which fit in shared memory as 32-bit
+// counters (3 x 64 KB): S0 / S1 = even / odd columns over rows < h/4*4 (-> hist_cfa and, for the green
+// parity, hist_field[0][c]) and S2 = the GBRG reading of the same rows (hist_field[1][(c + 3) % 4], green
+// parity x % 2 == y % 2, rows 5 .. (h-1)/4*4).  The block adds its non-zero bins to the global tables once.
+constexpr int STATS_A_THREADS = 1024;
+constexpr int STATS_A_SMEM = 3 * 16384 * (int)sizeof(unsigned);
 
 template <bool HIST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(STATS_A_THREADS, 1)
 diso_stats_a_kernel(const uint16_t *__restrict__ img, int w, int h, int black, int white, const double *__restrict__ raw2evf,
                     StatsA *__restrict__ S)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ unsigned sa_hist[];
+    unsigned *S0 = sa_hist, *S1 = sa_hist + 16384, *S2 = sa_hist + 32768;
+    const int c = blockIdx.x & 3, nper = gridDim.x >> 2;                  // gridDim.x is a multiple of 4
+    if (HIST) {
+        for (int i = threadIdx.x; i < 3 * 16384; i += blockDim.x) sa_hist[i] = 0u;
+        __syncthreads();
+    }
     double ev = 0.0;
     unsigned num = 0;
-    if (x < w) {
-        for (int y = blockIdx.y; y < h; y += gridDim.y) {
-            const int p = img[x + (size_t)y * w];
+    const int h0 = h / 4 * 4, h1 = (h - 1) / 4 * 4;
+    for (int y = c + 4 * (blockIdx.x >> 2); y < h; y += 4 * nper) {
+        const bool in0 = y < h0, in1 = (y - 1) >= 4 && (y - 1) < h1;
+        const bool inner_y = y >= 2 && y < h - 2;
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(img + (size_t)y * w);
+        const uint32_t *row2 = reinterpret_cast<const uint32_t *>(img + (size_t)(y + 2) * w);
+        for (int xp = threadIdx.x; xp < (w >> 1); xp += blockDim.x) {     // w is even
+            const uint32_t pp = __ldg(row + xp);
+            const int pe = (int)(pp & 0xFFFFu), po = (int)(pp >> 16);
             if (HIST) {
-                if (y < h / 4 * 4) atomicAdd(&S->hist_cfa[(y % 2) * 2 + (x % 2)][p & 16383], 1u);          // hdr.c:461-465
-                if (y < h / 4 * 4 && (x % 2) != (y % 2)) atomicAdd(&S->hist_field[0][y % 4][p & 16383], 1u);   // hdr.c:540-550
-                const int ys = y - 1;                                                                      // GBRG: frame starts one row lower
-                if (ys >= 4 && ys < (h - 1) / 4 * 4 && (x % 2) != (ys % 2)) atomicAdd(&S->hist_field[1][ys % 4][p & 16383], 1u);
+                if (in0) { atomicAdd(&S0[pe & 16383], 1u); atomicAdd(&S1[po & 16383], 1u); }      // hdr.c:461-465, 540-550
+                if (in1) atomicAdd(&S2[((c & 1) ? po : pe) & 16383], 1u);                          // GBRG: frame starts one row lower
             }
-            if (x >= 2 && x < w - 2 && y >= 2 && y < h - 2) {                                              // hdr.c:419-433
-                const int p2 = img[x + (size_t)(y + 2) * w];
-                if ((p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
-                    ev += fabs(raw2evf[p2] - raw2evf[p]);
-                    num++;
+            if (inner_y) {                                                                         // hdr.c:419-433
+                const uint32_t qq = __ldg(row2 + xp);
+                const int x = 2 * xp;
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int p = k ? po : pe, p2 = k ? (int)(qq >> 16) : (int)(qq & 0xFFFFu);
+                    if (x + k >= 2 && x + k < w - 2 && (p > black + 32 || p2 > black + 32) && p < white && p2 < white) {
+                        ev += fabs(raw2evf[p2] - raw2evf[p]);
+                        num++;
+                    }
                 }
             }
         }
     }
     // block reduction of the hdr_check sum
-    __shared__ double s_ev[8];
-    __shared__ unsigned s_num[8];
+    __shared__ double s_ev[32];
+    __shared__ unsigned s_num[32];
     for (int o = 16; o; o >>= 1) { ev += __shfl_xor_sync(0xFFFFFFFFu, ev, o); num += __shfl_xor_sync(0xFFFFFFFFu, num, o); }
     if ((threadIdx.x & 31) == 0) { s_ev[threadIdx.x >> 5] = ev; s_num[threadIdx.x >> 5] = num; }
     __syncthreads();
     if (threadIdx.x == 0) {
         double e = 0; unsigned n = 0;
-        for (int i = 0; i < 8; i++) { e += s_ev[i]; n += s_num[i]; }
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) { e += s_ev[i]; n += s_num[i]; }
         if (n) { atomicAdd(&S->ev_sum, e); atomicAdd(&S->ev_num, (unsigned long long)n); }
     }
+    if (HIST) {
+        unsigned *g_cfa0 = S->hist_cfa[(c & 1) * 2], *g_cfa1 = S->hist_cfa[(c & 1) * 2 + 1];
+        unsigned *g_f0 = S->hist_field[0][c], *g_f1 = S->hist_field[1][(c + 3) & 3];
+        for (int i = threadIdx.x; i < 16384; i += blockDim.x) {
+            const unsigned a0 = S0[i], a1 = S1[i], a2 = S2[i];
+            if (a0) atomicAdd(&g_cfa0[i], a0);
+            if (a1) atomicAdd(&g_cfa1[i], a1);
+            const unsigned g = (c & 1) ? a0 : a1;                          // green columns of this row class: x % 2 != y % 2
+            if (g) atomicAdd(&g_f0[i], g);
+            if (a2) atomicAdd(&g_f1[i], a2);
+        }
+    }
+}
+
+static int launch_stats_a(bool hist, const uint16_t *d_img, int w, int h, int black, int white, const double *raw2evf, StatsA *S,
+                          int sm_count, cudaStream_t st)
+{
+    if ((w & 1) || ((uintptr_t)d_img & 3)) return MLVB_ERR_UNSUPPORTED;   // pixel pairs are read as 32-bit words
+    const int nblocks = std::max(4, std::min(sm_count > 0 ? sm_count : 148, (h + 3) / 4 * 4) / 4 * 4);
+    if (hist) {
+        static std::once_flag once;
+        std::call_once(once, [] { cudaFuncSetAttribute(diso_stats_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STATS_A_SMEM); });
+        diso_stats_a_kernel<true><<<nblocks, STATS_A_THREADS, STATS_A_SMEM, st>>>(d_img, w, h, black, white, raw2evf, S);
+    } else {
+        diso_stats_a_kernel<false><<<nblocks, STATS_A_THREADS, 0, st>>>(d_img, w, h, black, white, raw2evf, S);
+    }
+    return MLVB_OK;
 }
 
 // ------------------------------------------------------------------ phase B: white levels (hdr.c:250-300)
@@ -176,6 +226,10 @@ struct PixParams {
     const int *ev2raw;                                // pointer pre-offset by 10 EV
     const double *fullres_curve;                      // [2^20], keyed by black (hdr.c:890-913: the reference keeps the same table)
     const double *mix_curve;                          // [2^20], rebuilt for every frame (hdr.c:1562-1571)
+    // where the curves are flat: [0] first index with a non-zero value, [1] one past the last index with a value
+    // other than 1.0, [2] first index above FULLRES_THR, [3] one past the last index not above it ([2] == [3]: the
+    // threshold is a plain comparison).  Outside [0], [1] the table value is exactly 0.0 / 1.0 and is not fetched.
+    const int *fullres_lim, *mix_lim;
     int use_fullres, use_alias;
     int method;                                       // 0 AMaZE + edge-directed, 1 mean23 (hdr.c:1888-1896)
     AmazeView amz;
@@ -267,19 +321,56 @@ __device__ __forceinline__ double fullres_curve_at(int i, int black)         // 
 
 // the two blending curves as tables over the 20-bit bright sample, like the reference's own mix_curve /
 // fullres_curve arrays: fullres_curve depends on black only, mix_curve on this frame's exposure match
-__global__ void diso_fullres_curve_kernel(double *__restrict__ curve, int black)
+__device__ __forceinline__ void curve_limits(int i, double v, int *__restrict__ lim)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N20) curve[i] = fullres_curve_at(i, black);
+    // block-aggregated (256 threads): at most one atomic per block and limit, none where it cannot change the limit
+    int a0 = v != 0.0 ? i : N20, a1 = v != 1.0 ? i + 1 : 0, a2 = v > FULLRES_THR ? i : N20, a3 = !(v > FULLRES_THR) ? i + 1 : 0;
+    for (int o = 16; o; o >>= 1) {
+        a0 = min(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, o)); a1 = max(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, o));
+        a2 = min(a2, __shfl_xor_sync(0xFFFFFFFFu, a2, o)); a3 = max(a3, __shfl_xor_sync(0xFFFFFFFFu, a3, o));
+    }
+    __shared__ int s_lim[8][4];
+    if ((threadIdx.x & 31) == 0) { s_lim[threadIdx.x >> 5][0] = a0; s_lim[threadIdx.x >> 5][1] = a1; s_lim[threadIdx.x >> 5][2] = a2; s_lim[threadIdx.x >> 5][3] = a3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        int r = s_lim[0][k];
+        for (int wp = 1; wp < (int)(blockDim.x >> 5); wp++) r = (k & 1) ? max(r, s_lim[wp][k]) : min(r, s_lim[wp][k]);
+        if (k & 1) { if (r > 0 && r > lim[k]) atomicMax(&lim[k], r); }
+        else if (r < N20 && r < lim[k]) atomicMin(&lim[k], r);
+    }
 }
-__global__ void diso_mix_curve_kernel(double *__restrict__ curve, int black, double corr_ev, double max_ev, double overlap)
+__global__ void diso_curve_lim_init_kernel(int *__restrict__ lim) { lim[0] = N20; lim[1] = 0; lim[2] = N20; lim[3] = 0; }
+
+__global__ void diso_fullres_curve_kernel(double *__restrict__ curve, int *__restrict__ lim, int black)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N20) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // grid covers N20 exactly
+    const double v = fullres_curve_at(i, black);
+    curve[i] = v;
+    curve_limits(i, v, lim);
+}
+__global__ void diso_mix_curve_kernel(double *__restrict__ curve, int *__restrict__ lim, int black, double corr_ev, double max_ev,
+                                      double overlap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // grid covers N20 exactly
     const double ev = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0)) + corr_ev;
     const double c = -cos(fmax(fmin(ev - (max_ev - overlap), overlap), 0.0) * M_PI / overlap);
-    const double k = (c + 1.0) / 2.0;
-    curve[i] = fmax(fmin(k, 1.0), 0.0);
+    const double k = fmax(fmin((c + 1.0) / 2.0, 1.0), 0.0);
+    curve[i] = k;
+    curve_limits(i, k, lim);
+}
+// table value with the flat ends answered from the limits (exactly 0.0 below lim[0], exactly 1.0 from lim[1] on)
+__device__ __forceinline__ double curve_at(const double *__restrict__ curve, const int *__restrict__ lim, int i)
+{
+    if (i < __ldg(lim)) return 0.0;
+    if (i >= __ldg(lim + 1)) return 1.0;
+    return __ldg(curve + i);
+}
+__device__ __forceinline__ bool fullres_above_thr(const double *__restrict__ curve, const int *__restrict__ lim, int i)
+{
+    const int lo = __ldg(lim + 2), hi = __ldg(lim + 3);
+    if (lo == hi) return i >= lo;
+    return __ldg(curve + i) > FULLRES_THR;
 }
 
 // half-res blend (hdr.c:1562-1611) + overexposure flags (hdr.c:1627-1633) + alias-map skip mask
@@ -289,11 +380,13 @@ __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
     if (i >= np) return;
     const int b = (int)bright[i], d = (int)dark[i];
-    const double k = __ldg(P.mix_curve + (b & 0xFFFFF));
-    const int mixed = (int)((double)__ldg(P.raw2ev + b) * (1.0 - k) + (double)__ldg(P.raw2ev + d) * k);
+    const double k = curve_at(P.mix_curve, P.mix_lim, b & 0xFFFFF);
+    // a term with weight exactly 0.0 contributes exactly 0 (the table values are finite): its gather is skipped
+    const double evb = k < 1.0 ? (double)__ldg(P.raw2ev + b) : 0.0, evd = k > 0.0 ? (double)__ldg(P.raw2ev + d) : 0.0;
+    const int mixed = (int)(evb * (1.0 - k) + evd * k);
     halfres[i] = (uint32_t)__ldg(P.ev2raw + mixed);
     over[i] = (b >= P.white_darkened || d >= P.white) ? 100 : 0;
-    skip[i] = __ldg(P.fullres_curve + (b & 0xFFFFF)) > FULLRES_THR;
+    skip[i] = fullres_above_thr(P.fullres_curve, P.fullres_lim, b & 0xFFFFF);
 }
 
 // alias map, pass 1 (hdr.c:1397-1415)
@@ -384,17 +477,21 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
     if (i >= np) return;
     const int b = (int)bright[i];
-    const int hrev = __ldg(P.raw2ev + hrs[i]), frev = __ldg(P.raw2ev + fullres[i]), frsev = __ldg(P.raw2ev + frs[i]);
-    double f = __ldg(P.fullres_curve + (b & 0xFFFFF)), c = 0.0;
+    double f = curve_at(P.fullres_curve, P.fullres_lim, b & 0xFFFFF), c = 0.0;
     if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
     const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
     c = fmax(c, ovf);
     const double noo = fmax(ovf, 1.0 - f);
     f = fmax(f, c);
-    const double fev = noo * (double)frsev + (1.0 - noo) * (double)frev;
     const int sig = (int)((dark[i] + bright[i]) / 2);
     f = fmax(0.0, fmin(f, (double)(sig - P.black) / (double)(4 * DARK_NOISE)));
-    int o = (int)((double)hrev * (1.0 - f) + fev * f);
+    // the three EV gathers are weighted by (1 - f), f * noo and f * (1 - noo); a weight of exactly 0.0 contributes
+    // exactly 0 (finite table values), so that gather is skipped -- most pixels need one of the three
+    const double hrev = f < 1.0 ? (double)__ldg(P.raw2ev + hrs[i]) : 0.0;
+    const double frsev = (f > 0.0 && noo > 0.0) ? (double)__ldg(P.raw2ev + frs[i]) : 0.0;
+    const double frev = (f > 0.0 && noo < 1.0) ? (double)__ldg(P.raw2ev + fullres[i]) : 0.0;
+    const double fev = noo * frsev + (1.0 - noo) * frev;
+    int o = (int)(hrev * (1.0 - f) + fev * f);
     o = min(max(o, -10 * EVR), 14 * EVR - 1);
     const uint32_t v20 = (uint32_t)__ldg(P.ev2raw + o);
     out16[i] = (uint16_t)min(max((int)((double)v20 / 16.0 + 0.5), 0), 0xFFFF);
@@ -484,6 +581,7 @@ struct DisoScratch {        // carved out of the slot's aux buffer
     uint16_t *over, *over2, *amap, *aux;
     uint8_t *skip;
     double *mix_curve;      // [2^20]
+    int *mix_lim;           // [4]
     AmazeScratch amz;
 };
 
@@ -509,6 +607,7 @@ size_t carve(uint8_t *base, int w, int h, int interp_method, DisoScratch *S)
     s.amap = (uint16_t *)take(npix * 2); s.aux = (uint16_t *)take(npix * 2);
     s.skip = (uint8_t *)take(npix);
     s.mix_curve = (double *)take((size_t)N20 * sizeof(double));
+    s.mix_lim = (int *)take(4 * sizeof(int));
     memset(&s.amz, 0, sizeof(s.amz));
     if (interp_method == 0) o += amaze_scratch_bytes(w, h, &s.amz, base ? base + o : nullptr);
     if (S) *S = s;
@@ -532,6 +631,7 @@ struct DualIsoTables {
     int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
     double *d_raw2evf = nullptr;        // 16384 + MAX_BLACK doubles
     double *d_fullres_curve = nullptr;  // 2^20 doubles, keyed by lut_black
+    int *d_fullres_lim = nullptr;       // 4 ints, see PixParams::fullres_lim
     double *d_test_a = nullptr;
     std::vector<double> test_a;
 };
@@ -609,7 +709,8 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
 
     // ---------------- phase A
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<true><<<dim3(ceil_div(w, 256), std::min(h, STATS_A_ROWS)), 256, 0, st>>>(d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA);
+    if (launch_stats_a(true, d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA, ctx->sm_count, st))
+        return MLVB_ERR_UNSUPPORTED;
     ctx->launches += 1;
     PinnedLease stage(T);
     if (!stage.p) return MLVB_ERR_CUDA;
@@ -739,7 +840,9 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
             MLVB_CUDA_OK(cudaMemcpy(T->d_raw2ev, r2e.data(), N20 * sizeof(int), cudaMemcpyHostToDevice));
             MLVB_CUDA_OK(cudaMemcpy(T->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
             if (!T->d_fullres_curve) MLVB_CUDA_OK(cudaMalloc(&T->d_fullres_curve, (size_t)N20 * sizeof(double)));
-            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(T->d_fullres_curve, black);
+            if (!T->d_fullres_lim) MLVB_CUDA_OK(cudaMalloc(&T->d_fullres_lim, 4 * sizeof(int)));
+            diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(T->d_fullres_lim);
+            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(T->d_fullres_curve, T->d_fullres_lim, black);
             MLVB_CUDA_OK(cudaStreamSynchronize(st));                    // other streams read the table from now on
             ctx->launches += 1;
             T->lut_black = black;
@@ -747,10 +850,13 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
         P.raw2ev = T->d_raw2ev;
         P.ev2raw = T->d_ev2raw_0 + 10 * EVR;
         P.fullres_curve = T->d_fullres_curve;
+        P.fullres_lim = T->d_fullres_lim;
     }
     P.mix_curve = D.mix_curve;
-    diso_mix_curve_kernel<<<N20 / 256, 256, 0, st>>>(D.mix_curve, black, P.corr_ev, P.max_ev, P.overlap);
-    ctx->launches += 1;
+    P.mix_lim = D.mix_lim;
+    diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(D.mix_lim);
+    diso_mix_curve_kernel<<<N20 / 256, 256, 0, st>>>(D.mix_curve, D.mix_lim, black, P.corr_ev, P.max_ev, P.overlap);
+    ctx->launches += 2;
 
     // ---------------- phase D: per-pixel pipeline
     const size_t np = (size_t)w * h;
@@ -764,7 +870,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
         AmazeScratch A;
         amaze_scratch_bytes(w, h, &A, (uint8_t *)D.amz.rawf);
         int nl = 0;
-        const int rc = launch_amaze_stage(D.raw32, w, h, black, white_darkened, F.is_bright, P.raw2ev, A, st, &nl);
+        const int rc = launch_amaze_stage(D.raw32, w, h, black, white_darkened, F.is_bright, P.raw2ev, P.fullres_curve, P.fullres_lim, A, st, &nl);
         if (rc) return rc;
         ctx->launches += nl;
         P.amz.red = A.red; P.amz.green = A.green; P.amz.blue = A.blue; P.amz.squeezed = A.squeezed; P.amz.edir = A.edir;
@@ -826,8 +932,8 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
         }
     }
     MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    diso_stats_a_kernel<false><<<dim3(ceil_div(g.w, 256), std::min(g.h, STATS_A_ROWS)), 256, 0, st>>>(d_img, g.w, g.h, g.black, g.white,
-                                                                      T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA);
+    if (launch_stats_a(false, d_img, g.w, g.h, g.black, g.white, T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA, ctx->sm_count, st))
+        return MLVB_ERR_UNSUPPORTED;
     ctx->launches += 1;
     double ev_sum = 0;
     unsigned long long ev_num = 0;

@@ -187,9 +187,10 @@ fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, uns
     }
 }
 
-// Rows with many entries: one warp stages the whole image row in shared memory, lane 0 applies the row's entries
-// in list order there (every dual-ISO-mode rule of fix_entry stays inside the row: horizontal interpolation or a
-// copy from x +- 2), then the warp writes the row back.  The chain never waits for global memory.
+// Rows with many entries: one warp stages the whole image row in shared memory and applies the row's entries there
+// (every dual-ISO-mode rule of fix_entry stays inside the row: horizontal interpolation or a copy from x +- 2) --
+// independent runs of entries on different lanes, each run in list order -- then writes the row back.  The chains
+// never wait for global memory.
 constexpr int LONG_WARPS_MAX = 16;
 
 template <bool SMEM_EV2RAW>
@@ -274,16 +275,45 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         for (int x = lane; x < w; x += 32) row[x] = grow[x];
         __syncwarp();
         lastx = -100;
-        if (lane == 0) {
-            for (unsigned m = m0; m < m1; m++) {                                // rows 4 .. h-4: fix_entry with dual_iso = 1
-                const int x = A.list[m].x - A.crop_x;
-                if (x > 2 && x < w - 3) interp_h(x);
-                else if (A.edge_rules && x >= 0 && x < w) {
-                    if (x <= 3) row[x] = row[x + 2];
-                    else row[x] = row[x - 2];
+        auto one_entry = [&](int x) {                                           // rows 4 .. h-4: fix_entry with dual_iso = 1
+            if (x > 2 && x < w - 3) interp_h(x);
+            else if (A.edge_rules && x >= 0 && x < w) {
+                if (x <= 3) row[x] = row[x + 2];
+                else row[x] = row[x - 2];
+                lastx = -100;
+            }
+        };
+        // Entries more than 3 columns apart cannot see each other (an entry reads x-3 .. x+3 and writes x), so a row
+        // whose entries come in ascending x splits into independent runs: every lane that holds the first entry of a
+        // run walks that run in list order, all runs of a 32-entry chunk at once.  Rows that are not ascending (a
+        // focus-pixel map in file order) keep the single walker.
+        bool ascending = true;
+        for (unsigned mb = m0; mb < m1; mb += 32) {
+            const unsigned m = mb + lane;
+            const int x = m < m1 ? A.list[m].x : 0x3FFFFFFF;
+            const int xn = m + 1 < m1 ? A.list[m + 1].x : 0x3FFFFFFF;
+            ascending = ascending && !__any_sync(0xFFFFFFFFu, xn < x);
+        }
+        if (ascending) {
+            for (unsigned mb = m0; mb < m1; mb += 32) {
+                const unsigned m = mb + lane;
+                const int x = m < m1 ? A.list[m].x - A.crop_x : 0x3FFFFFFF;
+                const int xprev = (m > m0 && m < m1) ? A.list[m - 1].x - A.crop_x : -0x3FFFFFFF;
+                if (m < m1 && x - xprev > 3) {
                     lastx = -100;
+                    unsigned mm = m;
+                    int xx = x;
+                    while (true) {
+                        one_entry(xx);
+                        if (++mm >= m1) break;
+                        const int xnext = A.list[mm].x - A.crop_x;
+                        if (xnext - xx > 3) break;
+                        xx = xnext;
+                    }
                 }
             }
+        } else if (lane == 0) {
+            for (unsigned m = m0; m < m1; m++) one_entry(A.list[m].x - A.crop_x);
         }
         __syncwarp();
         for (int x = lane; x < w; x += 32) grow[x] = row[x];

@@ -116,3 +116,31 @@ def test_dual_iso_device_batch_matches_per_frame(fresh_ctx, method, cs):
         got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
         for i in range(n):
             assert np.array_equal(got[i], want[i]), (rep, i, int(np.count_nonzero(got[i] != want[i])))
+
+
+def test_dual_iso_pixel_fix_long_rows(fresh_ctx, oracle):
+    """Rows with many bad pixels are staged in shared memory and repaired as independent runs (entries more than
+    3 columns apart) on different lanes; runs of neighbouring entries stay sequential.  Bit-exact against the
+    list-order walk of the reference (cs.c:314-330 with dual_iso = 1), including entries at the row ends."""
+    w, h = 2048, 96
+    hdr = F.make_frame_headers(w, h, file_guid=0xB0B0)
+    img = synth.make_frame(w, h, 3, dual_iso=True)
+    rng = np.random.default_rng(5)
+    # ~12 % hot pixels with runs at distance 1, 2, 3 and 4 (the last one is the first independent distance)
+    hot = rng.random((h, w)) < 0.06
+    for d in (1, 2, 3, 4):
+        seed = rng.random((h, w)) < 0.01
+        hot |= seed | np.roll(seed, d, axis=1)
+    hot[:, :8] |= rng.random((h, 8)) < 0.3           # edge rules at both row ends
+    hot[:, -8:] |= rng.random((h, 8)) < 0.3
+    img[hot] = 16000
+    want_list = oracle.badpix_detect(img, 2048, 1)
+    per_row = np.bincount(want_list[:, 1], minlength=h)
+    assert per_row.max() >= 128, "no row reaches the long-row path"
+    first = M.fix_bad_pixels(hdr, img.copy(), 1, 0)              # detects the map (2-D interpolator, level schedule)
+    assert np.array_equal(first, oracle.badpix_apply(img, 2048, want_list))
+    img2 = synth.make_frame(w, h, 4, dual_iso=True)
+    img2[hot] = 15900
+    got = M.fix_bad_pixels(hdr, img2.copy(), 1, 1)               # same map, horizontal interpolator
+    want = oracle.badpix_apply(img2, 2048, want_list, dual_iso=1)
+    assert np.array_equal(got, want), int(np.count_nonzero(got != want))
