@@ -517,7 +517,6 @@ int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr
     const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
     if (coded && ctx->batch_status_cap < (size_t)nframes) {
         if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
-    if (ctx->d_batch_aux) cudaFree(ctx->d_batch_aux);
         ctx->d_batch_status = nullptr; ctx->batch_status_cap = 0;
         MLVB_CUDA_OK(cudaMalloc(&ctx->d_batch_status, sizeof(int) * nframes));
         ctx->batch_status_cap = nframes;
