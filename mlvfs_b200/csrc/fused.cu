@@ -280,7 +280,7 @@ static int build_patch_plan(const PixelList &list, int w, int h, int crop_x, int
         for (int s = 0; s < wstrips; s++) {
             const int px = x - (FW_STRIP_PX * s - FW_LANE_PX);
             if (px < 0 || px >= FW_WINDOW_PX) continue;
-            wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)px, (unsigned short)((y & 1) * 2 + (x & 1)), (unsigned)m});
+            wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)(px | ((y & 1) << 13)), (unsigned short)(y >> 1), (unsigned)m});
         }
     }
     std::vector<unsigned> wstart((size_t)wstrips * (ph + 1), 0);
@@ -423,7 +423,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         Q.packed = P.packed; Q.payload_stride = payload_stride; Q.out = d_out; Q.out_stride = out_stride_px;
         Q.w = g.w; Q.h = g.h; Q.black = g.black; Q.raw2ev = P.raw2ev; Q.ev2raw13 = ctx->luts.ev2raw_pos + 13 * MLVB_EV_RES;
         Q.black16 = P.black16; Q.white16 = P.white16;
-        for (int i = 0; i < 8; i++) Q.coef[i] = (unsigned)P.coef[i];
+        for (int i = 0; i < 8; i++) { Q.gain[i].coef = (unsigned)P.coef[i]; Q.gain[i].k1 = 0u - (unsigned)P.black16 * (unsigned)P.coef[i]; }
         if (plan) { Q.items = plan->d_wide_items; Q.row_start = plan->d_wide_row_start; Q.vals = P.vals; Q.n_entries = plan->n_entries; }
         Q.nstrips = ceil_div(g.w, FW_STRIP_PX); Q.nframes = nframes;
         Q.one = 1; Q.mone = -1;

@@ -27,6 +27,9 @@ namespace {
 #ifndef FW_COLS_CFG
 #define FW_COLS_CFG 4
 #endif
+#ifndef FW_PATCHES
+#define FW_PATCHES 1
+#endif
 #ifndef FW_WARPS_CFG
 #define FW_WARPS_CFG 16
 #endif
@@ -50,7 +53,7 @@ extern __shared__ __align__(16) uint8_t fw_smem[];
 #define FW_R2E(v) (reinterpret_cast<const int *>(fw_smem)[(v)])
 #define FW_T13(f) (reinterpret_cast<const uint16_t *>(fw_smem + FW_SMEM_R2E)[(f)])
 
-struct WideItem { unsigned short px; unsigned short sub; unsigned entry; };   // px: pixel column inside the strip's window
+struct WideItem { unsigned short px_sub; unsigned short qrow; unsigned entry; };   // px_sub: pixel column inside the strip's window | sub << 12
 
 struct WideParams {
     const uint8_t *packed; size_t payload_stride;
@@ -59,7 +62,7 @@ struct WideParams {
     const int *raw2ev;                // indexed by raw value (16384 entries)
     const uint16_t *ev2raw13;         // ev2raw[13 EV ...], 32768 entries
     int black16, white16;
-    unsigned coef[8];
+    struct { unsigned coef, k1; } gain[8];   // stripe gain and -black * gain (mod 2^32)
     int one, mone;                    // +1 / -1: multipliers of the FMA-pipe additions (opaque to the compiler)
     const WideItem *items; const unsigned *row_start; const uint16_t *vals; unsigned n_entries;
     int nstrips, nseg, seg_rows, nframes;
@@ -96,10 +99,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ int imin3(int a, int b, int c) { return min(min(a, b), c); }
-__device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }   // one VIMNMX3
+__device__ __forceinline__ int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-struct WideConst { uint32_t black, thr, white; uint32_t coef[8]; int one, mone; };
+struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8]; int one, mone; };
 
 // a * m + b on the FMA pipe (IMAD with a register multiplier the compiler cannot fold): the min/max network
 // keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
@@ -150,10 +153,14 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
 {
     if (STRIPES == 2 && IDX < 2) return min(v, K.white);
     if (STRIPES) {
-        if (v > K.thr) {                                                       // stripes.c:258: v > black + 64
-            const uint32_t t = (((v - K.black) * K.coef[IDX]) >> 16) + K.black;   // product < 2^32: coef < 2^18 (host check)
-            return min(t, K.white);
-        }
+        // ((v - black) * coef >> 16) + black as one multiply-add: k1 = -black * coef (mod 2^32); the product is exact
+        // for v > black (coef < 2^18, host check).  stripes.c:258: only v > black + 64 is touched.
+#ifdef FW_GAIN_MAD
+        const uint32_t t = min(((v * K.coef[IDX] + K.k1[IDX]) >> 16) + K.black, K.white);
+        return v > K.thr ? t : v;
+#else
+        if (v > K.thr) return min((((v - K.black) * K.coef[IDX]) >> 16) + K.black, K.white);
+#endif
     }
     return v;
 }
@@ -319,14 +326,18 @@ __device__ __forceinline__ void wide_patch(uint8_t *row, int bit, uint32_t v)
     if (s > 2) wds[k + 1] = (uint16_t)pair;
 }
 
-__device__ __noinline__ void wide_apply_patches(const WideItem *items, unsigned a, unsigned e, const uint16_t *vals, uint8_t *slot_rows,
-                                                int bit0)
+// applies the items of quad row `qrow` starting at index a (items are sorted by quad row); returns the index of the
+// first item of a later row
+__device__ __noinline__ unsigned wide_apply_patches(const WideItem *items, unsigned a, unsigned e, int qrow, const uint16_t *vals,
+                                                    uint8_t *slot_rows, int bit0, bool writer_lane)
 {
 #pragma unroll 1
-    for (unsigned i = a; i < e; i++) {
-        const WideItem it = items[i];
-        wide_patch(slot_rows + (it.sub >> 1) * FW_ROWBYTES, bit0 + it.px * 14, vals[it.entry]);
+    for (; a < e; a++) {
+        const WideItem it = items[a];
+        if ((int)it.qrow != qrow) break;
+        if (writer_lane) wide_patch(slot_rows + (it.px_sub >> 13) * FW_ROWBYTES, bit0 + (it.px_sub & 0xFFF) * 14, vals[it.entry]);
     }
+    return a;
 }
 
 template <int STRIPES>
@@ -349,7 +360,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
     WideConst K;
     K.black = (uint32_t)P.black16; K.thr = (uint32_t)P.black16 + 64u; K.white = (uint32_t)P.white16;
 #pragma unroll
-    for (int i = 0; i < 8; i++) K.coef[i] = P.coef[i];
+    for (int i = 0; i < 8; i++) { K.coef[i] = P.gain[i].coef; K.k1[i] = P.gain[i].k1; }
     K.one = P.one; K.mone = P.mone;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = fw_smem + FW_SMEM_R2E + FW_SMEM_T13 + warp * FW_STAGE_PER_WARP;
@@ -414,17 +425,20 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
             }
         };
 #endif
+        // repaired pixels of this segment: items [pc, pe) sorted by quad row; only the row of the next pending item is
+        // kept in a register, so a row step costs one compare unless it has a patch
+        unsigned pc = 0, pe = 0;
+        if (FW_PATCHES && row_start) { pc = __ldg(row_start + max(qr0 - 1, 0)); pe = __ldg(row_start + min(qr1, ph - 1) + 1); }
+        int next_patch_row = pc < pe ? (int)P.items[pc].qrow : 0x7FFFFFFF;
         auto arrive = [&](int qr, int slot) {                                // staged bytes of quad row qr are visible after this
             landed(qr, slot);
-            if (row_start && qr >= 0 && qr < ph) {
-                const unsigned a = __ldg(row_start + qr), e = __ldg(row_start + qr + 1);
-                if (a < e) {
-                    if (lane == 0) {
-                        wide_apply_patches(P.items, a, e, vals, stage + slot * 2 * FW_ROWBYTES, (byte0 - base16) * 8);
-                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes before the next bulk copy into this slot
-                    }
-                    __syncwarp();
-                }
+            if (qr == next_patch_row) {
+                pc = wide_apply_patches(P.items, pc, pe, qr, vals, stage + slot * 2 * FW_ROWBYTES, (byte0 - base16) * 8, lane == 0);
+                next_patch_row = pc < pe ? (int)P.items[pc].qrow : 0x7FFFFFFF;
+#ifdef FW_STAGE_TMA
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");           // generic writes before the next bulk copy into this slot
+#endif
+                __syncwarp();
             }
         };
 
