@@ -388,19 +388,26 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         const uint16_t *vals = P.vals + (size_t)frame_i * P.n_entries;
 
 #ifndef FW_STAGE_TMA
-        auto prefetch = [&](int qr, int slot) {
-            if (qr >= 0 && qr < ph) {
-                const uint8_t *src_row = frame + (size_t)(2 * qr) * rowbytes;
-                uint8_t *dst = stage + slot * 2 * FW_ROWBYTES;
+        // rows are requested in order (qr0-1, qr0, ...): a running source pointer per 16-byte chunk of the lane
+        constexpr int NCH = (FW_ROWBYTES / 16 + 31) / 32;
+        bool pf_ok[NCH];
+        const uint8_t *pf_src[NCH];
 #pragma unroll
-                for (int k = 0; k < (FW_ROWBYTES / 16 + 31) / 32; k++) {
-                    const int ch = lane + 32 * k;
-                    const int src = base16 + 16 * ch;
-                    if (ch < FW_ROWBYTES / 16 && src >= 0 && src + 16 <= rowbytes) {
-                        cp_async16(dst + 16 * ch, src_row + src);
-                        cp_async16(dst + FW_ROWBYTES + 16 * ch, src_row + rowbytes + src);
-                    }
+        for (int k = 0; k < NCH; k++) {
+            const int ch = lane + 32 * k, src = base16 + 16 * ch;
+            pf_ok[k] = ch < FW_ROWBYTES / 16 && src >= 0 && src + 16 <= rowbytes;
+            pf_src[k] = frame + (ptrdiff_t)(2 * (qr0 - 1)) * rowbytes + src;
+        }
+        auto prefetch = [&](int qr, int slot) {
+            const bool row_ok = (unsigned)qr < (unsigned)ph && qr <= qr1;
+#pragma unroll
+            for (int k = 0; k < NCH; k++) {
+                if (pf_ok[k] && row_ok) {
+                    uint8_t *dst = stage + slot * 2 * FW_ROWBYTES + 16 * (lane + 32 * k);
+                    cp_async16(dst, pf_src[k]);
+                    cp_async16(dst + FW_ROWBYTES, pf_src[k] + rowbytes);
                 }
+                pf_src[k] += 2 * rowbytes;
             }
             cp_async_commit();
         };
@@ -442,6 +449,8 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
             }
         };
 
+        // chroma_smooth.c:26: rows y = 2 * qr with 4 <= y < h - 5, i.e. quad rows 2 .. 2 + smooth_rows - 1
+        const unsigned smooth_rows = (unsigned)max((P.h - 5 + 1) / 2 - 2, 0);
         WideRow R0, R1;
 #pragma unroll
         for (int c = 0; c < FW_COLS; c++) { R0.dr[c] = R0.db[c] = R1.dr[c] = R1.db[c] = 0; }
@@ -453,33 +462,31 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         arrive(q, 0);
         wide_step<STRIPES>(R0, R1, stage, lane_off, perm, false, 0, false, false, false, orow, w, K);
         __syncwarp();
-        prefetch(q + 2 <= qr1 ? q + 2 : -1, 0);
+        prefetch(q + 2, 0);
         q++;
         arrive(q, 1);
         wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, perm, false, 0, false, false, false, orow, w, K);
         __syncwarp();
-        prefetch(q + 2 <= qr1 ? q + 2 : -1, 1);
+        prefetch(q + 2, 1);
         q++;
         // steady state: row q enters, row q-1 is written
         while (q <= qr1) {
             {
-                const int y = 2 * (q - 1);
-                const int thr = (y >= 4 && y < P.h - 5) ? 2 * MLVB_EV_RES : 0x7FFFFFFF;
+                const int thr = (unsigned)(q - 3) < smooth_rows ? 2 * MLVB_EV_RES : 0x7FFFFFFF;   // quad row q-1 is smoothed
                 arrive(q, 0);
                 wide_step<STRIPES>(R0, R1, stage, lane_off, perm, true, thr, edge_first, edge_last, writer, orow, w, K);
                 __syncwarp();
-                prefetch(q + 2 <= qr1 ? q + 2 : -1, 0);
+                prefetch(q + 2, 0);
                 orow += 2 * w;
                 q++;
             }
             if (q > qr1) break;
             {
-                const int y = 2 * (q - 1);
-                const int thr = (y >= 4 && y < P.h - 5) ? 2 * MLVB_EV_RES : 0x7FFFFFFF;
+                const int thr = (unsigned)(q - 3) < smooth_rows ? 2 * MLVB_EV_RES : 0x7FFFFFFF;
                 arrive(q, 1);
                 wide_step<STRIPES>(R1, R0, stage + 2 * FW_ROWBYTES, lane_off, perm, true, thr, edge_first, edge_last, writer, orow, w, K);
                 __syncwarp();
-                prefetch(q + 2 <= qr1 ? q + 2 : -1, 1);
+                prefetch(q + 2, 1);
                 orow += 2 * w;
                 q++;
             }
