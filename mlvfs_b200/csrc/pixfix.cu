@@ -467,7 +467,9 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
     // only the log table there (the exp table is then read through L1) to avoid a second round of serial chains
     int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / row_bytes);
     bool long_ev2raw_smem = ev2raw_octaves_ok != 0;
-    if ((long long)nlong * nframes > (long long)long_warps * sms || long_warps < 1) {
+    const char *force_smem = getenv("MLVB_LONG_SMEM");
+    if (!(force_smem && *force_smem == '1' && long_warps >= 1) &&
+        ((long long)nlong * nframes > (long long)long_warps * sms || long_warps < 1)) {
         const int alt = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - 16384 * sizeof(int) - 1024) / row_bytes);
         if (alt > long_warps) { long_warps = alt; long_ev2raw_smem = false; }
     }
