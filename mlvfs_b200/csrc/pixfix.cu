@@ -192,6 +192,7 @@ fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, uns
 // independent runs of entries on different lanes, each run in list order -- then writes the row back.  The chains
 // never wait for global memory.
 constexpr int LONG_WARPS_MAX = 16;
+constexpr int LONG_CHUNK = 256;            // list entries staged per warp at a time
 
 template <bool SMEM_EV2RAW>
 __global__ void __launch_bounds__(LONG_WARPS_MAX * 32)
@@ -283,37 +284,45 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
                 lastx = -100;
             }
         };
-        // Entries more than 3 columns apart cannot see each other (an entry reads x-3 .. x+3 and writes x), so a row
-        // whose entries come in ascending x splits into independent runs: every lane that holds the first entry of a
-        // run walks that run in list order, all runs of a 32-entry chunk at once.  Rows that are not ascending (a
-        // focus-pixel map in file order) keep the single walker.
-        bool ascending = true;
-        for (unsigned mb = m0; mb < m1; mb += 32) {
-            const unsigned m = mb + lane;
-            const int x = m < m1 ? A.list[m].x : 0x3FFFFFFF;
-            const int xn = m + 1 < m1 ? A.list[m + 1].x : 0x3FFFFFFF;
-            ascending = ascending && !__any_sync(0xFFFFFFFFu, xn < x);
-        }
-        if (ascending) {
-            for (unsigned mb = m0; mb < m1; mb += 32) {
-                const unsigned m = mb + lane;
-                const int x = m < m1 ? A.list[m].x - A.crop_x : 0x3FFFFFFF;
-                const int xprev = (m > m0 && m < m1) ? A.list[m - 1].x - A.crop_x : -0x3FFFFFFF;
-                if (m < m1 && x - xprev > 3) {
-                    lastx = -100;
-                    unsigned mm = m;
-                    int xx = x;
-                    while (true) {
-                        one_entry(xx);
-                        if (++mm >= m1) break;
-                        const int xnext = A.list[mm].x - A.crop_x;
-                        if (xnext - xx > 3) break;
-                        xx = xnext;
+        // The entries' columns are staged LONG_CHUNK at a time (coalesced) so that no walk waits for the list.
+        // Entries more than 3 columns apart cannot see each other (an entry reads x-3 .. x+3 and writes x), so a chunk
+        // whose entries come in ascending x splits into independent runs: the lane that holds the first entry of a
+        // run walks that run in list order, all runs of the chunk at once.  A run that continues from the previous
+        // chunk is continued by whoever holds its next entry: the EV window is only a cache of the staged row.
+        // Chunks that are not ascending (a focus-pixel map in file order) are walked by lane 0 alone.
+        uint16_t *xs = s_rows + (size_t)warps_per_block * ((w + 7) & ~7) + (size_t)warp * LONG_CHUNK;
+        int prev_last = -0x3FFFFFFF;                                            // column of the entry before this chunk
+        for (unsigned mb = m0; mb < m1; mb += LONG_CHUNK) {
+            const int n = (int)min((unsigned)LONG_CHUNK, m1 - mb);
+            bool ascending = true;
+            for (int i = lane; i < n; i += 32) {
+                const int x = A.list[mb + i].x - A.crop_x;
+                xs[i] = (uint16_t)min(max(x, -1), 0xFFFE) + 1;                  // biased by 1: 0 = left of the frame
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) ascending = ascending && !(i + 1 < n && xs[i + 1] < xs[i]);
+            ascending = __all_sync(0xFFFFFFFFu, ascending) && (int)xs[0] - 1 >= prev_last;
+            if (ascending) {
+                for (int i = lane; i < n; i += 32) {
+                    const int x = (int)xs[i] - 1, xp = i ? (int)xs[i - 1] - 1 : prev_last;
+                    if (x - xp > 3 || (i == 0 && lane == 0)) {                  // first entry of a run (or of the chunk)
+                        lastx = -100;                                           // (re)build the EV window from the staged row
+                        int j = i, xx = x;
+                        while (true) {
+                            one_entry(xx);
+                            if (++j >= n) break;
+                            const int xnext = (int)xs[j] - 1;
+                            if (xnext - xx > 3) break;
+                            xx = xnext;
+                        }
                     }
                 }
+            } else if (lane == 0) {
+                lastx = -100;
+                for (int i = 0; i < n; i++) one_entry((int)xs[i] - 1);
             }
-        } else if (lane == 0) {
-            for (unsigned m = m0; m < m1; m++) one_entry(A.list[m].x - A.crop_x);
+            prev_last = (int)xs[n - 1] - 1;
+            __syncwarp();
         }
         __syncwarp();
         for (int x = lane; x < w; x += 32) grow[x] = row[x];
@@ -465,12 +474,13 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
     const size_t row_bytes = (size_t)((w + 7) & ~7) * sizeof(uint16_t);
     // rows per SM with both tables in shared memory; if that cannot hold all long rows of the batch at once, keep
     // only the log table there (the exp table is then read through L1) to avoid a second round of serial chains
-    int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / row_bytes);
+    const size_t warp_bytes = row_bytes + LONG_CHUNK * sizeof(uint16_t);          // staged row + staged entry columns
+    int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / warp_bytes);
     bool long_ev2raw_smem = ev2raw_octaves_ok != 0;
     const char *force_smem = getenv("MLVB_LONG_SMEM");
     if (!(force_smem && *force_smem == '1' && long_warps >= 1) &&
         ((long long)nlong * nframes > (long long)long_warps * sms || long_warps < 1)) {
-        const int alt = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - 16384 * sizeof(int) - 1024) / row_bytes);
+        const int alt = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - 16384 * sizeof(int) - 1024) / warp_bytes);
         if (alt > long_warps) { long_warps = alt; long_ev2raw_smem = false; }
     }
     const unsigned *segs = d_seg_start;
@@ -483,7 +493,7 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
             fix_row_runs_kernel<false><<<b0, RUN_THREADS, RUN_SMEM, st>>>(A, d_seg_start, nseg, nframes);
         }
     } else if (nlong) {
-        const size_t smem = (long_ev2raw_smem ? RUN_SMEM : 16384 * sizeof(int)) + (size_t)long_warps * row_bytes;
+        const size_t smem = (long_ev2raw_smem ? RUN_SMEM : 16384 * sizeof(int)) + (size_t)long_warps * warp_bytes;
         const int blocks = (int)std::min<long long>(sms, ceil_div((long long)nlong * nframes, long_warps));
         if (long_ev2raw_smem) {
             MLVB_CUDA_OK(cudaFuncSetAttribute(fix_long_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
