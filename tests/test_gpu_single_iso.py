@@ -242,3 +242,40 @@ def test_wide_fused_kernel_batches(fresh_ctx, oracle, monkeypatch, w, h, n, stri
             assert np.array_equal(got[i], want[i]), (rep, i, int(np.count_nonzero(got[i] != want[i])),
                                                      np.argwhere(got[i] != want[i])[:8].tolist())
     assert fresh_ctx.path_count(1) >= 2, "the wide kernel did not run"
+
+
+@pytest.mark.parametrize("black,white,bits_noise", [(1024, 16000, 16), (4000, 14000, 64), (2048, 15000, 600)])
+def test_wide_fused_kernel_levels_and_dark_frames(fresh_ctx, oracle, monkeypatch, black, white, bits_noise):
+    """Other black / white levels (the shared-memory raw2ev copy is cut for the clip's black level) and frames with
+    many samples at or below black: raw2ev[black] is INT_MIN and the EV arithmetic wraps exactly like the reference's
+    (chroma_smooth.c:32); samples above white are clamped by the stripe stage."""
+    torch = pytest.importorskip("torch")
+    monkeypatch.setenv("MLVB_WIDE_MIN_ROWS", "1")
+    w, h, n = 704, 258, 4
+    hdr = _hdr(w, h, black=black, white=white, file_guid=0xC0DE0000 + black)
+    frames = []
+    for i in range(n):
+        f = synth.make_frame(w, h, i, black=black, white=white, hot_cold=True, stripes=True, noise_amp=bits_noise, bad_density=1e-4)
+        rng = np.random.default_rng(100 + i)
+        dark = rng.random((h, w)) < 0.05
+        f[dark] = np.clip(black + rng.integers(-40, 3, size=int(dark.sum())), 0, 16383)     # around and exactly at black
+        frames.append(f)
+    want, _ = oracle.single_iso_chain(frames, black, white, hdr.rawi_hdr.raw_info.frame_size,
+                                      chroma_smooth_method=3, fix_bad_pixels=1, fix_stripes=1)
+    packed = np.stack([synth.pack_bits(f) for f in frames])
+    stride = packed.shape[1] * 2
+    d_in = torch.from_numpy(packed.view(np.int16)).cuda()
+    d_out = torch.empty((n, h * w), dtype=torch.int16, device="cuda")
+    o = M.Options(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=1)
+    name = f"widelvl_{black}.MLV"
+    for rep in range(3):
+        d_out.zero_()
+        fresh_ctx.process_batch_device(hdr, o, name, d_in.data_ptr(), stride, stride, d_out.data_ptr(), h * w, n,
+                                       torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint16).reshape(n, h, w)
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), (rep, i, int(np.count_nonzero(got[i] != want[i])),
+                                                     np.argwhere(got[i] != want[i])[:8].tolist())
+    if bits_noise < 100:        # the very noisy clip has chained bad pixels: level-scheduled general path by design
+        assert fresh_ctx.path_count(1) >= 2, "the wide kernel did not run"
