@@ -283,26 +283,44 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     C.sync();
 
     // ---- variance-based choice + bounding, in place (:748-803): thread per column, rows in order ----
+    // Everything a row reads except the two left-neighbour lanes and the row two above is still original when the
+    // previous row is processed, so the operands of row rr+1 are loaded before row rr's barrier: the L2 latency of
+    // the next row hides behind this row's work instead of adding to every one of the ~150 sequential steps.
     {
         const int ncol = 4 * cdiv(cc1 - 8, 4);                            // columns 4 .. 4+ncol-1
         const int cc = 4 + tid, lane = tid & 3;
         const bool active = tid < ncol;
+        struct VarIn { float c0, cl, cr, cu, cd, h0, hm2, hp2, ha, ham2, hap2, v0, vm2, vp2, va, vam2, vap2; };
+        auto load_row = [&](int rr) {
+            VarIn L;
+            const int i = rr * TS + cc;
+            L.c0 = cfa[i]; L.cl = cfa[i - 1]; L.cr = cfa[i + 1]; L.cu = cfa[i - V1]; L.cd = cfa[i + V1];
+            L.h0 = W.hcd[i]; L.hm2 = W.hcd[i - 2]; L.hp2 = W.hcd[i + 2];
+            L.ha = W.hcdalt[i]; L.ham2 = W.hcdalt[i - 2]; L.hap2 = W.hcdalt[i + 2];
+            L.v0 = W.vcd[i]; L.vm2 = W.vcd[i - V2]; L.vp2 = W.vcd[i + V2];   // vm2 is only used for rows 4, 5 (rows 2, 3 are never updated)
+            L.va = W.vcdalt[i]; L.vam2 = W.vcdalt[i - V2]; L.vap2 = W.vcdalt[i + V2];
+            return L;
+        };
         float vup[2] = {0.0f, 0.0f};                                      // updated vcd of rows rr-2 (same parity)
+        VarIn cur = {};
+        if (active && 4 < rr1 - 4) cur = load_row(4);
         for (int rr = 4; rr < rr1 - 4; rr++) {
             const int i = rr * TS + cc, buf = rr & 1;
+            VarIn nxt = {};
+            if (active && rr + 1 < rr1 - 4) nxt = load_row(rr + 1);
             float h = 0.0f, v = 0.0f, c0 = 0.0f, sgn = 1.0f, hm2 = 0.0f, h0 = 0.0f, hp2 = 0.0f, havar = 0.0f, ha = 0.0f;
             if (active) {
                 sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
-                c0 = cfa[i];
-                h0 = W.hcd[i]; hm2 = W.hcd[i - 2]; hp2 = W.hcd[i + 2];
-                ha = W.hcdalt[i];
-                havar = var3(W.hcdalt[i - 2], ha, W.hcdalt[i + 2]);
+                c0 = cur.c0;
+                h0 = cur.h0; hm2 = cur.hm2; hp2 = cur.hp2;
+                ha = cur.ha;
+                havar = var3(cur.ham2, ha, cur.hap2);
                 h = (havar < var3(hm2, h0, hp2)) ? ha : h0;
-                h = bound_cd(h, c0, cfa[i - 1], cfa[i + 1], sgn);
-                const float v0 = W.vcd[i], vm2 = rr >= 6 ? vup[rr & 1] : W.vcd[i - V2], vp2 = W.vcd[i + V2];
-                const float va = W.vcdalt[i];
-                v = (var3(W.vcdalt[i - V2], va, W.vcdalt[i + V2]) < var3(vm2, v0, vp2)) ? va : v0;
-                v = bound_cd(v, c0, cfa[i - V1], cfa[i + V1], sgn);
+                h = bound_cd(h, c0, cur.cl, cur.cr, sgn);
+                const float v0 = cur.v0, vm2 = rr >= 6 ? vup[rr & 1] : cur.vm2, vp2 = cur.vp2;
+                const float va = cur.va;
+                v = (var3(cur.vam2, va, cur.vap2) < var3(vm2, v0, vp2)) ? va : v0;
+                v = bound_cd(v, c0, cur.cu, cur.cd, sgn);
                 vup[rr & 1] = v;
                 if (lane >= 2) S.row[buf][tid] = h;
             }
@@ -311,11 +329,12 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
                 if (lane < 2 && tid >= 2) {                               // left neighbour is lane 2/3 of the previous vector: updated
                     const float hm2u = S.row[buf][tid - 2];
                     h = (havar < var3(hm2u, h0, hp2)) ? ha : h0;
-                    h = bound_cd(h, c0, cfa[i - 1], cfa[i + 1], sgn);
+                    h = bound_cd(h, c0, cur.cl, cur.cr, sgn);
                 }
                 W.hcd[i] = h; W.vcd[i] = v;
                 W.cddiffsq[i] = sq(v - h);
             }
+            cur = nxt;
         }
     }
     C.sync();
@@ -424,6 +443,25 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         const int r0 = pass ? 10 : 8;
         for (int k = tid; k < TSH; k += nthr) S.row[(r0 - 1) & 1][k] = P[(r0 - 1) * TSH + k];
         C.sync();
+        // a row reads its own and the next row's original values plus the previous row's updated ones (through the
+        // shared row buffer): with one site per thread the originals of row rr+1 are loaded before row rr's barrier
+        struct RefIn { float t, dl, dr, c, m, p; bool in; };
+        auto load_ref = [&](int rr, int k) {
+            RefIn L = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
+            const int par = fc(rr, 2) & 1;
+            const int ns = pass ? 4 * cdiv(cc1 - 20 - par, 8) : cdiv(cc1 - 16 - par, 2);
+            const int k0 = (r0 + par) >> 1;
+            L.t = P[rr * TSH + k];
+            L.in = k >= k0 && k < k0 + ns;
+            if (L.in) {
+                L.dl = P[(rr + 1) * TSH + k - 1 + par]; L.dr = P[(rr + 1) * TSH + k + par];
+                if (pass) { L.c = cfa[rr * TS + 2 * k + par]; L.m = W.rbm[rr * TSH + k]; L.p = W.rbp[rr * TSH + k]; }
+            }
+            return L;
+        };
+        const bool one_site = nthr >= TSH;                                  // every thread owns at most one half-row site
+        RefIn cur_in = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
+        if (one_site && tid < TSH && r0 < rr1 - r0) cur_in = load_ref(r0, tid);
         for (int rr = r0; rr < rr1 - r0; rr++) {
             const int par = fc(rr, 2) & 1;
             // processed sites: scalar bound for hvwt, whole 4-site vectors for pmwt
@@ -431,22 +469,41 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int k0 = (r0 + par) >> 1;                                // half index of the first processed site
             const float *prev = S.row[(rr - 1) & 1];
             float *cur = S.row[rr & 1];
-            for (int k = tid; k < TSH; k += nthr) {
-                float t = P[rr * TSH + k];
-                if (k >= k0 && k < k0 + ns) {
-                    // diagonal neighbours: previous row (updated) at half indices k-1+par, k+par; next row (original)
-                    const float ul = prev[k - 1 + par], ur = prev[k + par];
-                    const float dl = P[(rr + 1) * TSH + k - 1 + par], dr = P[(rr + 1) * TSH + k + par];
-                    const float s4 = ul + ur + dl + dr;
-                    const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
-                    t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
-                    P[rr * TSH + k] = t;
-                    if (pass) {
-                        const int i = rr * TS + 2 * k + par;
-                        W.rbint[rr * TSH + k] = 0.5f * (cfa[i] + W.rbm[rr * TSH + k] * (1.0f - t) + W.rbp[rr * TSH + k] * t);
+            if (one_site) {
+                RefIn nxt_in = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
+                if (tid < TSH) {
+                    const int k = tid;
+                    if (rr + 1 < rr1 - r0) nxt_in = load_ref(rr + 1, k);
+                    float t = cur_in.t;
+                    if (cur_in.in) {
+                        const float ul = prev[k - 1 + par], ur = prev[k + par];
+                        const float s4 = ul + ur + cur_in.dl + cur_in.dr;
+                        const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
+                        t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
+                        P[rr * TSH + k] = t;
+                        if (pass) W.rbint[rr * TSH + k] = 0.5f * (cur_in.c + cur_in.m * (1.0f - t) + cur_in.p * t);
                     }
+                    cur[k] = t;
                 }
-                cur[k] = t;
+                cur_in = nxt_in;
+            } else {
+                for (int k = tid; k < TSH; k += nthr) {
+                    float t = P[rr * TSH + k];
+                    if (k >= k0 && k < k0 + ns) {
+                        // diagonal neighbours: previous row (updated) at half indices k-1+par, k+par; next row (original)
+                        const float ul = prev[k - 1 + par], ur = prev[k + par];
+                        const float dl = P[(rr + 1) * TSH + k - 1 + par], dr = P[(rr + 1) * TSH + k + par];
+                        const float s4 = ul + ur + dl + dr;
+                        const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
+                        t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
+                        P[rr * TSH + k] = t;
+                        if (pass) {
+                            const int i = rr * TS + 2 * k + par;
+                            W.rbint[rr * TSH + k] = 0.5f * (cfa[i] + W.rbm[rr * TSH + k] * (1.0f - t) + W.rbp[rr * TSH + k] * t);
+                        }
+                    }
+                    cur[k] = t;
+                }
             }
             C.sync();
         }
