@@ -427,6 +427,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         if (plan) { Q.items = plan->d_wide_items; Q.row_start = plan->d_wide_row_start; Q.vals = P.vals; Q.n_entries = plan->n_entries; }
         Q.nstrips = ceil_div(g.w, FW_STRIP_PX); Q.nframes = nframes;
         Q.one = 1; Q.mone = -1;
+        Q.shl[0] = 1u << 14; Q.shl[1] = 1u << 10; Q.shl[2] = 1u << 6; Q.shl[3] = 1u << 2;
         Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, ctx->sm_count * FW_WARPS);
         Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
         static std::once_flag once;

@@ -64,6 +64,7 @@ struct WideParams {
     int black16, white16;
     struct { unsigned coef, k1; } gain[8];   // stripe gain and -black * gain (mod 2^32)
     int one, mone;                    // +1 / -1: multipliers of the FMA-pipe additions (opaque to the compiler)
+    unsigned shl[4];                  // 2^14, 2^10, 2^6, 2^2: left shifts done as FMA-pipe multiplies (-DFW_EXTRACT_SHL)
     const WideItem *items; const unsigned *row_start; const uint16_t *vals; unsigned n_entries;
     int nstrips, nseg, seg_rows, nframes;
 };
@@ -102,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }   // one VIMNMX3
 __device__ __forceinline__ int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8]; int one, mone; };
+struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8]; uint32_t shl[4]; int one, mone; };
 
 // a * m + b on the FMA pipe (IMAD with a register multiplier the compiler cannot fold): the min/max network
 // keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
@@ -128,11 +129,19 @@ __device__ __forceinline__ int imed3(int a, int b, int c, const WideConst &K)
 
 // pixel I of a lane's pixel group; W[] are the group's 32-bit words in stream order
 template <int I>
-__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW])
+__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW], const uint32_t (&shl)[4])
 {
     constexpr int bit = 14 * I, j = bit >> 5, s = bit & 31;
     uint32_t v;
+#ifdef FW_EXTRACT_SHL
+    // (W << s) >> 18 with the left shift as a multiply by a kernel parameter (2^s, opaque to the compiler): the
+    // multiply issues on the FMA pipe and leaves one ALU-pipe shift instead of shift + mask
+    if constexpr (s == 0) v = W[j] >> 18;
+    else if constexpr (s == 14 || s == 10 || s == 6 || s == 2) v = (W[j] * shl[(14 - s) / 4]) >> 18;
+    else if constexpr (s <= 18) v = (W[j] >> (18 - s)) & 0x3FFFu;
+#else
     if constexpr (s <= 18) v = (W[j] >> (18 - s)) & 0x3FFFu;
+#endif
     else v = __funnelshift_l(W[j + 1], W[j], s) >> 18;
     asm("" : "+r"(v));          // keep the table address a plain v * 4 (one IMAD) instead of a second shift + mask of W
     return v;
@@ -168,8 +177,8 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
 template <int STRIPES, int C>
 __device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[FW_NW], const uint32_t (&B)[FW_NW], const WideConst &K, WideRow &R)
 {
-    const uint32_t r = wide_px<2 * C>(T), g1 = wide_px<2 * C + 1>(T);
-    const uint32_t g2 = wide_px<2 * C>(B), b = wide_px<2 * C + 1>(B);
+    const uint32_t r = wide_px<2 * C>(T, K.shl), g1 = wide_px<2 * C + 1>(T, K.shl);
+    const uint32_t g2 = wide_px<2 * C>(B, K.shl), b = wide_px<2 * C + 1>(B, K.shl);
     const int ge = wadd(FW_R2E(g1), FW_R2E(g2)) / 2;
     R.ge[C] = ge;
     R.dr[C] = wsub(FW_R2E(r), ge);
@@ -362,6 +371,8 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
 #pragma unroll
     for (int i = 0; i < 8; i++) { K.coef[i] = P.gain[i].coef; K.k1[i] = P.gain[i].k1; }
     K.one = P.one; K.mone = P.mone;
+#pragma unroll
+    for (int i = 0; i < 4; i++) K.shl[i] = P.shl[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = fw_smem + FW_SMEM_R2E + FW_SMEM_T13 + warp * FW_STAGE_PER_WARP;
     const int w = P.w, ph = P.h >> 1;
