@@ -116,7 +116,9 @@ __device__ __forceinline__ int fma_add(int a, int m, int b)
 // the middle of three = a + b + c - min - max; exact in wrap-around arithmetic (a permutation of the three)
 __device__ __forceinline__ int mid_of(int a, int b, int c, int lo, int hi, const WideConst &K)
 {
-#ifndef FW_SUMS_ON_FMA
+#if defined(FW_SUMS_HALF)
+    return fma_add(hi, K.mone, fma_add(lo, K.mone, (int)((unsigned)a + (unsigned)b + (unsigned)c)));   // one IADD3 + two IMAD
+#elif !defined(FW_SUMS_ON_FMA)
     return (int)((unsigned)a + (unsigned)b + (unsigned)c - (unsigned)lo - (unsigned)hi);
 #else
     return fma_add(hi, K.mone, fma_add(lo, K.mone, fma_add(c, K.one, fma_add(a, K.one, b))));
