@@ -23,7 +23,7 @@
 
 int amz_threads()
 {
-    static const int v = [] { const char *e = getenv("MLVB_AMZ_THREADS"); int t = e ? atoi(e) : 512; return t >= 64 && t <= 1024 && t % 32 == 0 ? t : 512; }();
+    static const int v = [] { const char *e = getenv("MLVB_AMZ_THREADS"); int t = e ? atoi(e) : 256; return t >= 64 && t <= 1024 && t % 32 == 0 ? t : 256; }();
     return v;
 }
 
@@ -31,9 +31,11 @@ int amz_blocks()
 {
     static const int v = [] {
         const char *e = getenv("MLVB_AMZ_BLOCKS_PER_SM");
-        int b = e ? atoi(e) : 2, sms = 148;
+        // 256 threads x 4 blocks per SM: measured best on B200 (tools/sweep_amz.sh); the row-sequential passes keep only
+        // ~80-160 threads of a tile busy, so more, smaller tile programs per SM hide their latency better
+        int b = e ? atoi(e) : 4, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-        b = b >= 1 && b <= 6 ? b : 2;
+        b = b >= 1 && b <= 6 ? b : 4;
         return std::min(b * sms, (int)AMZ_MAX_BLOCKS);
     }();
     return v;
@@ -91,13 +93,6 @@ __global__ void amz_gray_kernel(const float *__restrict__ red, const float *__re
     grayev[x + (size_t)y * w] = __ldg(raw2ev + (gray & 0xFFFFF));
 }
 
-__device__ __forceinline__ double amz_fullres_curve_at(int i, int black)         // hdr.c:904-909
-{
-    const double ev2 = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0));
-    const double c2 = -cos(fmax(fmin(ev2 - 4.0, 4.0), 0.0) * M_PI / 4.0);
-    return (c2 + 1.0) / 2.0;
-}
-
 __global__ void __launch_bounds__(128)
 amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ grayev, uint8_t *__restrict__ edir,
                     int w, int h, int black, int white_darkened, int b0, int b1, int b2, int b3,
@@ -111,7 +106,7 @@ amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ 
         const uint32_t p = raw32[x + (size_t)y * w];
         bool search;
         if (!isb[y & 3]) {                                                         // deep shadows of the dark exposure (hdr.c:1106-1120)
-            // fullres_curve[p] > 0.8 from the per-black table of dualiso.cu (same function as amz_fullres_curve_at);
+            // fullres_curve[p] > 0.8 from the per-black table of dualiso.cu (hdr.c:904-909);
             // where the table's crossing is a single index the test is a comparison
             const int lo = __ldg(fullres_lim + 2), hi = __ldg(fullres_lim + 3);
             search = lo == hi ? !((int)(p & 0xFFFFF) >= lo) : !(__ldg(fullres_curve + (p & 0xFFFFF)) > 0.8);
