@@ -193,6 +193,7 @@ fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, uns
 // never wait for global memory.
 constexpr int LONG_WARPS_MAX = 16;
 constexpr int LONG_CHUNK = 256;            // list entries staged per warp at a time
+constexpr int LONG_WIN = 1024;             // pixels of a row staged per warp at a time
 
 template <bool SMEM_EV2RAW>
 __global__ void __launch_bounds__(LONG_WARPS_MAX * 32)
@@ -213,7 +214,10 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
     const int w = A.w, h = A.h, black = A.lut.black;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp >= warps_per_block) return;
-    uint16_t *row = s_rows + (size_t)warp * ((w + 7) & ~7);
+    // per warp: a window of LONG_WIN pixels of the row being repaired (+ 8 spare) and LONG_CHUNK staged entry columns
+    uint16_t *win = s_rows + (size_t)warp * (LONG_WIN + 8 + LONG_CHUNK);
+    uint16_t *xs = win + LONG_WIN + 8;
+    uint16_t *row = win;                                                        // row[x] = win[x - wx0], set per window
     auto ev_of_raw = [&](int v) { return v < 16384 ? s_r2e[v] : __ldg(A.lut.raw2ev + v); };
     auto raw_of_ev = [&](int e) {
         const int c = clamp_ev(e);
@@ -273,9 +277,6 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
             continue;
         }
         uint16_t *grow = A.img + (size_t)frame * A.frame_stride + (size_t)y * w;
-        for (int x = lane; x < w; x += 32) row[x] = grow[x];
-        __syncwarp();
-        lastx = -100;
         auto one_entry = [&](int x) {                                           // rows 4 .. h-4: fix_entry with dual_iso = 1
             if (x > 2 && x < w - 3) interp_h(x);
             else if (A.edge_rules && x >= 0 && x < w) {
@@ -284,49 +285,72 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
                 lastx = -100;
             }
         };
-        // The entries' columns are staged LONG_CHUNK at a time (coalesced) so that no walk waits for the list.
-        // Entries more than 3 columns apart cannot see each other (an entry reads x-3 .. x+3 and writes x), so a chunk
-        // whose entries come in ascending x splits into independent runs: the lane that holds the first entry of a
-        // run walks that run in list order, all runs of the chunk at once.  A run that continues from the previous
-        // chunk is continued by whoever holds its next entry: the EV window is only a cache of the staged row.
-        // Chunks that are not ascending (a focus-pixel map in file order) are walked by lane 0 alone.
-        uint16_t *xs = s_rows + (size_t)warps_per_block * ((w + 7) & ~7) + (size_t)warp * LONG_CHUNK;
-        int prev_last = -0x3FFFFFFF;                                            // column of the entry before this chunk
-        for (unsigned mb = m0; mb < m1; mb += LONG_CHUNK) {
-            const int n = (int)min((unsigned)LONG_CHUNK, m1 - mb);
-            bool ascending = true;
-            for (int i = lane; i < n; i += 32) {
-                const int x = A.list[mb + i].x - A.crop_x;
-                xs[i] = (uint16_t)min(max(x, -1), 0xFFFE) + 1;                  // biased by 1: 0 = left of the frame
+        // ascending rows (a detected bad-pixel list is in raster order) are repaired window by window in shared memory;
+        // anything else (a focus-pixel map in file order) by one lane directly on the frame
+        bool ascending = true;
+        for (unsigned mb = m0; mb < m1; mb += 32) {
+            const unsigned m = mb + lane;
+            const bool bad = m + 1 < m1 && A.list[m + 1].x < A.list[m].x;
+            ascending = ascending && !__any_sync(0xFFFFFFFFu, bad);
+        }
+        if (!ascending) {
+            if (lane == 0) {
+                row = grow;
+                lastx = -100;
+                for (unsigned m = m0; m < m1; m++) one_entry(A.list[m].x - A.crop_x);
             }
             __syncwarp();
-            for (int i = lane; i < n; i += 32) ascending = ascending && !(i + 1 < n && xs[i + 1] < xs[i]);
-            ascending = __all_sync(0xFFFFFFFFu, ascending) && (int)xs[0] - 1 >= prev_last;
-            if (ascending) {
+            continue;
+        }
+        // Windows of LONG_WIN pixels slide along the row: a window starts 3 pixels left of the first entry that is still
+        // to do and takes every entry whose stencil (x-3 .. x+4) lies inside it.  The entries' columns are staged
+        // LONG_CHUNK at a time (coalesced) so that no walk waits for the list.  Entries more than 3 columns apart cannot
+        // see each other (an entry reads x-3 .. x+3 and writes x), so a chunk splits into independent runs: the lane
+        // that holds the first entry of a run walks that run in list order, all runs of the chunk at once; a run that
+        // continues from the previous chunk or window is picked up by lane 0 (the EV window is only a cache of the
+        // staged pixels).
+        unsigned m = m0;
+        while (m < m1) {
+            const int xf = min(max(A.list[m].x - A.crop_x, 0), w - 1);
+            const int wx0 = max(min(xf - 3, w - LONG_WIN), 0);
+            const int wlen = min(LONG_WIN, w - wx0);
+            const int xlim = wx0 + wlen >= w ? 0x3FFFFFFF : wx0 + wlen - 5;     // last column whose stencil fits
+            for (int i = lane; i < wlen; i += 32) win[i] = grow[wx0 + i];
+            row = win - wx0;
+            __syncwarp();
+            bool window_full = false;
+            while (m < m1 && !window_full) {
+                const int n = (int)min((unsigned)LONG_CHUNK, m1 - m);
+                int nin = 0;                                                    // staged entries that fit this window (a prefix)
                 for (int i = lane; i < n; i += 32) {
-                    const int x = (int)xs[i] - 1, xp = i ? (int)xs[i - 1] - 1 : prev_last;
-                    if (x - xp > 3 || (i == 0 && lane == 0)) {                  // first entry of a run (or of the chunk)
-                        lastx = -100;                                           // (re)build the EV window from the staged row
+                    const int x = A.list[m + i].x - A.crop_x;
+                    xs[i] = (uint16_t)(min(max(x, -1), 0xFFFE) + 1);            // biased by 1: 0 = left of the frame
+                    nin += x <= xlim;
+                }
+                for (int o = 16; o; o >>= 1) nin += __shfl_xor_sync(0xFFFFFFFFu, nin, o);
+                __syncwarp();
+                for (int i = lane; i < nin; i += 32) {
+                    const int x = (int)xs[i] - 1;
+                    if (i == 0 || x - ((int)xs[i - 1] - 1) > 3) {               // first entry of a run (or of the chunk)
+                        lastx = -100;                                           // (re)build the EV window from the staged pixels
                         int j = i, xx = x;
                         while (true) {
                             one_entry(xx);
-                            if (++j >= n) break;
+                            if (++j >= nin) break;
                             const int xnext = (int)xs[j] - 1;
                             if (xnext - xx > 3) break;
                             xx = xnext;
                         }
                     }
                 }
-            } else if (lane == 0) {
-                lastx = -100;
-                for (int i = 0; i < n; i++) one_entry((int)xs[i] - 1);
+                __syncwarp();
+                m += (unsigned)nin;
+                if (nin == 0) m++;                                              // cannot happen (a window takes its first entry); never spin
+                window_full = nin < n;
             }
-            prev_last = (int)xs[n - 1] - 1;
+            for (int i = lane; i < wlen; i += 32) grow[wx0 + i] = win[i];
             __syncwarp();
         }
-        __syncwarp();
-        for (int x = lane; x < w; x += 32) grow[x] = row[x];
-        __syncwarp();
     }
 }
 
@@ -474,7 +498,8 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
     const size_t row_bytes = (size_t)((w + 7) & ~7) * sizeof(uint16_t);
     // rows per SM with both tables in shared memory; if that cannot hold all long rows of the batch at once, keep
     // only the log table there (the exp table is then read through L1) to avoid a second round of serial chains
-    const size_t warp_bytes = row_bytes + LONG_CHUNK * sizeof(uint16_t);          // staged row + staged entry columns
+    (void)row_bytes;
+    const size_t warp_bytes = (LONG_WIN + 8 + LONG_CHUNK) * sizeof(uint16_t);     // staged pixel window + staged entry columns
     int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / warp_bytes);
     bool long_ev2raw_smem = ev2raw_octaves_ok != 0;
     const char *force_smem = getenv("MLVB_LONG_SMEM");
