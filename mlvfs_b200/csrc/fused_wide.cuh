@@ -22,6 +22,12 @@
 // (cs.c:49-84, chroma_smooth.c:22-71, stripes.c:250-266); results are bit-identical.
 #pragma once
 
+#ifdef FW_PLAIN_STORES
+#define FW_STORE(p, v) (*(p) = (v))
+#else
+#define FW_STORE(p, v) __stcs(p, v)
+#endif
+
 namespace {
 
 #ifndef FW_COLS_CFG
@@ -308,8 +314,8 @@ __device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const ui
         do_col(ColTag<3>{}); fin_col(ColTag<2>{});
         do_col(ColTag<4>{}); fin_col(ColTag<3>{});
         if (emit && writer) {
-            __stcs(reinterpret_cast<uint4 *>(orow), make_uint4(top[0], top[1], top[2], top[3]));
-            __stcs(reinterpret_cast<uint4 *>(orow + w), make_uint4(bot[0], bot[1], bot[2], bot[3]));
+            FW_STORE(reinterpret_cast<uint4 *>(orow), make_uint4(top[0], top[1], top[2], top[3]));
+            FW_STORE(reinterpret_cast<uint4 *>(orow + w), make_uint4(bot[0], bot[1], bot[2], bot[3]));
         }
         do_col(ColTag<5>{}); fin_col(ColTag<4>{});
         do_col(ColTag<6>{}); fin_col(ColTag<5>{});
@@ -318,8 +324,8 @@ __device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const ui
     fin_col(ColTag<FW_COLS - 1>{});
     if (emit && writer) {
         constexpr int o = FW_COLS - 4;
-        __stcs(reinterpret_cast<uint4 *>(orow + 2 * o), make_uint4(top[o], top[o + 1], top[o + 2], top[o + 3]));
-        __stcs(reinterpret_cast<uint4 *>(orow + w + 2 * o), make_uint4(bot[o], bot[o + 1], bot[o + 2], bot[o + 3]));
+        FW_STORE(reinterpret_cast<uint4 *>(orow + 2 * o), make_uint4(top[o], top[o + 1], top[o + 2], top[o + 3]));
+        FW_STORE(reinterpret_cast<uint4 *>(orow + w + 2 * o), make_uint4(bot[o], bot[o + 1], bot[o + 2], bot[o + 3]));
     }
 }
 
