@@ -298,6 +298,7 @@ void mlvb_context_destroy(mlvb_context *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    dual_iso_free_tables(ctx);
     for (auto &s : ctx->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);

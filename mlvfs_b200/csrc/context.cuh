@@ -162,6 +162,7 @@ size_t dual_iso_scratch_bytes(int w, int h, int interp_method);
 int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, uint16_t *d_img, int interp_method,
                  int use_fullres, int use_alias_map, int cs_method, int fix_bad_pixels_mode, void *d_aux, cudaStream_t st);
 void dual_iso_reset_tables(mlvb_context *ctx);
+void dual_iso_free_tables(mlvb_context *ctx);
 
 // fused.cu: MLVB_OK = enqueued, 1 = not eligible (use the general path), < 0 = error
 int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, const mlvb_options &opts,

@@ -127,8 +127,7 @@ static int launch_stats_a(bool hist, const uint16_t *d_img, int w, int h, int bl
     if ((w & 1) || ((uintptr_t)d_img & 3)) return MLVB_ERR_UNSUPPORTED;   // pixel pairs are read as 32-bit words
     const int nblocks = std::max(4, std::min(sm_count > 0 ? sm_count : 148, (h + 3) / 4 * 4) / 4 * 4);
     if (hist) {
-        static std::once_flag once;
-        std::call_once(once, [] { cudaFuncSetAttribute(diso_stats_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STATS_A_SMEM); });
+        cudaFuncSetAttribute(diso_stats_a_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STATS_A_SMEM);   // per device
         diso_stats_a_kernel<true><<<nblocks, STATS_A_THREADS, STATS_A_SMEM, st>>>(d_img, w, h, black, white, raw2evf, S);
     } else {
         diso_stats_a_kernel<false><<<nblocks, STATS_A_THREADS, 0, st>>>(d_img, w, h, black, white, raw2evf, S);
@@ -636,16 +635,38 @@ struct DualIsoTables {
     std::vector<double> test_a;
 };
 
+static std::mutex g_tabs_mu;
+static std::map<mlvb_context *, DualIsoTables *> g_tabs;
+
 static DualIsoTables *tables_of(mlvb_context *ctx)
 {
-    static std::mutex g_mu;
-    static std::map<mlvb_context *, DualIsoTables *> g_tabs;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_tabs_mu);
     auto it = g_tabs.find(ctx);
     if (it != g_tabs.end()) return it->second;
     DualIsoTables *t = new DualIsoTables();
     g_tabs[ctx] = t;
     return t;
+}
+
+// called by mlvb_context_destroy (the context's device is current, all work has finished)
+void dual_iso_free_tables(mlvb_context *ctx)
+{
+    DualIsoTables *t = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_tabs_mu);
+        auto it = g_tabs.find(ctx);
+        if (it == g_tabs.end()) return;
+        t = it->second;
+        g_tabs.erase(it);
+    }
+    for (void *p : t->pinned_free) cudaFreeHost(p);
+    if (t->d_raw2ev) cudaFree(t->d_raw2ev);
+    if (t->d_ev2raw_0) cudaFree(t->d_ev2raw_0);
+    if (t->d_raw2evf) cudaFree(t->d_raw2evf);
+    if (t->d_fullres_curve) cudaFree(t->d_fullres_curve);
+    if (t->d_fullres_lim) cudaFree(t->d_fullres_lim);
+    if (t->d_test_a) cudaFree(t->d_test_a);
+    delete t;
 }
 
 constexpr size_t PINNED_STAGE_BYTES = sizeof(StatsA) + 2 * 65536 * sizeof(unsigned) + 2 * (65536 + 8) * sizeof(unsigned) +

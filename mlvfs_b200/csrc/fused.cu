@@ -430,17 +430,16 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         Q.shl[0] = 1u << 14; Q.shl[1] = 1u << 10; Q.shl[2] = 1u << 6; Q.shl[3] = 1u << 2;
         Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, ctx->sm_count * FW_WARPS);
         Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
-        static std::once_flag once;
-        std::call_once(once, [] {
-            cudaFuncSetAttribute(fused3_wide_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
-            cudaFuncSetAttribute(fused3_wide_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
-            cudaFuncSetAttribute(fused3_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
-        });
-        StageTimer t(ctx, ST_CHROMA, st);
+        // the opt-in to > 48 KB of dynamic shared memory is per device: set it with every launch (a context may live on any GPU)
         const bool unit01 = P.coef[0] == 65536 && P.coef[1] == 65536 && P.white16 > P.black16 + 64;
-        if (P.stripes && unit01) fused3_wide_kernel<2><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
-        else if (P.stripes) fused3_wide_kernel<1><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
-        else fused3_wide_kernel<0><<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        auto launch = [&](auto kernel) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM_BYTES);
+            kernel<<<ctx->sm_count, FW_THREADS, FW_SMEM_BYTES, st>>>(Q);
+        };
+        StageTimer t(ctx, ST_CHROMA, st);
+        if (P.stripes && unit01) launch(fused3_wide_kernel<2>);
+        else if (P.stripes) launch(fused3_wide_kernel<1>);
+        else launch(fused3_wide_kernel<0>);
         ctx->launches += 1;
         ctx->path_count[1] += 1;
     } else {
