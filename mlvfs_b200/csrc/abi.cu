@@ -297,8 +297,13 @@ void mlvb_context_destroy(mlvb_context *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    {
+        std::lock_guard<std::mutex> lk(ctx->job_mu);
+        ctx->stopping = true;
+    }
+    ctx->job_cv.notify_all();
+    for (auto &t : ctx->submit_workers) t.join();
     cudaDeviceSynchronize();
-    dual_iso_free_tables(ctx);
     for (auto &s : ctx->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
@@ -323,6 +328,7 @@ void mlvb_context_destroy(mlvb_context *ctx)
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_stat) cudaFree(ctx->d_stat);
     mlvb_reset_clip_state(ctx);
+    dual_iso_free_tables(ctx);
     cudaFree(ctx->d_raw2ev_base);
     cudaFree(ctx->d_ev2raw_pos);
     cudaFree(ctx->d_ev2raw_full);
@@ -357,6 +363,8 @@ void mlvb_reset_clip_state(mlvb_context *ctx)
     ctx->bad_map_cursor = 0;
     ctx->focus_maps.clear();
     dual_iso_reset_tables(ctx);          // the 20-bit EV tables remember the first frame's white level (hdr.c:1089-1093)
+    std::lock_guard<std::mutex> jl(ctx->job_mu);
+    ctx->async_clips.clear();            // the next frame of every clip recreates its state synchronously
 }
 
 void mlvb_seed_dither(mlvb_context *ctx, unsigned seed)
@@ -419,6 +427,61 @@ uint64_t mlvb_path_count(mlvb_context *ctx, int which) { return (ctx && which >=
 
 // ------------------------------------------------------------------ host-buffer pipeline
 
+// H2D -> pipeline -> D2H -> event on the slot's stream (everything mlvb_submit enqueues for one frame)
+static int run_slot_job(mlvb_context *ctx, Slot *s, const struct frame_headers *hdr, const mlvb_options *opts, const char *mlv_filename,
+                        const void *src, size_t payload_bytes, uint16_t *dst)
+{
+    const FrameGeom g = geom_from_headers(hdr);
+    const size_t frame_bytes = g.npix * 2;
+    if (cudaMemcpyAsync(s->d_packed, src, payload_bytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) return MLVB_ERR_CUDA;
+    s->result = mlvb_frame_result();
+    *s->h_status = 0;
+    const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
+    int rc = reserve_device(&s->d_aux, &s->aux_cap,
+                            std::max(aux_bytes_for(g, *opts), coded ? lj92_scratch_bytes(payload_bytes, g.npix, 1) : (size_t)0));
+    if (rc) return rc;
+    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->d_status,
+                      s->d_aux, s->aux_cap, s->stream, &s->result);
+    if (rc == MLVB_OK && coded &&
+        cudaMemcpyAsync(s->h_status, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
+        rc = MLVB_ERR_CUDA;
+    if (rc) { cudaStreamSynchronize(s->stream); return rc; }
+    s->out_bytes = frame_bytes;
+    const bool dst_pinned = is_pinned(dst);
+    s->user_dst = dst_pinned ? nullptr : dst;
+    if (cudaMemcpyAsync(dst_pinned ? (void *)dst : (void *)s->h_out, s->d_b, frame_bytes, cudaMemcpyDeviceToHost,
+                        s->stream) != cudaSuccess ||
+        cudaEventRecord(s->done, s->stream) != cudaSuccess) {
+        cudaStreamSynchronize(s->stream);
+        return MLVB_ERR_CUDA;
+    }
+    return MLVB_OK;
+}
+
+static void submit_worker(mlvb_context *ctx)
+{
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        AsyncJob job;
+        {
+            std::unique_lock<std::mutex> lk(ctx->job_mu);
+            ctx->job_cv.wait(lk, [&] { return ctx->stopping || !ctx->jobs.empty(); });
+            if (ctx->jobs.empty()) return;                                  // stopping
+            job = ctx->jobs.front();
+            ctx->jobs.pop_front();
+        }
+        const int rc = run_slot_job(ctx, job.slot, &job.hdr, &job.opts, job.clip.c_str(), job.src, job.payload_bytes, job.dst);
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            job.slot->job_rc = rc;
+            job.slot->job_done = true;
+        }
+        ctx->cv.notify_all();
+    }
+}
+
+constexpr int SUBMIT_WORKERS = 4;
+
 mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
                         const mlvb_options *opts, const char *mlv_filename, uint16_t *dst)
 {
@@ -431,34 +494,41 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
     auto fail = [&](int rc) -> mlvb_ticket { release_slot(ctx, s); return rc; };
     int rc = slot_reserve(*s, payload_bytes, frame_bytes);
     if (rc) return fail(rc);
+    s->async = false; s->job_done = false; s->job_rc = MLVB_OK;
 
     // H2D: straight from the caller's buffer when it is pinned, else through the slot's pinned stage
     const void *src = payload;
     if (!is_pinned(payload)) { memcpy(s->h_in, payload, payload_bytes); src = s->h_in; }
-    if (cudaMemcpyAsync(s->d_packed, src, payload_bytes, cudaMemcpyHostToDevice, s->stream) != cudaSuccess)
-        return fail(MLVB_ERR_CUDA);
 
-    s->result = mlvb_frame_result();
-    *s->h_status = 0;
-    const bool coded = (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
-    rc = reserve_device(&s->d_aux, &s->aux_cap,
-                        std::max(aux_bytes_for(g, *opts), coded ? lj92_scratch_bytes(payload_bytes, g.npix, 1) : (size_t)0));
+    // The full dual-ISO pipeline waits on the host several times per frame (statistics read-backs): once the clip's
+    // per-clip state exists (its first frame went through synchronously, below), such frames go to the submit workers
+    // so that the frames in flight overlap.  payload (when pinned) and dst must stay valid until mlvb_wait.
+    const bool blocking = opts->dual_iso == 2 && !ctx->profiling && getenv("MLVB_SYNC_SUBMIT") == nullptr;
+    std::string key;
+    if (blocking) {
+        char tag[64];
+        snprintf(tag, sizeof(tag), "|%d.%d.%d.%d.%d.%d", opts->fix_bad_pixels, opts->fix_stripes, opts->chroma_smooth,
+                 opts->hdr_interpolation_method, opts->hdr_no_fullres, opts->hdr_no_alias_map);
+        key = std::string(mlv_filename ? mlv_filename : "") + tag;
+        std::unique_lock<std::mutex> lk(ctx->job_mu);
+        if (ctx->async_clips.count(key)) {
+            if (ctx->submit_workers.empty())
+                for (int i = 0; i < SUBMIT_WORKERS; i++) ctx->submit_workers.emplace_back(submit_worker, ctx);
+            s->async = true;
+            AsyncJob job;
+            job.slot = s; job.hdr = *hdr; job.opts = *opts; job.clip = mlv_filename ? mlv_filename : "";
+            job.src = src; job.payload_bytes = payload_bytes; job.dst = dst;
+            ctx->jobs.push_back(std::move(job));
+            lk.unlock();
+            ctx->job_cv.notify_one();
+            return s->ticket;
+        }
+    }
+    rc = run_slot_job(ctx, s, hdr, opts, mlv_filename, src, payload_bytes, dst);
     if (rc) return fail(rc);
-    rc = run_pipeline(ctx, hdr, *opts, mlv_filename, s->d_packed, 0, payload_bytes, s->d_a, s->d_b, g.npix, 1, s->d_status,
-                      s->d_aux, s->aux_cap, s->stream, &s->result);
-    if (rc == MLVB_OK && coded &&
-        cudaMemcpyAsync(s->h_status, s->d_status, sizeof(int), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
-        rc = MLVB_ERR_CUDA;
-    if (rc) { cudaStreamSynchronize(s->stream); return fail(rc); }
-
-    s->out_bytes = frame_bytes;
-    const bool dst_pinned = is_pinned(dst);
-    s->user_dst = dst_pinned ? nullptr : dst;
-    if (cudaMemcpyAsync(dst_pinned ? (void *)dst : (void *)s->h_out, s->d_b, frame_bytes, cudaMemcpyDeviceToHost,
-                        s->stream) != cudaSuccess ||
-        cudaEventRecord(s->done, s->stream) != cudaSuccess) {
-        cudaStreamSynchronize(s->stream);
-        return fail(MLVB_ERR_CUDA);
+    if (blocking) {
+        std::lock_guard<std::mutex> lk(ctx->job_mu);
+        ctx->async_clips.insert(key);
     }
     return s->ticket;
 }
@@ -467,13 +537,19 @@ int mlvb_wait(mlvb_context *ctx, mlvb_ticket ticket, mlvb_frame_result *res)
 {
     if (!ctx || ticket < 0) return MLVB_ERR_ARG;
     Slot *s = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        for (auto &c : ctx->slots) if (c.busy && c.ticket == ticket) { s = &c; break; }
-    }
-    if (!s) return MLVB_ERR_ARG;
     int rc = MLVB_OK;
-    if (cudaEventSynchronize(s->done) != cudaSuccess) {
+    {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        for (auto &c : ctx->slots) if (c.busy && c.ticket == ticket) { s = &c; break; }
+        if (!s) return MLVB_ERR_ARG;
+        if (s->async) {
+            ctx->cv.wait(lk, [&] { return s->job_done; });
+            rc = s->job_rc;
+        }
+    }
+    if (rc != MLVB_OK) {
+        // the worker already synchronised the stream
+    } else if (cudaEventSynchronize(s->done) != cudaSuccess) {
         fprintf(stderr, "libmlvfs_b200: frame failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         rc = MLVB_ERR_CUDA;
     } else if (*s->h_status != 0) {

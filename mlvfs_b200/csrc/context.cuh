@@ -4,6 +4,9 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <deque>
+#include <set>
+#include <thread>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -74,6 +77,19 @@ struct Slot {
     uint16_t *user_dst = nullptr;          // non-null: copy h_out -> user_dst in wait()
     size_t out_bytes = 0;
     mlvb_frame_result result{};
+    // asynchronous submission (frames whose pipeline waits on the host, see abi.cu): set under mlvb_context::mu
+    bool async = false, job_done = false;
+    int job_rc = 0;
+};
+
+struct AsyncJob {                          // one submitted frame waiting for a submit worker
+    Slot *slot;
+    struct frame_headers hdr;
+    mlvb_options opts;
+    std::string clip;
+    const void *src;
+    size_t payload_bytes;
+    uint16_t *dst;
 };
 
 struct mlvb_context {
@@ -89,6 +105,15 @@ struct mlvb_context {
     std::condition_variable cv;
     std::vector<Slot> slots;
     int64_t next_ticket = 0;
+
+    // submit workers: frames of the full dual-ISO pipeline block on statistics read-backs, so mlvb_submit hands them
+    // to a few host threads (one frame each, the slot's own stream) once the clip's per-clip state exists
+    std::vector<std::thread> submit_workers;
+    std::deque<AsyncJob> jobs;
+    std::mutex job_mu;
+    std::condition_variable job_cv;
+    bool stopping = false;
+    std::set<std::string> async_clips;     // clip + option keys whose first frame has been processed (under job_mu)
 
     std::mutex clip_mu;                    // per-clip state (creation is once-only, under this lock)
     std::map<std::string, StripesState> stripes;

@@ -144,3 +144,48 @@ def test_dual_iso_pixel_fix_long_rows(fresh_ctx, oracle):
     got = M.fix_bad_pixels(hdr, img2.copy(), 1, 1)               # same map, horizontal interpolator
     want = oracle.badpix_apply(img2, 2048, want_list, dual_iso=1)
     assert np.array_equal(got, want), int(np.count_nonzero(got != want))
+
+
+def test_dual_iso_frames_in_flight_match_one_at_a_time(fresh_ctx):
+    """mlvb_submit hands dual-ISO frames to its submit workers once the clip's state exists; several frames in flight
+    (pinned and pageable buffers mixed) must give exactly the frames that one-at-a-time processing gives."""
+    w, h, n = 640, 384, 7
+    hdr = F.make_frame_headers(w, h, file_guid=0xA5A5)
+    o = M.Options(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=3, fix_bad_pixels=1)
+    frames = [synth.make_frame(w, h, i, dual_iso=True, hot_cold=True) for i in range(n)]
+    packed = [synth.pack_bits(f) for f in frames]
+    want = []
+    for p in packed:
+        out, res = fresh_ctx.process_frame(hdr, p, o, "inflight.MLV")
+        assert res.status == 0 and res.is_dual_iso == 1
+        want.append(out.copy())
+    nbytes = packed[0].size * 2
+    pin_in = M.PinnedBuffer(n * nbytes)
+    pin_in.array[:] = np.concatenate([p.view(np.uint8).reshape(-1) for p in packed])
+    pin_out = [M.PinnedBuffer(w * h * 2) for _ in range(n)]
+    pageable_out = np.zeros((h, w), np.uint16)
+    try:
+        depth = 3                                                # the fixture's context has 4 slots: never ask for a 5th
+        for rep in range(2):
+            pending = []
+
+            def finish(i, t):
+                rc, res = fresh_ctx.wait(t)
+                assert rc == 0 and res.is_dual_iso == 1 and res.black_level == 8192
+                got = pageable_out if i == 3 else pin_out[i].array.view(np.uint16).reshape(h, w)
+                assert np.array_equal(got, want[i]), (rep, i)
+
+            for i in range(n):
+                if len(pending) == depth:
+                    finish(*pending.pop(-1 if i % 2 else 0))     # not always the oldest
+                dst = pageable_out.ctypes.data if i == 3 else pin_out[i].ptr
+                src = packed[i].ctypes.data if i == 5 else pin_in.ptr + i * nbytes
+                t = fresh_ctx.submit(hdr, C.c_void_p(src), nbytes, o, "inflight.MLV", C.c_void_p(dst))
+                assert t >= 0
+                pending.append((i, t))
+            while pending:
+                finish(*pending.pop())
+    finally:
+        pin_in.free()
+        for p in pin_out:
+            p.free()
