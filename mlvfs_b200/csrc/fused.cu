@@ -416,20 +416,41 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
     bool wide = ctx->ev2raw_octaves_ok && ctx->sm_count > 0 && (g.w % 64) == 0 && ((uintptr_t)d_out % 16) == 0 &&
                 (out_stride_px % 8) == 0 && (payload_stride % 16) == 0 && getenv("MLVB_NO_WIDE") == nullptr &&
                 (long long)nframes * ceil_div(g.w, FW_STRIP_PX) * (g.h / 2) >= wide_min_rows(ctx);
-    for (int i = 0; i < 8 && P.stripes; i++) wide = wide && P.coef[i] < (1 << 18);
+    // (v - black) * gain fits 32 bits, and so does (v - black) * gain + (black << 16) (the high-half form of FW_GAIN_X)
+    for (int i = 0; i < 8 && P.stripes; i++)
+        wide = wide && P.coef[i] > 0 && P.coef[i] < (1 << 18) &&
+               (16383LL - P.black16) * P.coef[i] + ((long long)P.black16 << 16) < (1LL << 32);
     if (wide) {
         WideParams Q;
         memset(&Q, 0, sizeof(Q));
         Q.packed = P.packed; Q.payload_stride = payload_stride; Q.out = d_out; Q.out_stride = out_stride_px;
         Q.w = g.w; Q.h = g.h; Q.black = g.black; Q.raw2ev = P.raw2ev; Q.ev2raw13 = ctx->luts.ev2raw_pos + 13 * MLVB_EV_RES;
         Q.black16 = P.black16; Q.white16 = P.white16;
-        for (int i = 0; i < 8; i++) { Q.gain[i].coef = (unsigned)P.coef[i]; Q.gain[i].k1 = 0u - (unsigned)P.black16 * (unsigned)P.coef[i]; }
+        for (int i = 0; i < 8; i++) {
+            Q.gain[i].coef = (unsigned)P.coef[i]; Q.gain[i].k1 = 0u - (unsigned)P.black16 * (unsigned)P.coef[i];
+            Q.coefh[i] = (unsigned)P.coef[i] << 14;       // coef < 2^18 (checked above)
+        }
+        Q.k4 = 0u - 4u * (unsigned)P.black16;
+        for (int i = 0; i < 8; i++) {
+            Q.gainx[i].coef = (unsigned)P.coef[i];
+            Q.gainx[i].kx = ((unsigned)P.black16 << 16) - (unsigned)P.black16 * (unsigned)P.coef[i];
+        }
+        Q.whitex = ((unsigned)P.white16 << 16) | 0xFFFFu;
         if (plan) { Q.items = plan->d_wide_items; Q.row_start = plan->d_wide_row_start; Q.vals = P.vals; Q.n_entries = plan->n_entries; }
         Q.nstrips = ceil_div(g.w, FW_STRIP_PX); Q.nframes = nframes;
         Q.one = 1; Q.mone = -1;
+        Q.shr[0] = 1u << 14; Q.shr[1] = 1u << 17;
         Q.shl[0] = 1u << 14; Q.shl[1] = 1u << 10; Q.shl[2] = 1u << 6; Q.shl[3] = 1u << 2;
-        Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, ctx->sm_count * FW_WARPS);
-        Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
+        // one contiguous run of quad rows per warp (nseg = 0); MLVB_WIDE_SEGMENTS=1 keeps the equal-segment split
+        const long long all_rows = (long long)nframes * Q.nstrips * (g.h / 2);
+        const int nwarps = ctx->sm_count * FW_WARPS;
+        if (all_rows < (1LL << 30) && getenv("MLVB_WIDE_SEGMENTS") == nullptr) {
+            Q.nseg = 0;
+            Q.seg_rows = (int)((all_rows + nwarps - 1) / nwarps);
+        } else {
+            Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, nwarps);
+            Q.seg_rows = ceil_div(g.h / 2, Q.nseg);
+        }
         // the opt-in to > 48 KB of dynamic shared memory is per device: set it with every launch (a context may live on any GPU)
         const bool unit01 = P.coef[0] == 65536 && P.coef[1] == 65536 && P.white16 > P.black16 + 64;
         auto launch = [&](auto kernel) {

@@ -30,6 +30,23 @@
 
 namespace {
 
+// Defaults, each measured on B200 (profiles/r01m_variants.md); -DFW_NO_<name> switches one off.
+#if !defined(FW_NO_MIDPAIR) && !defined(FW_MIDPAIR)
+#define FW_MIDPAIR
+#endif
+#if !defined(FW_NO_PACK_PRMT) && !defined(FW_PACK_PRMT)
+#define FW_PACK_PRMT
+#endif
+#if !defined(FW_NO_EXTRACT_SHL) && !defined(FW_EXTRACT_SHL)
+#define FW_EXTRACT_SHL
+#endif
+#if !defined(FW_NO_GAIN_X) && !defined(FW_GAIN_X) && defined(FW_PACK_PRMT) && !defined(FW_GAIN_HI) && !defined(FW_GAIN_MAD)
+#define FW_GAIN_X
+#endif
+#if defined(FW_GAIN_X) && !defined(FW_PACK_PRMT)
+#error "FW_GAIN_X needs FW_PACK_PRMT (the packing PRMT takes the high halves)"
+#endif
+
 #ifndef FW_COLS_CFG
 #define FW_COLS_CFG 4
 #endif
@@ -69,8 +86,12 @@ struct WideParams {
     const uint16_t *ev2raw13;         // ev2raw[13 EV ...], 32768 entries
     int black16, white16;
     struct { unsigned coef, k1; } gain[8];   // stripe gain and -black * gain (mod 2^32)
+    unsigned coefh[8], k4;            // gain << 14 and -4 * black: ((v - black) * gain) >> 16 as one high multiply (-DFW_GAIN_HI)
+    struct { unsigned coef, kx; } gainx[8];  // kx = (black << 16) - black * gain: v * gain + kx holds the corrected sample in its
+    unsigned whitex;                  // high half (-DFW_GAIN_X); whitex = white << 16 | 0xFFFF clamps it there
     int one, mone;                    // +1 / -1: multipliers of the FMA-pipe additions (opaque to the compiler)
     unsigned shl[4];                  // 2^14, 2^10, 2^6, 2^2: left shifts done as FMA-pipe multiplies (-DFW_EXTRACT_SHL)
+    unsigned shr[2];                  // 2^14, 2^17: right shifts by 18 / 15 as FMA-pipe high multiplies (-DFW_SHR_HI)
     const WideItem *items; const unsigned *row_start; const uint16_t *vals; unsigned n_entries;
     int nstrips, nseg, seg_rows, nframes;
 };
@@ -109,7 +130,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }   // one VIMNMX3
 __device__ __forceinline__ int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8]; uint32_t shl[4]; int one, mone; };
+struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8], coefh[8], k4, kx[8], whitex; uint32_t shl[4], shr[2]; int one, mone; };
 
 // a * m + b on the FMA pipe (IMAD with a register multiplier the compiler cannot fold): the min/max network
 // keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
@@ -137,11 +158,18 @@ __device__ __forceinline__ int imed3(int a, int b, int c, const WideConst &K)
 
 // pixel I of a lane's pixel group; W[] are the group's 32-bit words in stream order
 template <int I>
-__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW], const uint32_t (&shl)[4])
+__device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW], const uint32_t (&shl)[4], uint32_t m14)
 {
     constexpr int bit = 14 * I, j = bit >> 5, s = bit & 31;
     uint32_t v;
-#ifdef FW_EXTRACT_SHL
+#if defined(FW_SHR_HI)
+    // both pipes issue one instruction per two cycles and the ALU pipe is the full one: x >> 18 as the high word of
+    // x * 2^14 (IMAD.HI with a kernel-parameter multiplier the compiler cannot turn back into a shift) runs next door
+    if constexpr (s == 0) v = __umulhi(W[j], m14);
+    else if constexpr (s == 14 || s == 10 || s == 6 || s == 2) v = __umulhi(W[j] * shl[(14 - s) / 4], m14);
+    else if constexpr (s <= 18) v = (W[j] >> (18 - s)) & 0x3FFFu;
+    else if constexpr (s > 18) v = __umulhi(__funnelshift_l(W[j + 1], W[j], s), m14);
+#elif defined(FW_EXTRACT_SHL)
     // (W << s) >> 18 with the left shift as a multiply by a kernel parameter (2^s, opaque to the compiler): the
     // multiply issues on the FMA pipe and leaves one ALU-pipe shift instead of shift + mask
     if constexpr (s == 0) v = W[j] >> 18;
@@ -150,7 +178,9 @@ __device__ __forceinline__ uint32_t wide_px(const uint32_t (&W)[FW_NW], const ui
 #else
     if constexpr (s <= 18) v = (W[j] >> (18 - s)) & 0x3FFFu;
 #endif
+#if !defined(FW_SHR_HI)
     else v = __funnelshift_l(W[j + 1], W[j], s) >> 18;
+#endif
     asm("" : "+r"(v));          // keep the table address a plain v * 4 (one IMAD) instead of a second shift + mask of W
     return v;
 }
@@ -172,7 +202,15 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
     if (STRIPES) {
         // ((v - black) * coef >> 16) + black as one multiply-add: k1 = -black * coef (mod 2^32); the product is exact
         // for v > black (coef < 2^18, host check).  stripes.c:258: only v > black + 64 is touched.
-#ifdef FW_GAIN_MAD
+#if defined(FW_GAIN_HI)
+        // (v - black) * 4 < 2^16 and gain << 14 < 2^32: the high word of their product is ((v - black) * gain) >> 16,
+        // (IMAD.HI's addend is a 64-bit pair, so black is added by the clamp: VIADDMNMX) -- two FMA-pipe instructions
+        // and one ALU-pipe instruction under the predicate
+        if (v > K.thr) {
+            // clamp before adding black: the addition stays out of the IMAD.HI (its addend would need a register pair)
+            return min(__umulhi(v * 4u + K.k4, K.coefh[IDX]), K.white - K.black) + K.black;
+        }
+#elif defined(FW_GAIN_MAD)
         const uint32_t t = min(((v * K.coef[IDX] + K.k1[IDX]) >> 16) + K.black, K.white);
         return v > K.thr ? t : v;
 #else
@@ -182,19 +220,55 @@ __device__ __forceinline__ uint32_t wide_gain(uint32_t v, const WideConst &K)
     return v;
 }
 
+// -DFW_GAIN_X: a corrected sample is left in the HIGH half of its register: X = v * gain + ((black << 16) - black * gain)
+// = (v - black) * gain + (black << 16), so X >> 16 is the reference's ((v - black) * gain >> 16) + black and the clamp to
+// white is min(X, white << 16 | 0xFFFF).  The shift is free: the PRMT that packs two samples into a word picks the
+// high bytes.  One ALU-pipe instruction less per corrected pixel (the shift-and-add LEA.HI).  The host checks that X
+// cannot overflow 32 bits.
+template <int STRIPES, int IDX>
+__host__ __device__ constexpr bool wide_in_hi()
+{
+#ifdef FW_GAIN_X
+    return STRIPES == 1 || (STRIPES == 2 && IDX >= 2);
+#else
+    return false;
+#endif
+}
+template <int STRIPES, int IDX>
+__device__ __forceinline__ uint32_t wide_gain_x(uint32_t v, const WideConst &K)
+{
+    if constexpr (!wide_in_hi<STRIPES, IDX>()) return wide_gain<STRIPES, IDX>(v, K);
+    else {
+        uint32_t x = v << 16;
+        if (v > K.thr) x = min(v * K.coef[IDX] + K.kx[IDX], K.whitex);
+        return x;
+    }
+}
+// low half of the result = sample A, high half = sample B; AH / BH: the sample sits in the high half of its register
+template <bool AH, bool BH>
+__device__ __forceinline__ uint32_t wide_pack(uint32_t a, uint32_t b)
+{
+    return __byte_perm(a, b, (AH ? 0x32u : 0x10u) | ((BH ? 0x76u : 0x54u) << 8));
+}
+
 template <int STRIPES, int C>
 __device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[FW_NW], const uint32_t (&B)[FW_NW], const WideConst &K, WideRow &R)
 {
-    const uint32_t r = wide_px<2 * C>(T, K.shl), g1 = wide_px<2 * C + 1>(T, K.shl);
-    const uint32_t g2 = wide_px<2 * C>(B, K.shl), b = wide_px<2 * C + 1>(B, K.shl);
+    const uint32_t r = wide_px<2 * C>(T, K.shl, K.shr[0]), g1 = wide_px<2 * C + 1>(T, K.shl, K.shr[0]);
+    const uint32_t g2 = wide_px<2 * C>(B, K.shl, K.shr[0]), b = wide_px<2 * C + 1>(B, K.shl, K.shr[0]);
     const int ge = wadd(FW_R2E(g1), FW_R2E(g2)) / 2;
     R.ge[C] = ge;
     R.dr[C] = wsub(FW_R2E(r), ge);
     R.db[C] = wsub(FW_R2E(b), ge);
     R.r[C] = r;
     R.b[C] = b;
+#ifdef FW_PACK_PRMT
+    R.g1s[C] = wide_gain_x<STRIPES, (2 * C + 1) & 7>(g1, K);        // packed next to R by one PRMT in wide_finish_col
+    R.g2[C] = wide_gain_x<STRIPES, (2 * C) & 7>(g2, K);
+#else
     R.g1s[C] = wide_gain<STRIPES, (2 * C + 1) & 7>(g1, K) << 16;
     R.g2[C] = wide_gain<STRIPES, (2 * C) & 7>(g2, K);
+#endif
 }
 
 struct Tri { int lo, mid, hi; };
@@ -211,6 +285,15 @@ __device__ __forceinline__ int wide_med9(const Tri &l, const Tri &m, const Tri &
 {
     return imed3(imax3(l.lo, m.lo, r.lo), imed3(l.mid, m.mid, r.mid, K), imin3(l.hi, m.hi, r.hi), K);
 }
+// -DFW_MIDPAIR: the median of the three column medians as max(min(a, b), min(max(a, b), c)) with (a, b) the pair of
+// columns two neighbouring windows share (columns 2k, 2k + 1 of a lane): 6 two-input min/max per two windows instead
+// of 2 x (2 three-input min/max + 2 three-input adds)
+struct MidPair { int mn, mx; };
+__device__ __forceinline__ MidPair mid_pair(const Tri &a, const Tri &b) { MidPair p; p.mn = min(a.mid, b.mid); p.mx = max(a.mid, b.mid); return p; }
+__device__ __forceinline__ int wide_med9_pair(const Tri &l, const Tri &m, const Tri &r, const MidPair &p, int third, const WideConst &K)
+{
+    return imed3(imax3(l.lo, m.lo, r.lo), max(p.mn, min(p.mx, third)), imin3(l.hi, m.hi, r.hi), K);
+}
 __device__ __forceinline__ Tri tri_shfl_up(const Tri &t)
 {
     Tri o;
@@ -226,12 +309,16 @@ __device__ __forceinline__ Tri tri_shfl_down(const Tri &t)
 
 // ev2raw[min(e, 14 EV - 1)] for e > 0 from the top-octave table.  With t = (14 EV - 1) - e clamped at 0:
 // octave shift 13 - (e >> 15) == t >> 15 and the table index e & (EV - 1) == ~t & (EV - 1).
-__device__ __forceinline__ uint32_t wide_ev2raw(int e)
+__device__ __forceinline__ uint32_t wide_ev2raw(int e, uint32_t m17)
 {
     const int t = max(MLVB_EV_MAX - e, 0);
     uint32_t f = ~(uint32_t)t & (uint32_t)(MLVB_EV_RES - 1);
     asm("" : "+r"(f));          // index * 2 + table base as one IMAD
+#ifdef FW_SHR_HI
+    return (uint32_t)FW_T13(f) >> (__umulhi((uint32_t)t, m17) & 31);      // t >> 15 on the FMA pipe
+#else
     return (uint32_t)FW_T13(f) >> (((uint32_t)t >> 15) & 31);
+#endif
 }
 
 // finish quad column C of the middle row: smoothed R/B (chroma_smooth.c:30-68), stripe gains, packed words
@@ -248,13 +335,21 @@ __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb
     go = go && er > MLVB_EV_RES && eb > MLVB_EV_RES;
     // branch-free: both lookups always run (indices clamped into the table), the result is selected -- no
     // reconvergence barrier between the columns of a lane, so their instruction streams interleave freely
-    const uint32_t nr = wide_ev2raw(er) + K.black, nb = wide_ev2raw(eb) + K.black;
+    const uint32_t nr = wide_ev2raw(er, K.shr[1]) + K.black, nb = wide_ev2raw(eb, K.shr[1]) + K.black;
     r = go ? nr : r;
     b = go ? nb : b;
+#ifdef FW_PACK_PRMT
+    constexpr bool EH = wide_in_hi<STRIPES, (2 * C) & 7>(), OH = wide_in_hi<STRIPES, (2 * C + 1) & 7>();   // even / odd pixel column
+    r = wide_gain_x<STRIPES, (2 * C) & 7>(r, K);
+    b = wide_gain_x<STRIPES, (2 * C + 1) & 7>(b, K);
+    top = wide_pack<EH, OH>(r, M.g1s[C]);           // all four samples are < 2^16
+    bot = wide_pack<EH, OH>(M.g2[C], b);
+#else
     r = wide_gain<STRIPES, (2 * C) & 7>(r, K);
     b = wide_gain<STRIPES, (2 * C + 1) & 7>(b, K);
     top = r | M.g1s[C];
     bot = M.g2[C] | (b << 16);
+#endif
 }
 
 template <int C> struct ColTag { static constexpr int value = C; };
@@ -300,8 +395,15 @@ __device__ __forceinline__ void wide_step(WideRow &N, const WideRow &M, const ui
     uint32_t top[FW_COLS], bot[FW_COLS];
     auto fin_col = [&](auto cc) {
         constexpr int C = decltype(cc)::value;
+#ifdef FW_MIDPAIR
+        // window C holds columns C - 1 .. C + 1 = tr[C .. C + 2]; the shared pair is tr[P], tr[P + 1] with P = (C | 1)
+        constexpr int PP = C | 1, TH = (C & 1) ? C + 2 : C;
+        const int mr = wide_med9_pair(tr[C], tr[C + 1], tr[C + 2], mid_pair(tr[PP], tr[PP + 1]), tr[TH].mid, K);
+        const int mb = wide_med9_pair(tb[C], tb[C + 1], tb[C + 2], mid_pair(tb[PP], tb[PP + 1]), tb[TH].mid, K);
+#else
         const int mr = wide_med9(tr[C], tr[C + 1], tr[C + 2], K);
         const int mb = wide_med9(tb[C], tb[C + 1], tb[C + 2], K);
+#endif
         wide_finish_col<STRIPES, C>(M, mr, mb, ge_thr, edge_first, edge_last, K, top[C], bot[C]);
     };
     do_col(ColTag<0>{});
@@ -377,19 +479,39 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
     WideConst K;
     K.black = (uint32_t)P.black16; K.thr = (uint32_t)P.black16 + 64u; K.white = (uint32_t)P.white16;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { K.coef[i] = P.gain[i].coef; K.k1[i] = P.gain[i].k1; }
+    for (int i = 0; i < 8; i++) { K.coef[i] = P.gain[i].coef; K.k1[i] = P.gain[i].k1; K.coefh[i] = P.coefh[i]; }
+    K.k4 = P.k4; K.whitex = P.whitex;
+#ifdef FW_GAIN_X
+#pragma unroll
+    for (int i = 0; i < 8; i++) { K.coef[i] = P.gainx[i].coef; K.kx[i] = P.gainx[i].kx; }
+#endif
     K.one = P.one; K.mone = P.mone;
 #pragma unroll
     for (int i = 0; i < 4; i++) K.shl[i] = P.shl[i];
+    K.shr[0] = P.shr[0]; K.shr[1] = P.shr[1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = fw_smem + FW_SMEM_R2E + FW_SMEM_T13 + warp * FW_STAGE_PER_WARP;
     const int w = P.w, ph = P.h >> 1;
     const int rowbytes = (w * 7) >> 2;
-    const int total = P.nframes * P.nstrips * P.nseg;
+    // Work is cut two ways.  nseg > 0: frames x strips x nseg equal segments dealt round-robin to the warps.
+    // nseg == 0 (default): the frames x strips x quad-row sequence is cut into one contiguous run of seg_rows rows
+    // per warp, split only where it crosses into the next strip -- every warp gets the same number of rows (no
+    // partial last round) and re-reads halo rows for at most two or three pieces instead of one per segment.
+    const bool runs = P.nseg == 0;
+    const int gw = blockIdx.x * FW_WARPS + warp;
+    const int total = P.nframes * P.nstrips * (runs ? ph : P.nseg);
+    int cur = runs ? min(gw * P.seg_rows, total) : gw;
+    const int end = runs ? min(cur + P.seg_rows, total) : total;
 
-    for (int item = blockIdx.x * FW_WARPS + warp; item < total; item += gridDim.x * FW_WARPS) {
-        const int seg = item % P.nseg;
-        const int t0 = item / P.nseg;
+    while (cur < end) {
+        int t0, qr0, qr1;
+        if (runs) {
+            t0 = cur / ph; qr0 = cur - t0 * ph; qr1 = min(qr0 + (end - cur), ph);
+            cur += qr1 - qr0;
+        } else {
+            t0 = cur / P.nseg; qr0 = (cur - t0 * P.nseg) * P.seg_rows; qr1 = min(qr0 + P.seg_rows, ph);
+            cur += gridDim.x * FW_WARPS;
+        }
         const int strip = t0 % P.nstrips, frame_i = t0 / P.nstrips;
         const uint8_t *frame = P.packed + (size_t)frame_i * P.payload_stride;
         uint16_t *out = P.out + (size_t)frame_i * P.out_stride;
@@ -402,7 +524,6 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
         const int lane_byte = (byte0 - base16) + FW_LANE_BYTES * lane;
         const int lane_off = lane_byte & ~3;
         const uint32_t perm = (lane_byte & 2) ? 0x3254u : 0x1032u;
-        const int qr0 = seg * P.seg_rows, qr1 = min(qr0 + P.seg_rows, ph);
         const unsigned *row_start = P.items ? P.row_start + (size_t)strip * (ph + 1) : nullptr;
         const uint16_t *vals = P.vals + (size_t)frame_i * P.n_entries;
 
