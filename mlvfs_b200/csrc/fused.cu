@@ -441,12 +441,12 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         Q.one = 1; Q.mone = -1;
         Q.shr[0] = 1u << 14; Q.shr[1] = 1u << 17;
         Q.shl[0] = 1u << 14; Q.shl[1] = 1u << 10; Q.shl[2] = 1u << 6; Q.shl[3] = 1u << 2;
-        // one contiguous run of quad rows per warp (nseg = 0); MLVB_WIDE_SEGMENTS=1 keeps the equal-segment split
+        // one contiguous run of a strip's quad rows per warp (nseg = 0); MLVB_WIDE_SEGMENTS=1 keeps the equal-segment split
         const long long all_rows = (long long)nframes * Q.nstrips * (g.h / 2);
         const int nwarps = ctx->sm_count * FW_WARPS;
-        if (all_rows < (1LL << 30) && getenv("MLVB_WIDE_SEGMENTS") == nullptr) {
-            Q.nseg = 0;
-            Q.seg_rows = (int)((all_rows + nwarps - 1) / nwarps);
+        if (all_rows < (1LL << 30) && nwarps >= Q.nstrips && getenv("MLVB_WIDE_SEGMENTS") == nullptr) {
+            Q.nseg = 0;             // the kernel cuts each strip's column of nframes x h/2 rows among that strip's warps
+            Q.seg_rows = 0;
         } else {
             Q.nseg = wide_pick_segments(nframes, Q.nstrips, g.h / 2, nwarps);
             Q.seg_rows = ceil_div(g.h / 2, Q.nseg);

@@ -494,25 +494,37 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
     const int w = P.w, ph = P.h >> 1;
     const int rowbytes = (w * 7) >> 2;
     // Work is cut two ways.  nseg > 0: frames x strips x nseg equal segments dealt round-robin to the warps.
-    // nseg == 0 (default): the frames x strips x quad-row sequence is cut into one contiguous run of seg_rows rows
-    // per warp, split only where it crosses into the next strip -- every warp gets the same number of rows (no
-    // partial last round) and re-reads halo rows for at most two or three pieces instead of one per segment.
+    // nseg == 0 (default): the strips are dealt to the warps round-robin (warp gw owns strip gw % nstrips, so the
+    // warps of a CTA walk neighbouring strips in step and the bytes two strips share meet in L2), and the column
+    // of nframes x ph quad rows of a strip is cut into one contiguous run per warp of that strip, split only at
+    // frame ends -- every warp gets the same number of rows (no partial last round) and re-reads halo rows for two or
+    // three pieces instead of one per segment.
     const bool runs = P.nseg == 0;
-    const int gw = blockIdx.x * FW_WARPS + warp;
-    const int total = P.nframes * P.nstrips * (runs ? ph : P.nseg);
-    int cur = runs ? min(gw * P.seg_rows, total) : gw;
-    const int end = runs ? min(cur + P.seg_rows, total) : total;
+    const int gw = blockIdx.x * FW_WARPS + warp, nwarps = gridDim.x * FW_WARPS;
+    int cur, end, run_strip = 0;
+    if (runs) {
+        run_strip = gw % P.nstrips;
+        const int nw_s = (nwarps - run_strip + P.nstrips - 1) / P.nstrips;      // warps that own this strip
+        const int col_rows = P.nframes * ph;
+        const int per = (col_rows + nw_s - 1) / nw_s;
+        cur = min((gw / P.nstrips) * per, col_rows);
+        end = min(cur + per, col_rows);
+    } else {
+        cur = gw;
+        end = P.nframes * P.nstrips * P.nseg;
+    }
 
     while (cur < end) {
-        int t0, qr0, qr1;
+        int strip, frame_i, qr0, qr1;
         if (runs) {
-            t0 = cur / ph; qr0 = cur - t0 * ph; qr1 = min(qr0 + (end - cur), ph);
+            strip = run_strip; frame_i = cur / ph; qr0 = cur - frame_i * ph; qr1 = min(qr0 + (end - cur), ph);
             cur += qr1 - qr0;
         } else {
-            t0 = cur / P.nseg; qr0 = (cur - t0 * P.nseg) * P.seg_rows; qr1 = min(qr0 + P.seg_rows, ph);
-            cur += gridDim.x * FW_WARPS;
+            const int t0 = cur / P.nseg;
+            qr0 = (cur - t0 * P.nseg) * P.seg_rows; qr1 = min(qr0 + P.seg_rows, ph);
+            strip = t0 % P.nstrips; frame_i = t0 / P.nstrips;
+            cur += nwarps;
         }
-        const int strip = t0 % P.nstrips, frame_i = t0 / P.nstrips;
         const uint8_t *frame = P.packed + (size_t)frame_i * P.payload_stride;
         uint16_t *out = P.out + (size_t)frame_i * P.out_stride;
         const int xl = strip * FW_STRIP_PX - FW_LANE_PX + FW_LANE_PX * lane;   // first pixel column of this lane
