@@ -86,7 +86,7 @@ void release_slot(mlvb_context *ctx, Slot *s)
         s->busy = false;
         s->ticket = -1;
     }
-    ctx->cv.notify_one();
+    ctx->cv.notify_all();            // the condition variable is shared with mlvb_wait's job_done waiters: wake them all
 }
 
 namespace {
@@ -258,6 +258,8 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
     MLVB_CUDA_OK(cudaSetDevice(device));
     mlvb_context *ctx = new mlvb_context();
     ctx->device = device;
+    // a failure below returns from this lambda; the partly built context is torn down instead of leaked
+    const int rc_create = [&]() -> int {
     const size_t n1 = (16384 + MLVB_MAX_BLACK) * sizeof(int), n3 = 24 * MLVB_EV_RES * sizeof(int);
     const size_t n2 = 14 * MLVB_EV_RES * sizeof(uint16_t);
     std::vector<uint16_t> pos(14 * MLVB_EV_RES);
@@ -289,6 +291,12 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
         *s.h_status = 0;
     }
     MLVB_CUDA_OK(cudaStreamCreateWithFlags(&ctx->batch_stream, cudaStreamNonBlocking));
+    return MLVB_OK;
+    }();
+    if (rc_create != MLVB_OK) {
+        mlvb_context_destroy(ctx);
+        return rc_create;
+    }
     *out = ctx;
     return MLVB_OK;
 }
