@@ -72,7 +72,11 @@ constexpr int FW_SMEM_STAGE = FW_WARPS * FW_STAGE_PER_WARP;
 constexpr int FW_SMEM_BYTES = FW_SMEM_R2E + FW_SMEM_T13 + FW_SMEM_STAGE + FW_WARPS * 2 * 8;   // + one mbarrier per warp and slot
 static_assert(FW_COLS == 4 || FW_COLS == 8, "a lane owns 8 or 16 pixels of a row");
 
+#ifdef MLVB_HOST_EMU
+static thread_local uint8_t *fw_smem;              // tests/emu/wide_emu.cpp: the block's "shared memory", one host thread per lane
+#else
 extern __shared__ __align__(16) uint8_t fw_smem[];
+#endif
 #define FW_R2E(v) (reinterpret_cast<const int *>(fw_smem)[(v)])
 #define FW_T13(f) (reinterpret_cast<const uint16_t *>(fw_smem + FW_SMEM_R2E)[(f)])
 
@@ -96,6 +100,13 @@ struct WideParams {
     int nstrips, nseg, seg_rows, nframes;
 };
 
+#ifdef MLVB_HOST_EMU
+// host emulation: the copy happens at once, groups and waits are no-ops (the __syncwarp after the wait orders it)
+inline void cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait1() {}
+inline void cp_async_wait0() {}
+#else
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -127,6 +138,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+#endif
+
 __device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }   // one VIMNMX3
 __device__ __forceinline__ int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
@@ -136,9 +149,13 @@ struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8], coefh[8]
 // keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
 __device__ __forceinline__ int fma_add(int a, int m, int b)
 {
+#ifdef MLVB_HOST_EMU
+    return (int)((unsigned)a * (unsigned)m + (unsigned)b);
+#else
     int d;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
     return d;
+#endif
 }
 // the middle of three = a + b + c - min - max; exact in wrap-around arithmetic (a permutation of the three)
 __device__ __forceinline__ int mid_of(int a, int b, int c, int lo, int hi, const WideConst &K)
