@@ -271,28 +271,11 @@ static int build_patch_plan(const PixelList &list, int w, int h, int crop_x, int
     if (!items.empty()) MLVB_CUDA_OK(cudaMemcpy(plan->d_items, items.data(), items.size() * sizeof(PatchItem), cudaMemcpyHostToDevice));
     MLVB_CUDA_OK(cudaMemcpy(plan->d_bucket_start, start.data(), start.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
 
-    // wide kernel: a strip is a window of 32 lanes starting one lane left of pixel FW_STRIP_PX * s (lanes 0 and 31 are halo)
-    const int wstrips = ceil_div(w, FW_STRIP_PX);
-    std::vector<std::vector<WideItem>> wb((size_t)wstrips * ph);
-    for (size_t m = 0; m < list.host.size(); m++) {
-        const int x = list.host[m].x - crop_x, y = list.host[m].y - crop_y;
-        if (!(x > 2 && x < w - 3 && y > 2 && y < h - 3)) continue;
-        for (int s = 0; s < wstrips; s++) {
-            const int px = x - (FW_STRIP_PX * s - FW_LANE_PX);
-            if (px < 0 || px >= FW_WINDOW_PX) continue;
-            wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)(px | ((y & 1) << 13)), (unsigned short)(y >> 1), (unsigned)m});
-        }
-    }
-    std::vector<unsigned> wstart((size_t)wstrips * (ph + 1), 0);
+    // wide kernel: per strip and quad row (fused_wide.cuh::wide_build_items)
+    std::vector<unsigned> wstart;
     std::vector<WideItem> witems;
-    for (int s = 0; s < wstrips; s++) {
-        for (int q = 0; q < ph; q++) {
-            wstart[(size_t)s * (ph + 1) + q] = (unsigned)witems.size();
-            auto &v = wb[(size_t)s * ph + q];
-            witems.insert(witems.end(), v.begin(), v.end());
-        }
-        wstart[(size_t)s * (ph + 1) + ph] = (unsigned)witems.size();
-    }
+    wide_build_items(list.host.size(), [&](size_t m, int &x, int &y) { x = list.host[m].x - crop_x; y = list.host[m].y - crop_y; },
+                     w, h, witems, wstart);
     MLVB_CUDA_OK(cudaMalloc(&plan->d_wide_items, std::max<size_t>(witems.size(), 1) * sizeof(WideItem)));
     MLVB_CUDA_OK(cudaMalloc(&plan->d_wide_row_start, wstart.size() * sizeof(unsigned)));
     if (!witems.empty()) MLVB_CUDA_OK(cudaMemcpy(plan->d_wide_items, witems.data(), witems.size() * sizeof(WideItem), cudaMemcpyHostToDevice));

@@ -22,6 +22,8 @@
 // (cs.c:49-84, chroma_smooth.c:22-71, stripes.c:250-266); results are bit-identical.
 #pragma once
 
+#include <vector>
+
 #ifdef FW_PLAIN_STORES
 #define FW_STORE(p, v) (*(p) = (v))
 #else
@@ -80,7 +82,38 @@ extern __shared__ __align__(16) uint8_t fw_smem[];
 #define FW_R2E(v) (reinterpret_cast<const int *>(fw_smem)[(v)])
 #define FW_T13(f) (reinterpret_cast<const uint16_t *>(fw_smem + FW_SMEM_R2E)[(f)])
 
-struct WideItem { unsigned short px_sub; unsigned short qrow; unsigned entry; };   // px_sub: pixel column inside the strip's window | sub << 12
+struct WideItem { unsigned short px_sub; unsigned short qrow; unsigned entry; };   // px_sub: pixel column inside the strip's window | (y & 1) << 13
+
+// Host: the kernel's patch lists for n repaired pixels (list order; get(m, x, y) gives entry m's position inside the
+// frame).  A strip is a window of 32 lanes starting one lane left of pixel FW_STRIP_PX * s (lanes 0 and 31 are halo), so
+// an entry near a seam is listed for both strips.  items are grouped by strip, then quad row; row_start[s * (ph + 1) + q]
+// is the first item of strip s at quad row q or below it.  Only interior entries are repaired (cs.c:317).
+template <class GetXY>
+inline void wide_build_items(size_t n, GetXY get, int w, int h, std::vector<WideItem> &items, std::vector<unsigned> &row_start)
+{
+    const int ph = h / 2, wstrips = (w + FW_STRIP_PX - 1) / FW_STRIP_PX;
+    std::vector<std::vector<WideItem>> wb((size_t)wstrips * ph);
+    for (size_t m = 0; m < n; m++) {
+        int x, y;
+        get(m, x, y);
+        if (!(x > 2 && x < w - 3 && y > 2 && y < h - 3)) continue;
+        for (int s = 0; s < wstrips; s++) {
+            const int px = x - (FW_STRIP_PX * s - FW_LANE_PX);
+            if (px < 0 || px >= FW_WINDOW_PX) continue;
+            wb[(size_t)s * ph + (y >> 1)].push_back(WideItem{(unsigned short)(px | ((y & 1) << 13)), (unsigned short)(y >> 1), (unsigned)m});
+        }
+    }
+    row_start.assign((size_t)wstrips * (ph + 1), 0);
+    items.clear();
+    for (int s = 0; s < wstrips; s++) {
+        for (int q = 0; q < ph; q++) {
+            row_start[(size_t)s * (ph + 1) + q] = (unsigned)items.size();
+            auto &v = wb[(size_t)s * ph + q];
+            items.insert(items.end(), v.begin(), v.end());
+        }
+        row_start[(size_t)s * (ph + 1) + ph] = (unsigned)items.size();
+    }
+}
 
 struct WideParams {
     const uint8_t *packed; size_t payload_stride;

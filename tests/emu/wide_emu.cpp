@@ -4,7 +4,8 @@
 // warp, a std::barrier for __syncwarp / __syncthreads, an exchange array for the shuffles.  The kernel source is
 // compiled unchanged (-DMLVB_HOST_EMU only swaps the PTX of the async copies for memcpy and the extern shared array
 // for a pointer), with one warp per block (-DFW_WARPS_CFG=1); the blocks of the grid run one after the other.
-// Bad-pixel patches are not emulated (their lists are built by device code); the GPU tests cover them.
+// Bad-pixel patches: the lists come from the library's own host helper (wide_build_items); the repaired values, which the
+// library computes on the device (patch_values_kernel), are handed in by the test (the oracle's).
 // Built by tests/test_wide_emu.py with  g++ -O1 -std=c++20 -shared -fPIC -pthread.
 #include <stddef.h>
 #include <stdint.h>
@@ -85,11 +86,12 @@ static_assert(FW_WARPS == 1, "the emulation runs one warp per block");
 
 // One launch of fused3_wide_kernel on `grid` blocks of one warp.  Tables as the library uploads them: raw2ev indexed by
 // raw value for this black level (16384 entries), ev2raw13 = ev2raw[13 EV .. 14 EV) as uint16.  coef == NULL: no stripe
-// correction.  segments != 0: the equal-segment split with that many segments per strip instead of the per-strip runs.
+// correction.  bad_xy == NULL / n_bad == 0: no repaired pixels.  segments != 0: the equal-segment split with that many
+// segments per strip instead of the per-strip runs.
 // Returns the STRIPES variant that ran, or < 0 when the frame shape is not eligible (the checks of fused.cu).
 extern "C" int wide_emu_run(const uint8_t *packed, size_t payload_stride, uint16_t *out, size_t out_stride_px, int w, int h,
                             int black, int white, int nframes, const int *raw2ev, const uint16_t *ev2raw13, const int *coef,
-                            int grid, int segments)
+                            int grid, int segments, const int *bad_xy, int n_bad, const uint16_t *bad_vals)
 {
     if ((w % 64) != 0 || ((uintptr_t)out % 16) != 0 || (out_stride_px % 8) != 0 || (payload_stride % 16) != 0 || (h & 1)) return -1;
     WideParams Q;
@@ -116,6 +118,14 @@ extern "C" int wide_emu_run(const uint8_t *packed, size_t payload_stride, uint16
     Q.shl[0] = 1u << 14; Q.shl[1] = 1u << 10; Q.shl[2] = 1u << 6; Q.shl[3] = 1u << 2;
     if (segments > 0) { Q.nseg = segments; Q.seg_rows = (h / 2 + segments - 1) / segments; }
     if (grid < Q.nstrips && segments <= 0) return -3;
+    // repaired pixels: entry m at (bad_xy[2m], bad_xy[2m + 1]) takes bad_vals[frame * n_bad + m]
+    std::vector<WideItem> items;
+    std::vector<unsigned> row_start;
+    if (n_bad > 0) {
+        wide_build_items((size_t)n_bad, [&](size_t m, int &x, int &y) { x = bad_xy[2 * m]; y = bad_xy[2 * m + 1]; }, w, h, items, row_start);
+        items.push_back(WideItem{0, 0xFFFF, 0});                       // never read (the kernel stops at row_start); keeps data() non-null
+        Q.items = items.data(); Q.row_start = row_start.data(); Q.vals = bad_vals; Q.n_entries = (unsigned)n_bad;
+    }
 
     std::vector<uint8_t> smem(FW_SMEM_BYTES + 64);
     uint8_t *sm = smem.data();

@@ -4,8 +4,9 @@ std::thread per lane, a barrier for __syncwarp, an exchange array for the shuffl
 chain, bit for bit.  This pins, without a GPU: the work split (per-strip runs cut at frame ends, and the older equal
 segments), the row staging and the byte-permute extraction, the sorted-column medians with the shared pair, the
 octave lookup of ev2raw, the stripe gain kept in the high half and the PRMT packing, image borders and strip seams.
-tests/test_gpu_single_iso.py -k wide then confirms the same source on the device (with bad-pixel patches, which the
-emulation leaves out)."""
+Bad-pixel patches: the item lists come from the library's host helper (wide_build_items), the repaired values -- computed by
+a separate device kernel in the library -- from the oracle.  tests/test_gpu_single_iso.py -k wide then confirms the
+same source on the device."""
 import ctypes as C
 import os
 import subprocess
@@ -30,7 +31,7 @@ def emu(request, tmp_path_factory, oracle):
                           BUILDS[request.param] + ["-o", so, os.path.join(ROOT, "tests", "emu", "wide_emu.cpp")])
     lib = C.CDLL(so)
     lib.wide_emu_run.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     olib = oracle.load_oracle()
     olib.orc_raw2ev.restype = C.POINTER(C.c_int)
     olib.orc_raw2ev.argtypes = [C.c_int]
@@ -38,7 +39,7 @@ def emu(request, tmp_path_factory, oracle):
     ev2raw = np.ctypeslib.as_array(olib.orc_ev2raw(), shape=(14 * EV,))
     top = np.ascontiguousarray(ev2raw[13 * EV:], dtype=np.uint16)
 
-    def run(frames, black, white, coef, grid, segments=0):
+    def run(frames, black, white, coef, grid, segments=0, bad_xy=None, bad_vals=None):
         n = len(frames)
         h, w = frames[0].shape
         packed = np.stack([synth.pack_bits(f) for f in frames]).view(np.uint8)
@@ -48,8 +49,12 @@ def emu(request, tmp_path_factory, oracle):
         out = np.full((n, h, w), 0xDEAD, np.uint16)
         assert out.ctypes.data % 16 == 0
         c8 = None if coef is None else np.ascontiguousarray(coef, np.int32)
+        nb = 0 if bad_xy is None else len(bad_xy)
+        xy = None if nb == 0 else np.ascontiguousarray(bad_xy, np.int32)
+        bv = None if nb == 0 else np.ascontiguousarray(bad_vals, np.uint16)
         rc = lib.wide_emu_run(packed.ctypes.data, stride, out.ctypes.data, h * w, w, h, black, white, n, raw2ev.ctypes.data,
-                              top.ctypes.data, None if c8 is None else c8.ctypes.data, grid, segments)
+                              top.ctypes.data, None if c8 is None else c8.ctypes.data, grid, segments,
+                              None if nb == 0 else xy.ctypes.data, nb, None if nb == 0 else bv.ctypes.data)
         return rc, out
 
     return run
@@ -109,3 +114,25 @@ def test_ineligible_shapes_are_refused(emu):
     assert emu(fr, 2048, 15000, None, 4)[0] == -1                       # width not a multiple of 64
     fr = [np.full((8, 128), 3000, np.uint16)]
     assert emu(fr, 2048, 15000, [65536, 65536, 1 << 18, 65536, 65536, 65536, 65536, 65536], 4)[0] == -2
+
+
+@pytest.mark.parametrize("w,h,n,grid,segments,density", [(640, 48, 3, 7, 0, 2e-3), (640, 48, 2, 5, 2, 2e-3), (256, 40, 2, 11, 0, 2e-2)])
+def test_repaired_pixels_are_patched_into_the_staged_rows(emu, oracle, w, h, n, grid, segments, density):
+    """--bad-pix: the repaired samples are written into the staged stream bytes before extraction, in both strips of a
+    seam, at the right row of a run whatever piece of the column a warp owns (dense lists: many rows carry patches)."""
+    black, white = 2048, 15000
+    frames = [synth.make_frame(w, h, i, hot_cold=True, stripes=True, bad_density=density) for i in range(n)]
+    plist = oracle.badpix_detect(frames[0], black, 0)
+    assert len(plist) >= 8
+    fixed = [oracle.badpix_apply(f, black, plist) for f in frames]
+    vals = np.stack([f[plist[:, 1], plist[:, 0]] for f in fixed])
+    assert any((fixed[i] != frames[i]).any() for i in range(n))
+    want, state = oracle.single_iso_chain(frames, black, white, h * w * 14 // 8, chroma_smooth_method=3, fix_bad_pixels=1,
+                                          fix_stripes=1)
+    assert np.array_equal(state["badpix"], plist)
+    needed, coef = state["stripes"]
+    assert needed
+    rc, got = emu(frames, black, white, coef, grid, segments, bad_xy=plist, bad_vals=vals)
+    assert rc == 2
+    for i in range(n):
+        assert np.array_equal(got[i], want[i]), (i, int(np.count_nonzero(got[i] != want[i])))
