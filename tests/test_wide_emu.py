@@ -21,7 +21,8 @@ EV = 32768
 
 
 # the shipped defaults, and the plain forms they replaced (every -DFW_NO_* switch of fused_wide.cuh)
-BUILDS = {"default": [], "plain": ["-DFW_NO_MIDPAIR", "-DFW_NO_PACK_PRMT", "-DFW_NO_EXTRACT_SHL", "-DFW_NO_GAIN_X"]}
+BUILDS = {"default": [], "plain": ["-DFW_NO_MIDPAIR", "-DFW_NO_PACK_PRMT", "-DFW_NO_EXTRACT_SHL", "-DFW_NO_GAIN_X"],
+          "cols8": ["-DFW_COLS_CFG=8"]}         # 8 quad columns per lane (480-pixel strips): built, measured slower, kept honest
 
 
 @pytest.fixture(scope="module", params=sorted(BUILDS))
