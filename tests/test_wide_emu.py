@@ -137,3 +137,30 @@ def test_repaired_pixels_are_patched_into_the_staged_rows(emu, oracle, w, h, n, 
     assert rc == 2
     for i in range(n):
         assert np.array_equal(got[i], want[i]), (i, int(np.count_nonzero(got[i] != want[i])))
+
+
+def test_random_shapes_grids_and_splits(emu, oracle):
+    """Seeded sweep over widths, heights, frame counts, grid sizes (down to one warp per strip) and both work splits,
+    with repaired pixels: every output pixel is written exactly once and equals the oracle's."""
+    rng = np.random.default_rng(20261017)
+    black, white = 2048, 15000
+    for case in range(6):
+        w = int(rng.choice([128, 192, 256, 320, 512, 704]))
+        h = 2 * int(rng.integers(8, 26))
+        n = int(rng.integers(1, 5))
+        nstrips = -(-w // 240)
+        grid = int(rng.integers(nstrips, 4 * nstrips + 6))
+        segments = int(rng.integers(1, 4)) if case % 3 == 2 else 0
+        frames = [synth.make_frame(w, h, 10 * case + i, hot_cold=True, stripes=True, bad_density=3e-3) for i in range(n)]
+        want, state = oracle.single_iso_chain(frames, black, white, h * w * 14 // 8, chroma_smooth_method=3, fix_bad_pixels=1,
+                                              fix_stripes=1)
+        plist = state["badpix"]
+        needed, coef = state["stripes"]
+        vals = np.stack([oracle.badpix_apply(f, black, plist)[plist[:, 1], plist[:, 0]] for f in frames]) if len(plist) else None
+        rc, got = emu(frames, black, white, coef if needed else None, grid, segments,
+                      bad_xy=plist if len(plist) else None, bad_vals=vals)
+        assert rc >= 0, (case, w, h, n, grid, segments)
+        if not needed:                                     # coefficients inside 0.998 .. 1.002: stripes.c leaves the frame alone
+            want = [oracle.chroma_smooth(oracle.badpix_apply(f, black, plist), black, 3) for f in frames]
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), (case, w, h, n, grid, segments, i, int(np.count_nonzero(got[i] != want[i])))
