@@ -83,6 +83,10 @@ int  mlvb_device_count(void);
  * main.c:931 and resource_manager.c:143-146; pageable buffers also work, through a staging copy). */
 void *mlvb_host_alloc(size_t bytes);
 void  mlvb_host_free(void *p);
+/* mlvb_host_free keeps blocks for reuse (a pool of up to $MLVB_PIN_POOL_MB MiB, default 4096: page-locking is a
+ * millisecond-scale driver call and the frame cache needs a frame-sized buffer per frame); this returns the idle
+ * blocks to the system. */
+void  mlvb_host_pool_trim(void);
 
 /* Build one frame.  `payload` is the VIDF payload exactly as stored in the MLV (packed bits, or
  * uint32 size + LJ92 stream when file_hdr.videoClass has MLVB_VIDEO_CLASS_FLAG_LJ92);

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <thread>
 #include <vector>
 
@@ -14,8 +15,35 @@ namespace {
 
 int round_up(size_t v, size_t a, size_t *out) { *out = (v + a - 1) / a * a; return 0; }
 
-bool is_pinned(const void *p)
+// Pinned host memory handed out by mlvb_host_alloc: a process-wide pool.  Freed blocks are kept (up to
+// $MLVB_PIN_POOL_MB, default 4096) and handed out again, because cudaHostAlloc / cudaFreeHost are millisecond-scale,
+// driver-serialised calls and the frame builder needs a frame-sized buffer per frame (the reference's two
+// malloc()s at main.c:931-933).  The table also answers "is this caller buffer pinned?" without a driver call.
+struct PinPool {
+    std::mutex mu;
+    std::map<uintptr_t, size_t> blocks;                  // every block we own (in use or free): base -> bytes
+    std::multimap<size_t, void *> free_blocks;           // bytes -> base
+    size_t free_bytes = 0, cap_bytes = 0;
+    bool cap_read = false;
+};
+PinPool &pin_pool() { static PinPool *p = new PinPool(); return *p; }     // leaked on purpose: outlives static destructors
+
+constexpr size_t PIN_GRANULE = 64 * 1024;
+
+bool in_pin_pool(const void *p, size_t bytes)
 {
+    PinPool &P = pin_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.blocks.upper_bound((uintptr_t)p);
+    if (it == P.blocks.begin()) return false;
+    --it;
+    return (uintptr_t)p + bytes <= it->first + it->second;
+}
+
+// caller buffers that did not come from mlvb_host_alloc (torch pinned tensors, cudaHostRegister) cost one driver query
+bool host_is_pinned(const void *p, size_t bytes)
+{
+    if (in_pin_pool(p, bytes)) return true;
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
@@ -355,12 +383,64 @@ mlvb_context *mlvb_default_context(void)
 
 void *mlvb_host_alloc(size_t bytes)
 {
+    const size_t want = (std::max<size_t>(bytes, 1) + PIN_GRANULE - 1) / PIN_GRANULE * PIN_GRANULE;
+    PinPool &P = pin_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto it = P.free_blocks.lower_bound(want);
+        if (it != P.free_blocks.end() && it->first <= want + want / 4) {          // close enough in size: reuse
+            void *p = it->second;
+            P.free_bytes -= it->first;
+            P.free_blocks.erase(it);
+            return p;
+        }
+    }
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        mlvb_host_pool_trim();                                                     // give the cached blocks back and retry once
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.blocks[(uintptr_t)p] = want;
     return p;
 }
 
-void mlvb_host_free(void *p) { if (p) cudaFreeHost(p); }
+void mlvb_host_free(void *p)
+{
+    if (!p) return;
+    PinPool &P = pin_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        if (!P.cap_read) {
+            const char *mb = getenv("MLVB_PIN_POOL_MB");
+            P.cap_bytes = (size_t)(mb ? std::max(atol(mb), 0L) : 4096) << 20;
+            P.cap_read = true;
+        }
+        auto it = P.blocks.find((uintptr_t)p);
+        if (it == P.blocks.end()) { fprintf(stderr, "libmlvfs_b200: mlvb_host_free(%p): not from mlvb_host_alloc\n", p); return; }
+        if (P.free_bytes + it->second <= P.cap_bytes) {
+            P.free_blocks.emplace(it->second, p);
+            P.free_bytes += it->second;
+            return;
+        }
+        P.blocks.erase(it);
+    }
+    cudaFreeHost(p);
+}
+
+void mlvb_host_pool_trim(void)
+{
+    PinPool &P = pin_pool();
+    std::vector<void *> victims;
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        for (auto &kv : P.free_blocks) { victims.push_back(kv.second); P.blocks.erase((uintptr_t)kv.second); }
+        P.free_blocks.clear();
+        P.free_bytes = 0;
+    }
+    for (void *v : victims) cudaFreeHost(v);
+}
 
 void mlvb_reset_clip_state(mlvb_context *ctx)
 {
@@ -455,7 +535,7 @@ static int run_slot_job(mlvb_context *ctx, Slot *s, const struct frame_headers *
         rc = MLVB_ERR_CUDA;
     if (rc) { cudaStreamSynchronize(s->stream); return rc; }
     s->out_bytes = frame_bytes;
-    const bool dst_pinned = is_pinned(dst);
+    const bool dst_pinned = host_is_pinned(dst, frame_bytes);
     s->user_dst = dst_pinned ? nullptr : dst;
     if (cudaMemcpyAsync(dst_pinned ? (void *)dst : (void *)s->h_out, s->d_b, frame_bytes, cudaMemcpyDeviceToHost,
                         s->stream) != cudaSuccess ||
@@ -498,15 +578,45 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
     const FrameGeom g = geom_from_headers(hdr);
     const size_t frame_bytes = g.npix * 2;
 
+    // Legacy LZMA clips (main.c:598-616): the range coder is serial, so the payload is expanded on the host -- straight
+    // into the slot's pinned stage -- and the frame continues as an uncompressed one (unpack and everything after it on
+    // the GPU), exactly where the reference calls dng_get_image_data on LzmaUncompress's output.
+    struct frame_headers lzma_hdr;
+    size_t lzma_out = 0;
+    if (hdr->file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LZMA) {
+        if (payload_bytes < 4 + 5 + 5) return MLVB_ERR_ARG;
+        uint32_t stored;
+        memcpy(&stored, payload, 4);
+        lzma_out = stored;
+        if (lzma_out < mlvb_packed_bytes((uint32_t)g.npix, g.bpp)) {
+            fprintf(stderr, "libmlvfs_b200: LZMA frame expands to %zu bytes, the frame needs %zu\n", lzma_out,
+                    mlvb_packed_bytes((uint32_t)g.npix, g.bpp));
+            return MLVB_ERR_ARG;
+        }
+        lzma_hdr = *hdr;
+        lzma_hdr.file_hdr.videoClass &= ~MLVB_VIDEO_CLASS_FLAG_LZMA;
+    }
+
     Slot *s = acquire_slot(ctx);
     auto fail = [&](int rc) -> mlvb_ticket { release_slot(ctx, s); return rc; };
-    int rc = slot_reserve(*s, payload_bytes, frame_bytes);
+    int rc = slot_reserve(*s, std::max(payload_bytes, lzma_out), frame_bytes);
     if (rc) return fail(rc);
     s->async = false; s->job_done = false; s->job_rc = MLVB_OK;
 
     // H2D: straight from the caller's buffer when it is pinned, else through the slot's pinned stage
     const void *src = payload;
-    if (!is_pinned(payload)) { memcpy(s->h_in, payload, payload_bytes); src = s->h_in; }
+    if (lzma_out) {
+        const uint8_t *in = (const uint8_t *)payload;
+        size_t produced = lzma_out;
+        if (mlvb_lzma_decode(s->h_in, &produced, in + 9, payload_bytes - 9, in + 4) != MLVB_OK) {
+            fprintf(stderr, "libmlvfs_b200: LZMA Failed!\n");                             // main.c:612
+            return fail(MLVB_ERR_ARG);
+        }
+        if (produced < lzma_out) memset(s->h_in + produced, 0, lzma_out - produced);      // stream ended early (end marker)
+        src = s->h_in;
+        payload_bytes = lzma_out;
+        hdr = &lzma_hdr;
+    } else if (!host_is_pinned(payload, payload_bytes)) { memcpy(s->h_in, payload, payload_bytes); src = s->h_in; }
 
     // The full dual-ISO pipeline waits on the host several times per frame (statistics read-backs): once the clip's
     // per-clip state exists (its first frame went through synchronously, below), such frames go to the submit workers

@@ -76,32 +76,69 @@ PixelList::~PixelList()
     if (d_long_rows) cudaFree(d_long_rows);
 }
 
-int PixelList::upload()
+int PixelList::upload(const FrameGeom *fg)
 {
-    const size_t n = host.size();
     level_start.assign(2, 0);
     nlevels = 0;
+    has_wrapped = false;
+    if (fg) {
+        // cs.c:462-501: keep the entries that act in this frame, in file order
+        const long long w = fg->w, h = fg->h;
+        std::vector<PixelXY> kept;
+        kept.reserve(host.size());
+        for (const PixelXY &p : host) {
+            const long long x = (long long)p.x - fg->crop_x, y = (long long)p.y - fg->crop_y, i = x + y * w;
+            const bool interior = x > 2 && x < w - 3 && y > 2 && y < h - 3;
+            if (!interior && !(i > 0 && i < w * h)) continue;
+            if (!interior) {
+                const bool hedge = (x >= w - 3 && x < w) || (x >= 0 && x <= 3);
+                const bool vedge = (y >= h - 3 && y < h) || (y >= 0 && y <= 3);
+                if (!hedge && !vedge) continue;                    // x outside the frame on an interior row: no rule applies
+                if (x < 0 || x >= w) has_wrapped = true;
+            }
+            kept.push_back(p);
+        }
+        host.swap(kept);
+    }
+    const size_t n = host.size();
     if (n == 0) return MLVB_OK;
-    // level(m) = 1 + max level over earlier entries in the +-3 cross stencil (and at the same site)
+    // level(m) = 1 + max level over earlier entries in the +-3 cross stencil (and at the same site).  The stencil is
+    // symmetric, so an entry also waits for earlier entries that READ its site.
     std::vector<unsigned> level(n, 0);
     std::unordered_map<uint64_t, unsigned> last_at;       // site -> latest entry index so far
     last_at.reserve(n * 2);
     auto key = [](int x, int y) { return ((uint64_t)(uint32_t)x << 32) | (uint32_t)y; };
     unsigned maxlevel = 0;
     for (size_t m = 0; m < n; m++) {
-        const int x = host[m].x, y = host[m].y;
         unsigned lv = 0;
-        for (int d = -3; d <= 3; d++) {
-            auto it = last_at.find(key(x + d, y));
-            if (it != last_at.end()) lv = std::max(lv, level[it->second] + 1);
-            if (d != 0) {
-                it = last_at.find(key(x, y + d));
+        if (fg) {
+            // sites are linear indices: every rule reads i +- 1..3 and / or i +- (1..3) * w (interpolate_* and the
+            // +-2 copies), also when the index wrapped into a neighbouring row
+            const long long w = fg->w;
+            const long long i = ((long long)host[m].x - fg->crop_x) + ((long long)host[m].y - fg->crop_y) * w;
+            for (int d = -3; d <= 3; d++) {
+                auto it = last_at.find((uint64_t)(i + d));
                 if (it != last_at.end()) lv = std::max(lv, level[it->second] + 1);
+                if (d != 0) {
+                    it = last_at.find((uint64_t)(i + d * w));
+                    if (it != last_at.end()) lv = std::max(lv, level[it->second] + 1);
+                }
             }
+            last_at[(uint64_t)i] = (unsigned)m;
+        } else {
+            const int x = host[m].x, y = host[m].y;
+            for (int d = -3; d <= 3; d++) {
+                auto it = last_at.find(key(x + d, y));
+                if (it != last_at.end()) lv = std::max(lv, level[it->second] + 1);
+                if (d != 0) {
+                    it = last_at.find(key(x, y + d));
+                    if (it != last_at.end()) lv = std::max(lv, level[it->second] + 1);
+                }
+            }
+            last_at[key(x, y)] = (unsigned)m;
         }
         level[m] = lv;
         maxlevel = std::max(maxlevel, lv);
-        last_at[key(x, y)] = (unsigned)m;
     }
     nlevels = maxlevel + 1;
     level_start.assign(nlevels + 1, 0);
@@ -160,13 +197,13 @@ int apply_pixel_list(mlvb_context *ctx, const PixelList &L, uint16_t *d_img, con
                      int dual_iso, int edge_rules, cudaStream_t st)
 {
     if (!L.nlevels) return MLVB_OK;
-    if (dual_iso) {
+    if (dual_iso && !L.has_wrapped) {
         ctx->launches += (L.nseg > 0) + (L.nlong > 0);
         return launch_pixel_fix_rows(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, edge_rules, L.d_by_row,
                                      L.d_seg_start, L.nseg, L.d_long_rows, L.nlong, ctx->luts, ctx->ev2raw_octaves_ok, ctx->sm_count, st);
     }
     ctx->launches += 1 + (L.nlevels > 1);
-    return launch_pixel_fix(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, 0, edge_rules, L.d_by_level,
+    return launch_pixel_fix(d_img, g.w, g.h, frame_stride, nframes, g.black, g.crop_x, g.crop_y, dual_iso, edge_rules, L.d_by_level,
                             L.d_level_start, L.level_start.data(), L.nlevels, ctx->luts, st);
 }
 
@@ -257,33 +294,41 @@ int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const 
 }
 
 // cs.c:355-438: "<cameraModel hex>_<raw width>x<raw height>.fpm" in the current directory, one "x y" per line
-int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, std::shared_ptr<PixelList> *out)
+int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, std::shared_ptr<PixelList> *out)
 {
     const uint32_t cam = hdr->idnt_hdr.cameraModel;
     const int rw = hdr->rawi_hdr.raw_info.width, rh = hdr->rawi_hdr.raw_info.height;
+    FocusPixelMap *fm = nullptr;
     for (auto &m : ctx->focus_maps)
-        if (m.camera == cam && m.rawi_width == rw && m.rawi_height == rh) { *out = m.list; return MLVB_OK; }
-    FocusPixelMap fm;
-    fm.camera = cam; fm.rawi_width = rw; fm.rawi_height = rh;
-    char name[1024];
-    snprintf(name, sizeof(name), "%x_%ix%i.fpm", cam, rw, rh);
-    FILE *f = fopen(name, "r");
-    if (f) {
-        auto list = std::make_shared<PixelList>();
-        int x = 0, y = 0, ret;
-        while ((ret = fscanf(f, "%i %i", &x, &y)) != EOF) {
-            if (ret == 2) list->host.push_back(PixelXY{x, y});
-            else break;
+        if (m.camera == cam && m.rawi_width == rw && m.rawi_height == rh) { fm = &m; break; }
+    if (!fm) {
+        FocusPixelMap nm;
+        nm.camera = cam; nm.rawi_width = rw; nm.rawi_height = rh;
+        char name[1024];
+        snprintf(name, sizeof(name), "%x_%ix%i.fpm", cam, rw, rh);
+        FILE *f = fopen(name, "r");
+        if (f) {
+            int x = 0, y = 0, ret;
+            while ((ret = fscanf(f, "%i %i", &x, &y)) != EOF) {
+                if (ret == 2) nm.entries.push_back(PixelXY{x, y});
+                else break;
+            }
+            fclose(f);
         }
-        fclose(f);
-        if (!list->host.empty()) {
-            int rc = list->upload();
-            if (rc) return rc;
-            fm.list = list;
-        }
+        ctx->focus_maps.push_back(std::move(nm));
+        fm = &ctx->focus_maps.back();
     }
-    ctx->focus_maps.push_back(fm);
-    *out = fm.list;
+    out->reset();
+    if (fm->entries.empty()) return MLVB_OK;
+    for (auto &s : fm->schedules)
+        if (s.w == g.w && s.h == g.h && s.crop_x == g.crop_x && s.crop_y == g.crop_y) { *out = s.list; return MLVB_OK; }
+    auto list = std::make_shared<PixelList>();
+    list->host = fm->entries;
+    int rc = list->upload(&g);
+    if (rc) return rc;
+    if (fm->schedules.size() >= 8) fm->schedules.erase(fm->schedules.begin());   // panning clips: keep the latest offsets
+    fm->schedules.push_back({g.w, g.h, g.crop_x, g.crop_y, list});
+    *out = list;
     return MLVB_OK;
 }
 
@@ -355,7 +400,7 @@ int run_single_iso_chain(mlvb_context *ctx, const struct frame_headers *hdr, con
     std::shared_ptr<PixelList> focus, bad;
     if (!skip_pixfix) {
         std::lock_guard<std::mutex> lk(ctx->clip_mu);
-        rc = get_focus_pixel_map(ctx, hdr, &focus);
+        rc = get_focus_pixel_map(ctx, hdr, g, &focus);
         if (rc) return rc;
     }
     if (focus && focus->nlevels && g.black <= MLVB_MAX_BLACK) {

@@ -25,6 +25,7 @@ struct GlibcRand {
     int next();
 };
 
+struct FrameGeom;
 // A pixel list with its level schedule, resident on the device (bad-pixel map, focus-pixel map).
 struct PixelList {
     std::vector<PixelXY> host;             // original (reference) order
@@ -39,8 +40,14 @@ struct PixelList {
     unsigned nlong = 0;
     std::vector<unsigned> level_start;     // nlevels + 1 entries
     unsigned nlevels = 0;
+    // focus maps only: some entry lies outside [0, w) in x but still acts, on the wrapped linear index
+    // i = x + y * w (cs.c:467, 479-500).  Such a write leaves its row: the row-wise dual-ISO walk is not used then.
+    bool has_wrapped = false;
     ~PixelList();
-    int upload();                          // builds the level schedule from `host`
+    // Builds the level schedule from `host`.  Without a geometry (bad-pixel maps: interior entries only) the
+    // +-3 cross stencil in map coordinates; with one (focus maps, whose border rules depend on where an entry
+    // falls in the frame) entries that do nothing in this frame are dropped and levels come from linear indices.
+    int upload(const struct FrameGeom *focus_geom = nullptr);
 };
 
 struct BadPixelMap {                       // reference cs.c:186-193 + the 8-slot ring cs.c:215-217
@@ -54,7 +61,11 @@ struct BadPixelMap {                       // reference cs.c:186-193 + the 8-slo
 struct FocusPixelMap {                     // reference cs.c:176-184
     uint32_t camera = 0;
     int rawi_width = 0, rawi_height = 0;
-    std::shared_ptr<PixelList> list;       // null or empty: no map file for this camera/size
+    std::vector<PixelXY> entries;          // file order; empty: no map file for this camera/size
+    // one schedule per frame geometry the map has been applied to (the border rules of cs.c:479-500 and the
+    // wrapped linear indices depend on width, height and crop offsets)
+    struct Schedule { int w, h, crop_x, crop_y; std::shared_ptr<PixelList> list; };
+    std::vector<Schedule> schedules;
 };
 
 struct StripesState {                      // reference stripes.h:30-36, keyed by MLV path (stripes.c:29-38)
@@ -205,7 +216,7 @@ int run_deflicker(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, 
 // per-clip state accessors (call with ctx->clip_mu held)
 int get_bad_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, int aggressive,
                       const uint16_t *d_img, cudaStream_t st, std::shared_ptr<PixelList> *out);
-int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, std::shared_ptr<PixelList> *out);
+int get_focus_pixel_map(mlvb_context *ctx, const struct frame_headers *hdr, const FrameGeom &g, std::shared_ptr<PixelList> *out);
 int compute_stripes(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, cudaStream_t st, StripeCoef *out);
 
 // apply a pixel list to device frames: level schedule for the 2-D interpolator, independent row segments for

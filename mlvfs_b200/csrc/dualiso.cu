@@ -969,7 +969,7 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
     std::shared_ptr<PixelList> focus, bad;
     {
         std::lock_guard<std::mutex> lk(ctx->clip_mu);
-        rc = get_focus_pixel_map(ctx, hdr, &focus);
+        rc = get_focus_pixel_map(ctx, hdr, g, &focus);
         if (rc) return rc;
     }
     if (focus && focus->nlevels) {

@@ -331,7 +331,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         // focus-pixel maps are chains of neighbouring entries: general path
         for (auto &m : ctx->focus_maps)
             if (m.camera == hdr->idnt_hdr.cameraModel && m.rawi_width == hdr->rawi_hdr.raw_info.width &&
-                m.rawi_height == hdr->rawi_hdr.raw_info.height && m.list && m.list->nlevels) return 1;
+                m.rawi_height == hdr->rawi_hdr.raw_info.height && !m.entries.empty()) return 1;
         bool focus_known = false;
         for (auto &m : ctx->focus_maps)
             focus_known |= (m.camera == hdr->idnt_hdr.cameraModel && m.rawi_width == hdr->rawi_hdr.raw_info.width &&

@@ -123,7 +123,7 @@ int run_hdr_preview(mlvb_context *ctx, const struct frame_headers *hdr, const Fr
     std::shared_ptr<PixelList> focus;
     {
         std::lock_guard<std::mutex> lk(ctx->clip_mu);
-        int rc = get_focus_pixel_map(ctx, hdr, &focus);
+        int rc = get_focus_pixel_map(ctx, hdr, g, &focus);
         if (rc) return rc;
     }
     if (focus && focus->nlevels && g.black <= MLVB_MAX_BLACK) {

@@ -58,6 +58,9 @@ int launch_lj92_decode(const void *d_payload, size_t payload_stride, size_t payl
                        size_t out_stride_px, int w, int h, int nframes, int *d_status, void *d_scratch,
                        size_t scratch_bytes, cudaStream_t st);
 
+// ---- lzma_dec.cu (host code): raw LZMA1 stream -> bytes; *dst_len in = capacity, out = bytes produced ----
+int mlvb_lzma_decode(uint8_t *dst, size_t *dst_len, const uint8_t *src, size_t src_len, const uint8_t props[5]);
+
 // ---- patternnoise.cu ----
 size_t pattern_noise_scratch_bytes(int w, int h);
 int launch_pattern_noise(int16_t *d_raw, int w, int h, int white, void *d_scratch, cudaStream_t st);

@@ -229,3 +229,14 @@ def amaze_test_mosaic(w, h, seed):
     base = np.where((xx % 2) != (yy % 2), base * 0.5 + 60000, base)
     base[:, w // 2:] += 40000 * (xx[:, w // 2:] % 2)
     return np.clip(base, 0, 0xFFFFF).astype(np.int32).astype(np.float32)
+
+
+def lzma_payload(img, bpp=14, *, lc=3, lp=0, pb=2, dict_size=1 << 22):
+    """VIDF payload of a legacy LZMA clip (reference main.c:598-616): uint32 unpacked size, the 5 LZMA property
+    bytes, then the raw LZMA1 stream of the packed frame.  Input generation only (Python's lzma module)."""
+    import lzma
+    packed = pack_bits(img, bpp).tobytes()
+    alone = lzma.compress(packed, format=lzma.FORMAT_ALONE,
+                          filters=[{"id": lzma.FILTER_LZMA1, "lc": lc, "lp": lp, "pb": pb, "dict_size": dict_size}])
+    # FORMAT_ALONE = 5 property bytes + uint64 size + stream
+    return np.frombuffer(np.uint32(len(packed)).tobytes() + alone[:5] + alone[13:], dtype=np.uint8).copy()

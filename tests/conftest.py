@@ -60,3 +60,40 @@ def fresh_ctx(gpu_ctx):
     # the drop-in symbols run on the process-wide default context: clear its per-clip / dual-ISO state too
     mlvfs_b200.Context.default().reset_clip_state()
     return gpu_ctx
+
+
+def parity_record(name, got, want, tol):
+    """Append max |diff| / differing pixels / PSNR of a GPU-vs-reference comparison to gpurun_out/parity_r02.json
+    (copied to profiles/ after the run: the north star asks for the tolerance stages' PSNR to be reported)."""
+    import json
+    d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    mse = float(np.mean(d.astype(np.float64) ** 2))
+    rec = {"test": name, "shape": list(got.shape), "tolerance_dn": tol, "max_abs_diff_dn": int(d.max()),
+           "differing_px": int(np.count_nonzero(d)), "px": int(d.size),
+           "psnr_db": None if mse == 0 else round(float(10 * np.log10(65535.0 ** 2 / mse)), 2)}
+    path = os.path.join(ROOT, "gpurun_out", "parity_r02.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        recs = []
+        if os.path.exists(path):
+            with open(path) as f:
+                recs = json.load(f)
+        recs = [r for r in recs if r["test"] != name] + [rec]
+        with open(path, "w") as f:
+            json.dump(recs, f, indent=1)
+    except OSError:
+        pass
+    print(f"{name}: max |diff| = {rec['max_abs_diff_dn']} DN, differing px = {rec['differing_px']} / {rec['px']}, PSNR = {rec['psnr_db']} dB")
+    return rec
+
+
+def reference_frames(tmp_path, clip, nframes, opts):
+    """Frames of <tmp_path>/<clip> from the unmodified reference's process_frame in a fresh process (tests/refrun.py).
+    opts: dict with the fields of struct mlvfs (mlvfs.h:37-46)."""
+    import subprocess
+    order = ["chroma_smooth", "fix_bad_pixels", "fix_stripes", "dual_iso", "hdr_interpolation_method", "hdr_no_fullres",
+             "hdr_no_alias_map", "fix_pattern_noise", "deflicker"]
+    out = os.path.join(str(tmp_path), "ref_frames.npy")
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "refrun.py"), str(tmp_path), clip, str(nframes), out]
+                          + [str(int(opts.get(k, 0))) for k in order])
+    return np.load(out)

@@ -118,6 +118,49 @@ def main():
     np.savez_compressed(os.path.join(OUT, "single_iso.npz"), **g)
     print("wrote", os.path.join(OUT, "single_iso.npz"), os.path.getsize(os.path.join(OUT, "single_iso.npz")), "bytes")
     dual_iso_golden(ref)
+    focus_pixel_golden(ref)
+
+
+FOCUS_CAM, FOCUS_RAW = 0x80000326, (1808, 727)
+FOCUS_CASES = [  # (w, h, pan_x, pan_y, frame seed): full-width crop-mode frame, and a panned window whose left / right
+    (1808, 727, 0, 0, 11),      # neighbours in the map fall outside [0, w) on the top / bottom rows (wrapped indices)
+    (1280, 180, 260, 288, 12),
+]
+
+
+def focus_pixel_golden(ref):
+    """fix_focus_pixels with one of the reference's REAL maps (mlvfs/data/80000326_1808x727.fpm).  The map's entries
+    are stored in the fixture (the GPU box has no /root/reference); outputs are stored as (index, value) of the
+    pixels the reference changed."""
+    src = "/root/reference/mlvfs/data/%x_%dx%d.fpm" % (FOCUS_CAM, *FOCUS_RAW)
+    xy = np.loadtxt(src, dtype=np.int32).reshape(-1, 2)
+    g = {"fpm_xy": xy.astype(np.int16)}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            write_fpm(xy, FOCUS_CAM, *FOCUS_RAW)
+            for k, (w, h, px, py, seed) in enumerate(FOCUS_CASES):
+                hdr = F.make_frame_headers(w, h, camera_model=FOCUS_CAM, raw_width=FOCUS_RAW[0], raw_height=FOCUS_RAW[1],
+                                           pan_x=px, pan_y=py)
+                img = synth.make_frame(w, h, seed)
+                for dual in (0, 1):
+                    out = img.copy()
+                    with O.quiet_stdout():
+                        ref.fix_focus_pixels(C.byref(hdr), p(out), dual)
+                    idx = np.flatnonzero(out != img).astype(np.int32)
+                    g[f"case{k}_dual{dual}_idx"] = idx
+                    g[f"case{k}_dual{dual}_val"] = out.reshape(-1)[idx]
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "focus_pixels.npz"), **g)
+    print("wrote", os.path.join(OUT, "focus_pixels.npz"), os.path.getsize(os.path.join(OUT, "focus_pixels.npz")), "bytes")
+
+
+def write_fpm(xy, cam, rw, rh, dirname="."):
+    with open(os.path.join(dirname, "%x_%dx%d.fpm" % (cam, rw, rh)), "w") as f:
+        for x, y in xy:
+            f.write(f"{int(x)} \t {int(y)}\n")
 
 
 def dual_iso_golden(ref):
@@ -140,4 +183,7 @@ def dual_iso_golden(ref):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "focus":
+        focus_pixel_golden(O.load_ref())
+    else:
+        main()

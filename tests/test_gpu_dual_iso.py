@@ -21,9 +21,10 @@ def _psnr(a, b):
 
 
 def _check(got, want, label):
+    from conftest import parity_record
+    rec = parity_record(label, got, want, TOL_DN)
     d = np.abs(got.astype(np.int32) - want.astype(np.int32))
-    print(f"{label}: max |diff| = {d.max()} DN, differing px = {np.count_nonzero(d)} / {d.size}, PSNR = {_psnr(got, want):.1f} dB")
-    assert d.max() <= TOL_DN, f"{label}: max diff {d.max()} DN at {np.unravel_index(d.argmax(), d.shape)}"
+    assert rec["max_abs_diff_dn"] <= TOL_DN, f"{label}: max diff {d.max()} DN at {np.unravel_index(d.argmax(), d.shape)}"
 
 
 @pytest.mark.parametrize("w,h,cs,alias,badpix,fullres", [
