@@ -101,6 +101,16 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
                         const mlvb_options *opts, const char *mlv_filename, uint16_t *dst);
 int mlvb_wait(mlvb_context *ctx, mlvb_ticket ticket, mlvb_frame_result *res);
 
+/* Host batch -- what the --prefetch queue calls with its look-ahead frames: `nframes` frames of ONE clip, payloads
+ * and destinations in host memory (pinned for asynchronous copies; pageable memory works but serialises).  Frames
+ * whose results do not depend on per-frame statistics (no dual ISO, no deflicker) and that share one shape run as
+ * one device batch -- one pass of the fused kernels over all of them, copies overlapped with other batches in
+ * flight; anything else is pipelined frame by frame over the context's slots.  Blocks until every frame is in its
+ * destination.  results may be NULL.  Returns MLVB_OK or the last error (per-frame status in results[]). */
+int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_headers *hdrs, const void *const *payloads,
+                        const size_t *payload_bytes, const mlvb_options *opts, const char *mlv_filename, uint16_t *const *dsts,
+                        mlvb_frame_result *results);
+
 /* Device-resident batch: `nframes` payloads of one clip already in HBM (payload_stride bytes apart,
  * 16-byte aligned) -> `nframes` finished frames in HBM (out_stride_px uint16 apart).  Enqueued on
  * `cuda_stream` (a cudaStream_t; NULL = the context's own stream); does not synchronise unless the
@@ -120,7 +130,8 @@ int mlvb_get_bad_pixels(mlvb_context *ctx, uint64_t file_guid, int aggressive, i
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t mlvb_launch_count(mlvb_context *ctx);
 /* Introspection for tests: how often a given kernel path was taken.  which: 0 = fused single-ISO strip kernel
- * (per-frame and small batches), 1 = fused single-ISO wide kernel (large batches). */
+ * (per-frame and small batches), 1 = fused single-ISO wide kernel (large batches), 2 = host batches that ran as one
+ * device batch (mlvb_process_frames). */
 uint64_t mlvb_path_count(mlvb_context *ctx, int which);
 /* Per-stage device timing for the roofline report: between begin and end every stage of the
  * batch / per-frame pipeline is bracketed by CUDA events on its own stream.  Stage ids:

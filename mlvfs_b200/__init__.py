@@ -63,7 +63,7 @@ StripesCorrection._fields_ = [
 ABI_SYMBOLS = [
     "mlvb_context_create", "mlvb_context_destroy", "mlvb_default_context", "mlvb_device_count",
     "mlvb_host_alloc", "mlvb_host_free", "mlvb_host_pool_trim", "mlvb_process_frame", "mlvb_submit", "mlvb_wait",
-    "mlvb_process_batch_device", "mlvb_reset_clip_state", "mlvb_seed_dither", "mlvb_get_stripes",
+    "mlvb_process_frames", "mlvb_process_batch_device", "mlvb_reset_clip_state", "mlvb_seed_dither", "mlvb_get_stripes",
     "mlvb_get_bad_pixels", "mlvb_launch_count", "mlvb_path_count", "mlvb_profile_begin", "mlvb_profile_end",
     "dng_get_image_data", "dng_get_image_size", "get_image_data", "get_raw2evf", "get_raw2ev", "get_ev2raw",
     "chroma_smooth", "fix_bad_pixels", "fix_focus_pixels", "free_focus_pixel_maps",

@@ -310,15 +310,27 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
     ctx->luts.ev2raw_full = ctx->d_ev2raw_full + 10 * MLVB_EV_RES;
     if (nslots <= 0) nslots = 4;
     ctx->slots.resize(nslots);
+    {
+        // A wait that spins burns a host core per frame in flight; with several GPUs (or several processes) on one
+        // box those cores are what the copies and the other ranks need.  Events are created blocking by default.
+        const char *bs = getenv("MLVB_BLOCKING_SYNC");
+        ctx->blocking_sync = !(bs && *bs == '0');
+    }
+    const unsigned ev_flags = cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0);
     for (auto &s : ctx->slots) {
         MLVB_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        MLVB_CUDA_OK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        MLVB_CUDA_OK(cudaEventCreateWithFlags(&s.done, ev_flags));
         MLVB_CUDA_OK(cudaMalloc(&s.d_status, sizeof(int)));
         MLVB_CUDA_OK(cudaMemset(s.d_status, 0, sizeof(int)));
         MLVB_CUDA_OK(cudaHostAlloc(&s.h_status, sizeof(int), cudaHostAllocDefault));
         *s.h_status = 0;
     }
     MLVB_CUDA_OK(cudaStreamCreateWithFlags(&ctx->batch_stream, cudaStreamNonBlocking));
+    ctx->host_batches.resize(3);
+    for (auto &b : ctx->host_batches) {
+        MLVB_CUDA_OK(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+        MLVB_CUDA_OK(cudaEventCreateWithFlags(&b.done, ev_flags));
+    }
     return MLVB_OK;
     }();
     if (rc_create != MLVB_OK) {
@@ -354,6 +366,16 @@ void mlvb_context_destroy(mlvb_context *ctx)
     }
     if (ctx->d_batch_status) cudaFree(ctx->d_batch_status);
     if (ctx->d_batch_aux) cudaFree(ctx->d_batch_aux);
+    for (auto &b : ctx->host_batches) {
+        if (b.stream) cudaStreamDestroy(b.stream);
+        if (b.done) cudaEventDestroy(b.done);
+        if (b.d_in) cudaFree(b.d_in);
+        if (b.d_work) cudaFree(b.d_work);
+        if (b.d_out) cudaFree(b.d_out);
+        if (b.d_aux) cudaFree(b.d_aux);
+        if (b.d_status) cudaFree(b.d_status);
+        if (b.h_status) cudaFreeHost(b.h_status);
+    }
     for (auto &l : ctx->batch_lanes) {
         if (l.d_aux) cudaFree(l.d_aux);
         if (l.done) cudaEventDestroy(l.done);
@@ -511,7 +533,7 @@ int mlvb_profile_end(mlvb_context *ctx, float *ms_per_stage, int *spans_per_stag
 }
 
 uint64_t mlvb_launch_count(mlvb_context *ctx) { return ctx ? (uint64_t)ctx->launches : 0; }
-uint64_t mlvb_path_count(mlvb_context *ctx, int which) { return (ctx && which >= 0 && which < 2) ? (uint64_t)ctx->path_count[which] : 0; }
+uint64_t mlvb_path_count(mlvb_context *ctx, int which) { return (ctx && which >= 0 && which < 3) ? (uint64_t)ctx->path_count[which] : 0; }
 
 // ------------------------------------------------------------------ host-buffer pipeline
 
@@ -691,6 +713,133 @@ int mlvb_process_frame(mlvb_context *ctx, const struct frame_headers *hdr, const
         return (int)t;
     }
     return mlvb_wait(ctx, t, res);
+}
+
+// ------------------------------------------------------------------ host batches
+
+namespace {
+
+BatchSlot *acquire_batch_slot(mlvb_context *ctx)
+{
+    std::unique_lock<std::mutex> lk(ctx->hb_mu);
+    for (;;) {
+        for (auto &b : ctx->host_batches)
+            if (!b.busy) { b.busy = true; return &b; }
+        ctx->hb_cv.wait(lk);
+    }
+}
+
+void release_batch_slot(mlvb_context *ctx, BatchSlot *b)
+{
+    { std::lock_guard<std::mutex> lk(ctx->hb_mu); b->busy = false; }
+    ctx->hb_cv.notify_one();
+}
+
+// frames one device batch can hold: same geometry, levels, codec and crop offsets (one clip, no panning)
+bool same_batch_shape(const struct frame_headers &a, const struct frame_headers &b)
+{
+    const FrameGeom x = geom_from_headers(&a), y = geom_from_headers(&b);
+    return x.w == y.w && x.h == y.h && x.bpp == y.bpp && x.black == y.black && x.white == y.white && x.crop_x == y.crop_x &&
+           x.crop_y == y.crop_y && a.file_hdr.videoClass == b.file_hdr.videoClass && a.file_hdr.fileGuid == b.file_hdr.fileGuid &&
+           a.idnt_hdr.cameraModel == b.idnt_hdr.cameraModel && a.rawi_hdr.raw_info.width == b.rawi_hdr.raw_info.width &&
+           a.rawi_hdr.raw_info.height == b.rawi_hdr.raw_info.height;
+}
+
+}  // namespace
+
+int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_headers *hdrs, const void *const *payloads,
+                        const size_t *payload_bytes, const mlvb_options *opts, const char *mlv_filename, uint16_t *const *dsts,
+                        mlvb_frame_result *results)
+{
+    if (!ctx || nframes < 0 || (nframes && (!hdrs || !payloads || !payload_bytes || !opts || !dsts))) return MLVB_ERR_ARG;
+    if (nframes == 0) return MLVB_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MLVB_ERR_CUDA;
+
+    // One device batch needs frame-independent results and one shape; anything else is pipelined frame by frame
+    // over the context's slots (still one call for the host).
+    bool batch = nframes >= 2 && opts->dual_iso == 0 && opts->deflicker == 0 &&
+                 !(hdrs[0].file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LZMA);
+    for (int f = 1; f < nframes && batch; f++) batch = same_batch_shape(hdrs[0], hdrs[f]);
+    if (!batch) {
+        const int depth = (int)ctx->slots.size();
+        std::vector<mlvb_ticket> tk(nframes, -1);
+        int rc_all = MLVB_OK;
+        for (int f = 0; f < nframes + depth; f++) {
+            const int done = f - depth;
+            if (done >= 0 && tk[done] >= 0) {
+                const int rc = mlvb_wait(ctx, tk[done], results ? &results[done] : nullptr);
+                if (rc) rc_all = rc;
+            }
+            if (f < nframes) {
+                tk[f] = mlvb_submit(ctx, &hdrs[f], payloads[f], payload_bytes[f], opts, mlv_filename, dsts[f]);
+                if (tk[f] < 0) {
+                    rc_all = (int)tk[f];
+                    if (results) { results[f] = mlvb_frame_result(); results[f].status = (int)tk[f]; }
+                }
+            }
+        }
+        return rc_all;
+    }
+
+    const FrameGeom g = geom_from_headers(&hdrs[0]);
+    if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
+    const bool coded = (hdrs[0].file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LJ92) != 0;
+    size_t max_bytes = 0;
+    for (int f = 0; f < nframes; f++) max_bytes = std::max(max_bytes, payload_bytes[f]);
+    const size_t stride = (max_bytes + (coded ? 1024 : 0) + 255) / 256 * 256;
+    const size_t frame_px = (g.npix + 127) / 128 * 128;                       // 256-byte aligned frames
+
+    BatchSlot *b = acquire_batch_slot(ctx);
+    cudaStream_t st = b->stream;
+    int rc = [&]() -> int {
+        int r = reserve_device((void **)&b->d_in, &b->in_cap, stride * nframes + 1024);
+        if (!r) r = reserve_device((void **)&b->d_work, &b->work_cap, frame_px * 2 * nframes);
+        if (!r) r = reserve_device((void **)&b->d_out, &b->out_cap, frame_px * 2 * nframes);
+        if (!r) r = reserve_device(&b->d_aux, &b->aux_cap,
+                                   std::max(aux_bytes_for(g, *opts), coded ? lj92_scratch_bytes(stride, g.npix, nframes) : (size_t)0));
+        if (r) return r;
+        if (b->status_cap < nframes) {
+            if (b->d_status) cudaFree(b->d_status);
+            if (b->h_status) cudaFreeHost(b->h_status);
+            b->d_status = nullptr; b->h_status = nullptr; b->status_cap = 0;
+            MLVB_CUDA_OK(cudaMalloc(&b->d_status, sizeof(int) * nframes));
+            MLVB_CUDA_OK(cudaHostAlloc(&b->h_status, sizeof(int) * nframes, cudaHostAllocDefault));
+            b->status_cap = nframes;
+        }
+        MLVB_CUDA_OK(cudaMemsetAsync(b->d_status, 0, sizeof(int) * nframes, st));
+        for (int f = 0; f < nframes; f++) {
+            if (!coded && payload_bytes[f] < mlvb_packed_bytes((uint32_t)g.npix, g.bpp)) return MLVB_ERR_ARG;
+            MLVB_CUDA_OK(cudaMemcpyAsync(b->d_in + f * stride, payloads[f], payload_bytes[f], cudaMemcpyHostToDevice, st));
+            if (coded && payload_bytes[f] < stride)                           // a stale tail must not look like stream data
+                MLVB_CUDA_OK(cudaMemsetAsync(b->d_in + f * stride + payload_bytes[f], 0, stride - payload_bytes[f], st));
+        }
+        mlvb_frame_result res0;
+        r = run_pipeline(ctx, &hdrs[0], *opts, mlv_filename, b->d_in, stride, coded ? stride : max_bytes, b->d_work, b->d_out, frame_px,
+                         nframes, b->d_status, b->d_aux, b->aux_cap, st, &res0);
+        if (r) return r;
+        if (coded) MLVB_CUDA_OK(cudaMemcpyAsync(b->h_status, b->d_status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
+        for (int f = 0; f < nframes; f++)
+            MLVB_CUDA_OK(cudaMemcpyAsync(dsts[f], b->d_out + f * frame_px, g.npix * 2, cudaMemcpyDeviceToHost, st));
+        MLVB_CUDA_OK(cudaEventRecord(b->done, st));
+        MLVB_CUDA_OK(cudaEventSynchronize(b->done));
+        int rr = MLVB_OK;
+        for (int f = 0; f < nframes; f++) {
+            int s = MLVB_OK;
+            if (coded && b->h_status[f] != 0) {
+                fprintf(stderr, "libmlvfs_b200: LJ92: frame %d of the batch failed (%d)\n", f, b->h_status[f]);    // main.c:671-679
+                s = rr = MLVB_ERR_ARG;
+            }
+            if (results) { results[f] = res0; results[f].status = s; }
+        }
+        return rr;
+    }();
+    if (rc && rc != MLVB_ERR_ARG) cudaStreamSynchronize(st);
+    else if (rc) cudaStreamSynchronize(st);
+    ctx->path_count[2] += 1;
+    release_batch_slot(ctx, b);
+    if (rc && results)
+        for (int f = 0; f < nframes; f++) if (results[f].status == MLVB_OK) results[f].status = rc;
+    return rc;
 }
 
 // ------------------------------------------------------------------ device-resident batch

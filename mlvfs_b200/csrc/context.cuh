@@ -93,6 +93,19 @@ struct Slot {
     int job_rc = 0;
 };
 
+// A host batch in flight (mlvb_process_frames): device staging for n payloads, n work frames and n finished frames
+// of one clip, its own stream and scratch, so that batches issued by different host threads overlap.
+struct BatchSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *d_in = nullptr;     size_t in_cap = 0;
+    uint16_t *d_work = nullptr;  size_t work_cap = 0;
+    uint16_t *d_out = nullptr;   size_t out_cap = 0;
+    void *d_aux = nullptr;       size_t aux_cap = 0;
+    int *d_status = nullptr, *h_status = nullptr; int status_cap = 0;
+    bool busy = false;
+};
+
 struct AsyncJob {                          // one submitted frame waiting for a submit worker
     Slot *slot;
     struct frame_headers hdr;
@@ -146,8 +159,14 @@ struct mlvb_context {
     std::vector<BatchLane> batch_lanes;
     cudaEvent_t batch_fork = nullptr;
 
+    // host batches (mlvb_process_frames)
+    std::mutex hb_mu;
+    std::condition_variable hb_cv;
+    std::vector<BatchSlot> host_batches;
+    bool blocking_sync = true;             // waits sleep on the event instead of spinning ($MLVB_BLOCKING_SYNC=0: spin)
+
     std::atomic<uint64_t> launches{0};
-    std::atomic<uint64_t> path_count[2] = {{0}, {0}};   // fused strip kernel, fused wide kernel (mlvb_path_count)
+    std::atomic<uint64_t> path_count[3] = {{0}, {0}, {0}};   // fused strip kernel, fused wide kernel, host batches (mlvb_path_count)
 
     // optional per-stage device timing (mlvb_profile_begin / mlvb_profile_end), bench.py's roofline leg
     bool profiling = false;
