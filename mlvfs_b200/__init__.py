@@ -101,6 +101,8 @@ def lib():
         L.mlvb_submit.restype = C.c_int64
         L.mlvb_submit.argtypes = [vp, vp, vp, sz, vp, C.c_char_p, vp]
         L.mlvb_wait.argtypes = [vp, C.c_int64, vp]
+        L.mlvb_process_frames.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_char_p, vp, vp]
+        L.mlvb_host_pool_trim.argtypes = []
         L.mlvb_process_batch_device.argtypes = [vp, vp, vp, C.c_char_p, vp, sz, sz, vp, sz, C.c_int, vp]
         L.mlvb_reset_clip_state.argtypes = [vp]
         L.mlvb_seed_dither.argtypes = [vp, C.c_uint]
@@ -173,6 +175,18 @@ class Context:
         if rc != OK:
             raise RuntimeError(f"mlvb_process_frame failed with {rc}")
         return out, res
+
+    def process_frames(self, hdrs, payload_ptrs, payload_bytes, opts, mlv_filename, dst_ptrs):
+        """mlvb_process_frames: a host batch of frames of one clip.  hdrs: list of FrameHeaders; payload_ptrs /
+        dst_ptrs: host addresses (ints); returns (rc, [FrameResult])."""
+        n = len(hdrs)
+        H = (FrameHeaders * n)(*hdrs)
+        P = (C.c_void_p * n)(*payload_ptrs)
+        B = (C.c_size_t * n)(*payload_bytes)
+        D = (C.c_void_p * n)(*dst_ptrs)
+        R = (FrameResult * n)()
+        rc = lib().mlvb_process_frames(self._h, n, H, P, B, C.byref(opts), mlv_filename.encode(), D, R)
+        return rc, list(R)
 
     def submit(self, hdr, payload_ptr, payload_bytes, opts, mlv_filename, dst_ptr):
         return lib().mlvb_submit(self._h, C.byref(hdr), payload_ptr, payload_bytes, C.byref(opts),

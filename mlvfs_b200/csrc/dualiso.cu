@@ -623,14 +623,29 @@ size_t dual_iso_scratch_bytes(int w, int h, int interp_method)
 // Per-context dual-ISO tables: the 20-bit EV LUTs keyed by black like the reference's statics (built
 // from the first converted frame's white level, hdr.c:1089-1093), the fp64 log table of hdr_check and
 // the 3000 candidate slopes of match_exposures.
+// One immutable set of 20-bit tables for a black level.  Frames in flight on any stream keep reading the set they
+// started with: a set is never rewritten, a black-level change publishes a NEW set and retires the old one, and
+// retired sets are only freed after a device-wide synchronisation (or with the context).
+struct Lut20Set {
+    int black = -1, white = 0;
+    int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
+    double *d_fullres_curve = nullptr;  // 2^20 doubles
+    int *d_fullres_lim = nullptr;       // 4 ints, see PixParams::fullres_lim
+    ~Lut20Set()
+    {
+        if (d_raw2ev) cudaFree(d_raw2ev);
+        if (d_ev2raw_0) cudaFree(d_ev2raw_0);
+        if (d_fullres_curve) cudaFree(d_fullres_curve);
+        if (d_fullres_lim) cudaFree(d_fullres_lim);
+    }
+};
+
 struct DualIsoTables {
     std::mutex mu;
     std::vector<void *> pinned_free;    // host staging for the statistics read-backs (pinned: async, full PCIe rate)
-    int lut_black = -1;
-    int *d_raw2ev = nullptr, *d_ev2raw_0 = nullptr;
+    std::shared_ptr<Lut20Set> current;  // keyed by black, built with the white level of the frame that created it
+    std::vector<std::shared_ptr<Lut20Set>> retired;
     double *d_raw2evf = nullptr;        // 16384 + MAX_BLACK doubles
-    double *d_fullres_curve = nullptr;  // 2^20 doubles, keyed by lut_black
-    int *d_fullres_lim = nullptr;       // 4 ints, see PixParams::fullres_lim
     double *d_test_a = nullptr;
     std::vector<double> test_a;
 };
@@ -660,11 +675,9 @@ void dual_iso_free_tables(mlvb_context *ctx)
         g_tabs.erase(it);
     }
     for (void *p : t->pinned_free) cudaFreeHost(p);
-    if (t->d_raw2ev) cudaFree(t->d_raw2ev);
-    if (t->d_ev2raw_0) cudaFree(t->d_ev2raw_0);
+    t->current.reset();
+    t->retired.clear();
     if (t->d_raw2evf) cudaFree(t->d_raw2evf);
-    if (t->d_fullres_curve) cudaFree(t->d_fullres_curve);
-    if (t->d_fullres_lim) cudaFree(t->d_fullres_lim);
     if (t->d_test_a) cudaFree(t->d_test_a);
     delete t;
 }
@@ -695,7 +708,8 @@ void dual_iso_reset_tables(mlvb_context *ctx)
 {
     DualIsoTables *t = tables_of(ctx);
     std::lock_guard<std::mutex> lk(t->mu);
-    t->lut_black = -1;
+    if (t->current) t->retired.push_back(std::move(t->current));      // frames in flight may still read it
+    t->current.reset();
 }
 
 // hdr_interpolate on a device-resident 14-bit frame (in place -> 16-bit).  Returns 1 converted,
@@ -853,25 +867,33 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     // 20-bit EV tables, rebuilt only when black changes (with this frame's white), hdr.c:1089-1093
     {
         std::lock_guard<std::mutex> lk(T->mu);
-        if (T->lut_black != black) {
+        if (!T->current || T->current->black != black) {
+            if (T->retired.size() >= 4) {                               // rare: clips with different black levels alternating
+                MLVB_CUDA_OK(cudaDeviceSynchronize());
+                T->retired.clear();
+            }
+            auto S = std::make_shared<Lut20Set>();
             std::vector<int> r2e, e2r;
             build_luts20(black, white, r2e, e2r);
-            if (!T->d_raw2ev) MLVB_CUDA_OK(cudaMalloc(&T->d_raw2ev, N20 * sizeof(int)));
-            if (!T->d_ev2raw_0) MLVB_CUDA_OK(cudaMalloc(&T->d_ev2raw_0, 24 * EVR * sizeof(int)));
-            MLVB_CUDA_OK(cudaMemcpy(T->d_raw2ev, r2e.data(), N20 * sizeof(int), cudaMemcpyHostToDevice));
-            MLVB_CUDA_OK(cudaMemcpy(T->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
-            if (!T->d_fullres_curve) MLVB_CUDA_OK(cudaMalloc(&T->d_fullres_curve, (size_t)N20 * sizeof(double)));
-            if (!T->d_fullres_lim) MLVB_CUDA_OK(cudaMalloc(&T->d_fullres_lim, 4 * sizeof(int)));
-            diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(T->d_fullres_lim);
-            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(T->d_fullres_curve, T->d_fullres_lim, black);
-            MLVB_CUDA_OK(cudaStreamSynchronize(st));                    // other streams read the table from now on
+            MLVB_CUDA_OK(cudaMalloc(&S->d_raw2ev, N20 * sizeof(int)));
+            MLVB_CUDA_OK(cudaMalloc(&S->d_ev2raw_0, 24 * EVR * sizeof(int)));
+            MLVB_CUDA_OK(cudaMemcpy(S->d_raw2ev, r2e.data(), N20 * sizeof(int), cudaMemcpyHostToDevice));
+            MLVB_CUDA_OK(cudaMemcpy(S->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
+            MLVB_CUDA_OK(cudaMalloc(&S->d_fullres_curve, (size_t)N20 * sizeof(double)));
+            MLVB_CUDA_OK(cudaMalloc(&S->d_fullres_lim, 4 * sizeof(int)));
+            diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(S->d_fullres_lim);
+            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(S->d_fullres_curve, S->d_fullres_lim, black);
+            MLVB_CUDA_OK(cudaStreamSynchronize(st));                    // complete before the set is published to other streams
             ctx->launches += 1;
-            T->lut_black = black;
+            S->black = black; S->white = white;
+            if (T->current) T->retired.push_back(std::move(T->current));
+            T->current = S;
         }
-        P.raw2ev = T->d_raw2ev;
-        P.ev2raw = T->d_ev2raw_0 + 10 * EVR;
-        P.fullres_curve = T->d_fullres_curve;
-        P.fullres_lim = T->d_fullres_lim;
+        const Lut20Set &S = *T->current;                                // stays alive (current or retired) until a device-wide sync
+        P.raw2ev = S.d_raw2ev;
+        P.ev2raw = S.d_ev2raw_0 + 10 * EVR;
+        P.fullres_curve = S.d_fullres_curve;
+        P.fullres_lim = S.d_fullres_lim;
     }
     P.mix_curve = D.mix_curve;
     P.mix_lim = D.mix_lim;

@@ -1,7 +1,10 @@
 /*
  * frame_server.c -- command-line driver of the host frame-request path, without FUSE:
  *   mlvb_frames <mlv_dir> <clip.MLV> [--cs3x3 --bad-pix --stripes ...] [--prefetch=N] [--readers=T]
- *               [--frames=K] [--dump=out.raw]
+ *               [--gpus=G] [--batch=B] [--slots=S] [--repeat=R] [--frames=K] [--dump=out.raw] [--dump-headers=out.bin]
+ * --gpus: one context per GPU, frames dealt in chunks of B (--batch, default 8 with --prefetch, else 1): frame n on
+ * GPU (n / B) mod G; look-ahead chunks of the prefetch queue run as one device batch.  --repeat: request the clip R
+ * times (cache emptied in between) and report the sustained rate of all passes after the first.
  * Requests every frame of the clip the way the FUSE read handler does (main.c:1460):
  * get_or_create_image_buffer(path, &process_frame, &was_created), touches the data, releases it.
  * Prints frames/s and an FNV-1a hash per run (and optionally dumps the frames) so tests can compare
@@ -23,6 +26,7 @@ static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static uint64_t *g_hash;
 static FILE *g_dump;
 static int g_failed = 0;
+static FILE *g_dump_headers;
 
 static uint64_t fnv1a(const void *p, size_t n)
 {
@@ -56,6 +60,12 @@ static void *reader(void *arg)
             fwrite(ib->data, 1, ib->size, g_dump);
             pthread_mutex_unlock(&g_mu);
         }
+        if (g_dump_headers && ib->header) {
+            pthread_mutex_lock(&g_mu);
+            fseeko(g_dump_headers, (off_t)i * (off_t)ib->header_size, SEEK_SET);
+            fwrite(ib->header, 1, ib->header_size, g_dump_headers);
+            pthread_mutex_unlock(&g_mu);
+        }
         release_image_buffer_by_path(path);
     }
 }
@@ -70,8 +80,8 @@ int main(int argc, char **argv)
     memset(&cfg, 0, sizeof(cfg));
     cfg.mlv_path = argv[1];
     snprintf(g_clip, sizeof(g_clip), "%s", argv[2]);
-    int prefetch = 0, readers = 1, limit = -1;
-    const char *dump = NULL;
+    int prefetch = 0, readers = 1, limit = -1, gpus = 1, batch = 0, slots = 0, repeat = 1, workers = 0;
+    const char *dump = NULL, *dump_headers = NULL;
     for (int i = 3; i < argc; i++) {                       /* option names of main.c:1853-1882 */
         const char *a = argv[i];
         if (!strcmp(a, "--cs2x2")) cfg.options.chroma_smooth = 2;
@@ -92,40 +102,71 @@ int main(int argc, char **argv)
         else if (!strncmp(a, "--readers=", 10)) readers = atoi(a + 10);
         else if (!strncmp(a, "--frames=", 9)) limit = atoi(a + 9);
         else if (!strncmp(a, "--dump=", 7)) dump = a + 7;
+        else if (!strncmp(a, "--dump-headers=", 15)) dump_headers = a + 15;
+        else if (!strncmp(a, "--gpus=", 7)) gpus = atoi(a + 7);
+        else if (!strncmp(a, "--batch=", 8)) batch = atoi(a + 8);
+        else if (!strncmp(a, "--slots=", 8)) slots = atoi(a + 8);
+        else if (!strncmp(a, "--repeat=", 9)) repeat = atoi(a + 9);
+        else if (!strncmp(a, "--workers=", 10)) workers = atoi(a + 10);
+        else if (!strcmp(a, "--no-fullres")) cfg.options.hdr_no_fullres = 1;
         else { fprintf(stderr, "unknown option %s\n", a); return 2; }
     }
+    if (batch <= 0) batch = prefetch > 0 ? 8 : 1;
     frame_builder_configure(&cfg);
     resource_manager_set_data_free(mlvb_host_free);
-    resource_manager_set_prefetch(prefetch, 0, frame_builder_frame_limit);
+    resource_manager_set_batch_builder(batch > 1 ? process_frame_batch : NULL, batch);
+    resource_manager_set_prefetch(prefetch, workers, frame_builder_frame_limit);
 
     char mlv_file[4096];
     snprintf(mlv_file, sizeof(mlv_file), "%s/%s", argv[1], g_clip);
     g_nframes = mlv_get_frame_count(mlv_file);
     if (limit >= 0 && limit < g_nframes) g_nframes = limit;
     if (g_nframes <= 0) { fprintf(stderr, "no frames in %s\n", mlv_file); return 1; }
-    if (!mlvb_default_context()) { fprintf(stderr, "no CUDA device: no CPU path\n"); return 3; }
+    gpus = frame_builder_use_gpus(gpus, slots, batch);
+    if (gpus <= 0) { fprintf(stderr, "no CUDA device: no CPU path\n"); return 3; }
     g_hash = calloc((size_t)g_nframes, sizeof(uint64_t));
     if (dump) g_dump = fopen(dump, "wb");
+    if (dump_headers) g_dump_headers = fopen(dump_headers, "wb");
 
     if (readers < 1) readers = 1;
     if (readers > 64) readers = 64;
+    if (repeat < 1) repeat = 1;
     pthread_t th[64];
     struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (int i = 0; i < readers; i++) pthread_create(&th[i], NULL, reader, NULL);
-    for (int i = 0; i < readers; i++) pthread_join(th[i], NULL);
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    double dt = 0, dt_sustained = 0;
+    for (int pass = 0; pass < repeat; pass++) {
+        g_next = 0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int i = 0; i < readers; i++) pthread_create(&th[i], NULL, reader, NULL);
+        for (int i = 0; i < readers; i++) pthread_join(th[i], NULL);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double d = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+        if (pass == 0) dt = d; else dt_sustained += d;
+        if (pass + 1 < repeat) {                               /* every pass builds every frame again */
+            resource_manager_set_prefetch(0, 0, NULL);
+            free_all_image_buffers();
+            resource_manager_set_prefetch(prefetch, workers, frame_builder_frame_limit);
+        }
+    }
     uint64_t all = 1469598103934665603ull, built = 0, hits = 0;
     for (int i = 0; i < g_nframes; i++) { all ^= g_hash[i]; all *= 1099511628211ull; }
     resource_manager_prefetch_stats(&built, &hits);
-    printf("{\"frames\": %d, \"failed\": %d, \"seconds\": %.6f, \"fps\": %.2f, \"readers\": %d, \"prefetch\": %d, "
-           "\"prefetch_built\": %llu, \"prefetch_hits\": %llu, \"hash\": \"%016llx\", \"frame0_hash\": \"%016llx\"}\n",
-           g_nframes, g_failed, dt, g_nframes / dt, readers, prefetch, (unsigned long long)built,
-           (unsigned long long)hits, (unsigned long long)all, (unsigned long long)g_hash[0]);
+    uint64_t device_batches = 0;
+    for (int i = 0; i < gpus; i++) device_batches += mlvb_path_count(frame_builder_context(i), 2);
+    printf("{\"frames\": %d, \"failed\": %d, \"seconds\": %.6f, \"fps\": %.2f, \"sustained_fps\": %.2f, \"passes\": %d, "
+           "\"readers\": %d, \"prefetch\": %d, \"gpus\": %d, \"batch\": %d, "
+           "\"prefetch_built\": %llu, \"prefetch_hits\": %llu, \"prefetch_batches\": %llu, \"device_batches\": %llu, "
+           "\"hash\": \"%016llx\", \"frame0_hash\": \"%016llx\"}\n",
+           g_nframes, g_failed, dt, g_nframes / dt, repeat > 1 ? g_nframes * (repeat - 1) / dt_sustained : g_nframes / dt, repeat,
+           readers, prefetch, gpus, batch, (unsigned long long)built, (unsigned long long)hits,
+           (unsigned long long)resource_manager_prefetch_batches(), (unsigned long long)device_batches,
+           (unsigned long long)all, (unsigned long long)g_hash[0]);
     if (g_dump) fclose(g_dump);
+    if (g_dump_headers) fclose(g_dump_headers);
     resource_manager_shutdown();
     free_all_image_buffers();
+    frame_builder_shutdown();
+    mlvb_host_pool_trim();
     mlv_clip_close_all();
     return g_failed ? 1 : 0;
 }

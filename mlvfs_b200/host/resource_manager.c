@@ -2,9 +2,19 @@
  * resource_manager.c -- frame cache + prefetch queue.  See resource_manager.h.
  * Cache behaviour follows reference resource_manager.c:39-121,195-227: a list of image_buffers in
  * creation order, one mutex per buffer held while the callback builds the frame, eviction of the
- * oldest unused buffers above a soft limit and of the oldest buffers, used or not, above a hard limit.
- * The limits grow with the prefetch depth so that frames built ahead are not evicted before they
- * are read.
+ * oldest idle buffers above a soft limit.  The limits grow with the prefetch depth so that frames
+ * built ahead are not evicted before they are read.
+ *
+ * Lifetime rule (the reference has none and can free a buffer under a reader): a buffer is never
+ * freed while it is pinned (`pins`, taken under the list lock by every lookup -- readers and prefetch
+ * workers alike -- and dropped after the build) or in use (`in_use`, from the request until
+ * release_image_buffer*).
+ *
+ * Prefetch: look-ahead frames are requested in CHUNKS of `batch` consecutive frames.  A worker
+ * creates the chunk's missing buffers, holds their mutexes (a reader that wants one of them waits,
+ * exactly as it would on a frame being built), and hands the whole chunk to the batch builder -- one
+ * device batch on one GPU (frame_builder.c) -- or, without a batch builder, builds them one by one
+ * through the frame callback.
  */
 #define _GNU_SOURCE
 #include "resource_manager.h"
@@ -16,28 +26,29 @@
 
 #define BASE_MAX_UNUSED 4      /* resource_manager.c:39 */
 #define BASE_MAX_TOTAL 16      /* resource_manager.c:40 */
+#define MAX_BATCH 64
 
 static pthread_mutex_t g_list_mu = PTHREAD_MUTEX_INITIALIZER;
 static struct image_buffer *g_head = NULL;
 static int g_count = 0;
 static void (*g_data_free)(void *) = free;
 
-/* ---- prefetch queue ---- */
-struct prefetch_req { char *path; image_buffer_cbr cbr; };
+/* ---- prefetch queue: chunk requests ---- */
+struct prefetch_req { char *path; int first, count; image_buffer_cbr cbr; };   /* path = any frame of the clip */
 #define PF_QUEUE_CAP 256
 static struct prefetch_req g_q[PF_QUEUE_CAP];
 static int g_q_head = 0, g_q_len = 0;
 static pthread_mutex_t g_q_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_q_cv = PTHREAD_COND_INITIALIZER;
 static pthread_t g_workers[32];
-static int g_nworkers = 0, g_depth = 0, g_stop = 0;
+static int g_nworkers = 0, g_depth = 0, g_stop = 0, g_batch = 1;
 static int (*g_frame_limit)(const char *) = NULL;
-static uint64_t g_pf_built = 0, g_pf_hits = 0;
+static image_buffer_batch_cbr g_batch_cbr = NULL;
+static uint64_t g_pf_built = 0, g_pf_hits = 0, g_pf_batches = 0;
 
 void resource_manager_set_data_free(void (*free_fn)(void *)) { g_data_free = free_fn ? free_fn : free; }
 
-static int max_unused(void) { return BASE_MAX_UNUSED + 2 * g_depth; }
-static int max_total(void) { return BASE_MAX_TOTAL + 4 * g_depth; }
+static int max_unused(void) { return BASE_MAX_UNUSED + 2 * (g_depth + g_batch); }
 
 static struct image_buffer *find_locked(const char *path)
 {
@@ -59,28 +70,14 @@ static void unlink_and_free_locked(struct image_buffer *victim)
     g_count--;
 }
 
-/* resource_manager.c:195-227.  A buffer whose mutex is held is being built right now: skip it. */
+/* resource_manager.c:195-227: drop the oldest idle buffers above the soft limit.  Pinned or in-use buffers are
+ * never victims; `pins` and `in_use` are only written under g_list_mu, which the caller holds. */
 static void cleanup_locked(void)
 {
     while (g_count > max_unused()) {
         struct image_buffer *victim = NULL;
-        for (struct image_buffer *b = g_head; b; b = b->next) {
-            if (pthread_mutex_trylock(&b->mutex) != 0) continue;
-            int idle = !b->in_use && b->data != NULL;
-            pthread_mutex_unlock(&b->mutex);
-            if (idle) { victim = b; break; }
-        }
-        if (!victim) break;
-        unlink_and_free_locked(victim);
-    }
-    while (g_count > max_total() && g_head) {
-        struct image_buffer *victim = NULL;
-        for (struct image_buffer *b = g_head; b; b = b->next) {
-            if (pthread_mutex_trylock(&b->mutex) != 0) continue;
-            pthread_mutex_unlock(&b->mutex);
-            victim = b;
-            break;
-        }
+        for (struct image_buffer *b = g_head; b; b = b->next)
+            if (!b->pins && !b->in_use) { victim = b; break; }
         if (!victim) break;
         unlink_and_free_locked(victim);
     }
@@ -101,7 +98,14 @@ static struct image_buffer *new_buffer_locked(const char *path)
     return b;
 }
 
-static struct image_buffer *get_or_create(const char *path, image_buffer_cbr cbr, int *was_created, int claim, int prefetch)
+static void unpin(struct image_buffer *b)
+{
+    pthread_mutex_lock(&g_list_mu);
+    b->pins--;
+    pthread_mutex_unlock(&g_list_mu);
+}
+
+static struct image_buffer *get_or_create(const char *path, image_buffer_cbr cbr, int *was_created, int claim)
 {
     struct image_buffer *b;
     int created = 0;
@@ -110,22 +114,22 @@ static struct image_buffer *get_or_create(const char *path, image_buffer_cbr cbr
     if (!b) {
         b = new_buffer_locked(path);
         created = 1;
-    } else if (!prefetch && b->prefetched) {
+    } else if (b->prefetched) {
         g_pf_hits++;
         b->prefetched = 0;
     }
-    if (b && claim) b->in_use = 1;
-    if (b && created && prefetch) b->prefetched = 1;
+    if (b) {
+        b->pins++;                                           /* cannot be evicted between here and the unpin below */
+        if (claim) b->in_use = 1;
+    }
     pthread_mutex_unlock(&g_list_mu);
     if (was_created) *was_created = created;
     if (!b) return NULL;
 
     pthread_mutex_lock(&b->mutex);                           /* resource_manager.c:111-118 */
-    if (!b->data) {
-        cbr(b);
-        if (prefetch) { __sync_fetch_and_add(&g_pf_built, 1); }
-    }
+    if (!b->data) cbr(b);
     pthread_mutex_unlock(&b->mutex);
+    unpin(b);
     return b;
 }
 
@@ -139,6 +143,17 @@ static int parse_frame_number(const char *path, size_t *digits_at)
     return atoi(dot - 6);
 }
 
+static char *path_of_frame(const char *any_frame_path, size_t digits_at, int n)
+{
+    char *p = strdup(any_frame_path);
+    char num[16];
+    if (!p) return NULL;
+    snprintf(num, sizeof(num), "%06d", n);
+    memcpy(p + digits_at, num, 6);
+    return p;
+}
+
+/* queue the chunks that cover frames n+1 .. n+depth of the clip (chunk c = frames [c*batch, (c+1)*batch)) */
 static void enqueue_following(const char *path, image_buffer_cbr cbr)
 {
     if (g_depth <= 0 || g_nworkers <= 0) return;
@@ -146,23 +161,78 @@ static void enqueue_following(const char *path, image_buffer_cbr cbr)
     int n = parse_frame_number(path, &at);
     if (n < 0) return;
     int limit = g_frame_limit ? g_frame_limit(path) : 0;
+    int last = n + g_depth;
+    if (limit > 0 && last >= limit) last = limit - 1;
+    if (last <= n) return;
     pthread_mutex_lock(&g_q_mu);
-    for (int k = 1; k <= g_depth; k++) {
-        if (limit > 0 && n + k >= limit) break;
-        if (g_q_len == PF_QUEUE_CAP) break;
-        char *p = strdup(path);
-        char num[16];
-        snprintf(num, sizeof(num), "%06d", n + k);
-        memcpy(p + at, num, 6);
+    for (int c = (n + 1) / g_batch; c <= last / g_batch; c++) {
+        int first = c * g_batch, count = g_batch;
+        if (first <= n) { count -= n + 1 - first; first = n + 1; }           /* the rest of the requested frame's own chunk */
+        if (limit > 0 && first + count > limit) count = limit - first;
+        if (count <= 0) continue;
+        /* skip chunks whose frames are all cached (or being built) already, and chunks already queued */
+        int missing = 0;
+        pthread_mutex_lock(&g_list_mu);
+        for (int k = 0; k < count && !missing; k++) {
+            char *p = path_of_frame(path, at, first + k);
+            if (p) { missing = find_locked(p) == NULL; free(p); }
+        }
+        pthread_mutex_unlock(&g_list_mu);
+        if (!missing) continue;
         int dup = 0;
-        for (int i = 0; i < g_q_len && !dup; i++) dup = !strcmp(g_q[(g_q_head + i) % PF_QUEUE_CAP].path, p);
-        if (dup) { free(p); continue; }
+        for (int i = 0; i < g_q_len && !dup; i++) {
+            const struct prefetch_req *r = &g_q[(g_q_head + i) % PF_QUEUE_CAP];
+            dup = r->first <= first && first + count <= r->first + r->count && !strncmp(r->path, path, at);
+        }
+        if (dup || g_q_len == PF_QUEUE_CAP) continue;
         struct prefetch_req *r = &g_q[(g_q_head + g_q_len) % PF_QUEUE_CAP];
-        r->path = p; r->cbr = cbr;
+        r->path = strdup(path);
+        if (!r->path) continue;
+        r->first = first; r->count = count; r->cbr = cbr;
         g_q_len++;
     }
     pthread_cond_broadcast(&g_q_cv);
     pthread_mutex_unlock(&g_q_mu);
+}
+
+/* Build the missing frames of one chunk.  New buffers are created, pinned and locked under the list lock (nobody
+ * else can hold a new buffer's mutex yet), so a reader that asks for one of them meanwhile waits on its mutex. */
+static void build_chunk(const struct prefetch_req *r)
+{
+    size_t at;
+    if (parse_frame_number(r->path, &at) < 0) return;
+    struct image_buffer *bufs[MAX_BATCH];
+    int n = 0;
+    pthread_mutex_lock(&g_list_mu);
+    for (int k = 0; k < r->count && n < MAX_BATCH; k++) {
+        char *p = path_of_frame(r->path, at, r->first + k);
+        if (!p) continue;
+        if (!find_locked(p)) {
+            struct image_buffer *b = new_buffer_locked(p);
+            if (b) {
+                b->pins++;
+                b->prefetched = 1;
+                pthread_mutex_lock(&b->mutex);
+                bufs[n++] = b;
+            }
+        }
+        free(p);
+    }
+    pthread_mutex_unlock(&g_list_mu);
+    if (!n) return;
+    if (g_batch_cbr && n > 1) {
+        g_batch_cbr(bufs, n);
+        __sync_fetch_and_add(&g_pf_batches, 1);
+    } else {
+        for (int k = 0; k < n; k++) r->cbr(bufs[k]);
+    }
+    for (int k = 0; k < n; k++) {
+        if (bufs[k]->data) __sync_fetch_and_add(&g_pf_built, 1);
+        pthread_mutex_unlock(&bufs[k]->mutex);
+    }
+    pthread_mutex_lock(&g_list_mu);
+    for (int k = 0; k < n; k++) bufs[k]->pins--;
+    pthread_mutex_unlock(&g_list_mu);
 }
 
 static void *prefetch_worker(void *arg)
@@ -176,7 +246,7 @@ static void *prefetch_worker(void *arg)
         g_q_head = (g_q_head + 1) % PF_QUEUE_CAP;
         g_q_len--;
         pthread_mutex_unlock(&g_q_mu);
-        get_or_create(r.path, r.cbr, NULL, 0, 1);
+        build_chunk(&r);
         free(r.path);
     }
 }
@@ -184,14 +254,14 @@ static void *prefetch_worker(void *arg)
 struct image_buffer *get_or_create_image_buffer(const char *path, image_buffer_cbr new_buffer_cbr, int *was_created)
 {
     enqueue_following(path, new_buffer_cbr);                 /* start the look-ahead before we block on this frame */
-    return get_or_create(path, new_buffer_cbr, was_created, 1, 0);
+    return get_or_create(path, new_buffer_cbr, was_created, 1);
 }
 
 void release_image_buffer(struct image_buffer *image_buffer)
 {
-    pthread_mutex_lock(&image_buffer->mutex);
+    pthread_mutex_lock(&g_list_mu);
     image_buffer->in_use = 0;
-    pthread_mutex_unlock(&image_buffer->mutex);
+    pthread_mutex_unlock(&g_list_mu);
 }
 
 void release_image_buffer_by_path(const char *path)
@@ -215,13 +285,23 @@ void resource_manager_set_prefetch(int depth, int workers, int (*frame_limit)(co
 {
     resource_manager_shutdown();
     g_frame_limit = frame_limit;
-    g_depth = depth < 0 ? 0 : (depth > 64 ? 64 : depth);
+    g_depth = depth < 0 ? 0 : (depth > 256 ? 256 : depth);
     if (g_depth == 0) return;
-    if (workers <= 0) workers = g_depth < 8 ? g_depth : 8;
+    if (workers <= 0) {
+        workers = (g_depth + g_batch - 1) / g_batch;         /* one worker per chunk in flight */
+        if (g_batch == 1 && workers > 8) workers = 8;
+        if (workers < 2 && g_batch > 1) workers = 2;
+    }
     if (workers > 32) workers = 32;
     g_stop = 0;
     for (g_nworkers = 0; g_nworkers < workers; g_nworkers++)
         if (pthread_create(&g_workers[g_nworkers], NULL, prefetch_worker, NULL)) break;
+}
+
+void resource_manager_set_batch_builder(image_buffer_batch_cbr batch_cbr, int batch)
+{
+    g_batch_cbr = batch_cbr;
+    g_batch = batch < 1 ? 1 : (batch > MAX_BATCH ? MAX_BATCH : batch);
 }
 
 void resource_manager_shutdown(void)
@@ -243,3 +323,5 @@ void resource_manager_prefetch_stats(uint64_t *built, uint64_t *hits)
     if (built) *built = g_pf_built;
     if (hits) *hits = g_pf_hits;
 }
+
+uint64_t resource_manager_prefetch_batches(void) { return g_pf_batches; }

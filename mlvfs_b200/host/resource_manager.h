@@ -30,9 +30,12 @@ struct image_buffer {                 /* reference resource_manager.h:33-43, sam
     pthread_mutex_t mutex;
     int in_use;
     int prefetched;                   /* appended (front-ends never allocate this struct): built by the prefetch queue */
+    int pins;                         /* appended: lookups in progress; a pinned buffer is never evicted */
 };
 
 typedef int (*image_buffer_cbr)(struct image_buffer *);
+/* builds `n` frames of one clip at once (consecutive frame numbers, every buffer locked by the caller) */
+typedef int (*image_buffer_batch_cbr)(struct image_buffer **, int n);
 
 struct image_buffer *get_or_create_image_buffer(const char *path, image_buffer_cbr new_buffer_cbr, int *was_created);
 void release_image_buffer_by_path(const char *path);
@@ -46,9 +49,14 @@ void resource_manager_set_data_free(void (*free_fn)(void *));
 /* --prefetch=N: build up to `depth` following frames ahead with `workers` threads (0 disables).
  * `frame_limit(path)` returns the clip's frame count for a virtual DNG path (or <= 0 if unknown). */
 void resource_manager_set_prefetch(int depth, int workers, int (*frame_limit)(const char *dng_path));
+/* Look-ahead frames are requested in chunks of `batch` consecutive frames and handed to `batch_cbr` as one call
+ * (one device batch on one GPU; frame_builder.c: process_frame_batch).  Call before resource_manager_set_prefetch.
+ * batch <= 1 or batch_cbr == NULL: frame-by-frame look-ahead through the frame callback. */
+void resource_manager_set_batch_builder(image_buffer_batch_cbr batch_cbr, int batch);
 void resource_manager_shutdown(void);
 /* statistics for tests / the frame server: frames built by prefetch workers, cache hits on them */
 void resource_manager_prefetch_stats(uint64_t *built, uint64_t *hits);
+uint64_t resource_manager_prefetch_batches(void);
 
 #ifdef __cplusplus
 }

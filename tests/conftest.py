@@ -87,7 +87,7 @@ def parity_record(name, got, want, tol):
     return rec
 
 
-def reference_frames(tmp_path, clip, nframes, opts):
+def reference_frames(tmp_path, clip, nframes, opts, with_headers=False):
     """Frames of <tmp_path>/<clip> from the unmodified reference's process_frame in a fresh process (tests/refrun.py).
     opts: dict with the fields of struct mlvfs (mlvfs.h:37-46)."""
     import subprocess
@@ -96,4 +96,6 @@ def reference_frames(tmp_path, clip, nframes, opts):
     out = os.path.join(str(tmp_path), "ref_frames.npy")
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "refrun.py"), str(tmp_path), clip, str(nframes), out]
                           + [str(int(opts.get(k, 0))) for k in order])
+    if with_headers:
+        return np.load(out), np.load(out + ".headers.npy")
     return np.load(out)

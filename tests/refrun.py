@@ -32,14 +32,16 @@ def main():
     assert ref.ref_get_frame_headers(os.path.join(mlv_dir, clip).encode(), 0, C.byref(fh))
     w, h = fh.rawi_hdr.xRes, fh.rawi_hdr.yRes
     frames = np.zeros((n, h, w), np.uint16)
+    headers = np.zeros((n, 65536), np.uint8)
     with O.quiet_stdout():
         for i in range(n):
             got = ref.ref_process_frame(f"/{clip}/{stem}_{i:06d}.dng".encode(), frames[i].ctypes.data_as(C.c_void_p),
-                                        frames[i].nbytes, None)
+                                        frames[i].nbytes, headers[i].ctypes.data_as(C.c_void_p))
             if got != frames[i].nbytes:
                 print(f"reference process_frame failed on frame {i}", file=sys.stderr)
                 return 4
     np.save(out, frames)
+    np.save(out + ".headers.npy", headers)
     return 0
 
 

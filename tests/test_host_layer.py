@@ -123,7 +123,7 @@ class ImageBuffer(C.Structure):
 
 ImageBuffer._fields_ = [("next", C.POINTER(ImageBuffer)), ("dng_filename", C.c_char_p), ("header_size", C.c_size_t),
                         ("size", C.c_size_t), ("header", C.c_void_p), ("data", C.c_void_p),
-                        ("mutex", C.c_byte * 40), ("in_use", C.c_int), ("prefetched", C.c_int)]
+                        ("mutex", C.c_byte * 40), ("in_use", C.c_int), ("prefetched", C.c_int), ("pins", C.c_int)]
 CBR = C.CFUNCTYPE(C.c_int, C.POINTER(ImageBuffer))
 
 
@@ -165,7 +165,7 @@ def test_frame_cache_and_prefetch_queue(host):
         b, h = C.c_uint64(), C.c_uint64()
         host.resource_manager_prefetch_stats(C.byref(b), C.byref(h))
         assert b.value >= 10 and h.value >= 10, (b.value, h.value)
-        assert host.get_image_buffer_count() <= 16 + 4 * 4
+        assert host.get_image_buffer_count() <= 4 + 2 * (4 + 1) + 4
         # a cached frame is returned without calling the callback again
         n = len(built)
         path = b"/clip.MLV/clip_%06d.dng" % 19
@@ -173,4 +173,122 @@ def test_frame_cache_and_prefetch_queue(host):
         assert created.value == 0 and len(built) == n
     finally:
         host.resource_manager_set_prefetch(0, 0, None)
+        host.free_all_image_buffers()
+
+
+BATCH_CBR = C.CFUNCTYPE(C.c_int, C.POINTER(C.POINTER(ImageBuffer)), C.c_int)
+
+
+def test_prefetch_in_chunks_through_the_batch_builder(host):
+    """Look-ahead frames are requested in chunks of `batch` consecutive frames; each chunk reaches the batch builder
+    as ONE call holding only the frames that are not cached yet, every frame is built exactly once, and a reader that
+    asks for a frame of a chunk under construction waits for it instead of building it again."""
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    host.resource_manager_set_batch_builder.argtypes = [C.c_void_p, C.c_int]
+    host.resource_manager_prefetch_batches.restype = C.c_uint64
+    singles, batches = [], []
+    lock = threading.Lock()
+
+    def fill(ib):
+        ib.size = 64
+        ib.data = libc.malloc(64)
+        ib.header = libc.malloc(16)
+        ib.header_size = 16
+
+    def build(ib):
+        with lock:
+            singles.append(ib.contents.dng_filename.decode())
+        time.sleep(0.004)
+        fill(ib.contents)
+        return 1
+
+    def build_batch(bufs, n):
+        names = [bufs[k].contents.dng_filename.decode() for k in range(n)]
+        with lock:
+            batches.append(names)
+        time.sleep(0.02)
+        for k in range(n):
+            fill(bufs[k].contents)
+        return 1
+
+    cbr, bcbr = CBR(build), BATCH_CBR(build_batch)
+    nframes = 50
+    limit = C.CFUNCTYPE(C.c_int, C.c_char_p)(lambda p: nframes)
+    host.free_all_image_buffers()
+    before = host.resource_manager_prefetch_batches()
+    host.resource_manager_set_batch_builder(bcbr, 8)
+    host.resource_manager_set_prefetch(16, 0, limit)
+    created = C.c_int()
+    try:
+        for i in range(nframes):
+            path = b"/clip.MLV/clip_%06d.dng" % i
+            ib = host.get_or_create_image_buffer(path, cbr, C.byref(created))
+            assert ib and C.cast(ib, C.POINTER(ImageBuffer)).contents.data
+            host.release_image_buffer_by_path(path)
+        time.sleep(0.1)
+        num = lambda s: int(s[-10:-4])
+        flat = [f for b in batches for f in b]
+        assert sorted(singles + flat) == [f"/clip.MLV/clip_{i:06d}.dng" for i in range(nframes)]     # each exactly once
+        assert len(singles) <= 2                                   # frame 0 (nothing was ahead of it yet), rarely one more
+        for b in batches:
+            ns = [num(f) for f in b]
+            assert ns == list(range(ns[0], ns[0] + len(ns)))       # consecutive frames
+            assert ns[0] // 8 == ns[-1] // 8                       # of one chunk (= one GPU)
+        assert max(len(b) for b in batches) == 8
+        assert host.resource_manager_prefetch_batches() - before == len([b for b in batches if len(b) > 1])
+    finally:
+        host.resource_manager_set_prefetch(0, 0, None)
+        host.resource_manager_set_batch_builder(None, 1)
+        host.free_all_image_buffers()
+
+
+def test_buffers_in_use_or_being_looked_up_are_never_evicted(host):
+    """Readers hold frames (in_use) while a flood of other requests pushes the cache far beyond its soft limit: the
+    held frames keep their data pointer; idle ones are evicted (resource_manager.c:195-227 frees by age only)."""
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+
+    def build(ib):
+        ib.contents.size = 64
+        ib.contents.data = libc.malloc(64)
+        C.memset(ib.contents.data, int(ib.contents.dng_filename[-5:-4]) + 1, 64)
+        ib.contents.header = libc.malloc(16)
+        ib.contents.header_size = 16
+        return 1
+
+    cbr = CBR(build)
+    host.free_all_image_buffers()
+    host.resource_manager_set_prefetch(0, 0, None)
+    created = C.c_int()
+    held = {}
+    try:
+        for i in range(6):                                         # more held frames than the soft limit of 4
+            path = b"/hold.MLV/hold_%06d.dng" % i
+            held[path] = C.cast(host.get_or_create_image_buffer(path, cbr, C.byref(created)), C.POINTER(ImageBuffer))
+        stop = threading.Event()
+
+        def flood(t):
+            k = 0
+            while not stop.is_set():
+                path = b"/flood%d.MLV/flood_%06d.dng" % (t, k % 500)
+                assert host.get_or_create_image_buffer(path, cbr, None)
+                host.release_image_buffer_by_path(path)
+                k += 1
+
+        ts = [threading.Thread(target=flood, args=(t,)) for t in range(4)]
+        [t.start() for t in ts]
+        time.sleep(0.5)
+        stop.set()
+        [t.join() for t in ts]
+        for path, ib in held.items():
+            assert ib.contents.in_use == 1 and ib.contents.dng_filename == path
+            data = C.string_at(ib.contents.data, 64)
+            assert data == bytes([int(path[-5:-4]) + 1]) * 64
+        assert host.get_image_buffer_count() <= 6 + 4 + 4          # held + soft limit + lookups in flight
+        for path in held:
+            host.release_image_buffer_by_path(path)
+    finally:
         host.free_all_image_buffers()
