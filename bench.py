@@ -1,31 +1,34 @@
 #!/usr/bin/env python3
 """bench.py -- DNG frames/s of the MLVFS per-frame raw path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]           our CUDA path (default workload C2)
-  python bench.py --impl reference [...]                        the reference's CPU path (oracle/_ref)
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our CUDA path: headline workload C2 + every other config
+  python bench.py --impl reference [...]                        the reference's CPU path (oracle/_ref), same workloads
   torchrun --nproc-per-node N bench.py --gpus N ...             one rank per GPU, frames sharded by rank
-  python bench.py --workload C1|C2|C3|C4|C5 ...                    the other BASELINE.json configs (not the headline line)
+  python bench.py --workload C1|C2|C3|C4|C5 --only ...           one config as the headline line, nothing else
 
 Headline workload (config.workload): BASELINE.json configs[1] = C2 -- 1920x1080 14-bit uncompressed MLV frames
 with --stripes --bad-pix --cs3x3 (the full single-ISO correction chain), synthetic input (mlvfs_b200/synth.py).
 A "step" is one pass of the hot path over a batch of `frames_per_step` frames.
 
-  value  frames/s with the payloads already resident in HBM (mlvb_process_batch_device), CUDA-event timed
-         on the launching stream, max over ranks.
-  e2e    frames/s through the host-buffer C ABI (mlvb_submit / mlvb_wait): pinned host payload -> H2D ->
-         kernels -> D2H of the finished 16-bit frame, all inside the timed region.
-  roofline      the dominant stage of the workload: algorithmic bytes per launch / its
-                CUDA-event duration measured in the timed region, vs MEASURED_PEAKS.json.
+  value      frames/s with the payloads already resident in HBM (mlvb_process_batch_device), CUDA-event timed
+             on the launching stream, max over ranks.  `sustained` = the same step repeated for >= 1 s.
+  e2e        frames/s through the host-buffer C ABI (mlvb_process_frames, what the --prefetch queue calls): pinned
+             host payloads -> H2D -> kernels -> D2H of the finished 16-bit frames, all inside the timed region.
+  roofline   the dominant stage of the workload: algorithmic bytes per launch / its CUDA-event
+             duration measured in the timed region, vs MEASURED_PEAKS.json.
+  workloads  the other BASELINE.json configs (C1, C3, C4, C5), each with value / e2e / roofline, at every N.
+  host_path  frames/s of the frame-request path itself (mlvb_frames: frame cache -> process_frame -> per-GPU
+             contexts, batched prefetch) in ONE process using all N GPUs, run by rank 0.
   cpu_baseline  the unmodified reference (oracle/_ref, process_frame) on this box's host cores on a
-                bounded sample of the same workload (falls back to the oracle port if _ref is absent).
+                bounded sample of the headline workload (falls back to the oracle port if _ref is absent).
 
 The oracle is used here only as the CPU baseline / reference arm, never on the measured GPU path.
 """
 import argparse
-import collections
 import ctypes as C
 import json
 import os
+import subprocess
 import sys
 import tempfile
 import threading
@@ -40,33 +43,57 @@ sys.path.insert(0, ROOT)
 # pixel of the whole chain and of the dominant stage
 WORKLOADS = {
     "C1": dict(w=1920, h=1080, opts={}, variant={}, codec="raw", chain_bpp=3.75, stage="unpack", stage_bpp=3.75,
-               desc="C1: 1920x1080 14-bit uncompressed MLV, plain unpack -> DNG", frames=256,
-               kernel="unpack_groups_kernel<14>"),
+               desc="C1: 1920x1080 14-bit uncompressed MLV, plain unpack -> DNG", frames=256, e2e_chunk=32,
+               kernel="unpack_groups_kernel<14>", cli=[]),
     "C2": dict(w=1920, h=1080, opts=dict(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=1),
                variant=dict(hot_cold=True, stripes=True), codec="raw", chain_bpp=3.75, stage="chroma", stage_bpp=3.75,
-               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256,
-               kernel="fused3_wide_kernel (unpack + bad-pixel patches + 3x3 median chroma smoothing + stripes, one pass; persistent, EV tables in shared memory)"),
+               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256, e2e_chunk=32,
+               kernel="fused3_wide_kernel (unpack + bad-pixel patches + 3x3 median chroma smoothing + stripes, one pass; persistent, EV tables in shared memory)",
+               cli=["--cs3x3", "--bad-pix", "--stripes"]),
     "C3": dict(w=3840, h=1536, opts=dict(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5),
                variant=dict(dual_iso=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
-               desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=8,
-               kernel="dual-ISO stage (statistics + mean23 + 2x cs5x5 on 20-bit planes + alias map + blend)"),
+               desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=8, e2e_chunk=8,
+               kernel="dual-ISO stage (statistics + mean23 + 2x cs5x5 on 20-bit planes + alias map + blend)",
+               cli=["--dual-iso", "--mean23", "--cs5x5"]),
     "C4": dict(w=5760, h=3240, opts=dict(dual_iso=2, hdr_interpolation_method=0, fix_bad_pixels=2),
                variant=dict(dual_iso=True, hot_cold=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
-               desc="C4: 5760x3240 14-bit dual-ISO MLV, --dual-iso --amaze-edge --alias-map --really-bad-pix", frames=4,
-               kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)"),
+               desc="C4: 5760x3240 14-bit dual-ISO MLV, --dual-iso --amaze-edge --alias-map --really-bad-pix", frames=4, e2e_chunk=4,
+               kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)",
+               cli=["--dual-iso", "--amaze-edge", "--alias-map", "--really-bad-pix"]),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,
-               desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=64,
-               kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + wavefront prediction + untile, 14 launches)"),
+               desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=64, e2e_chunk=16,
+               kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + separated predictor-6 scans + untile)",
+               cli=[]),
 }
 METRIC = "DNG frames/sec per B200 and at 1/2/4/8 GPUs; achieved HBM GB/s vs peak"   # BASELINE.json metric
+DTYPE = "u16 pixels / int32 EV-LUT arithmetic (dual-ISO configs: + fp64 blends, fp32 AMaZE)"
+
+
+def config_of(wl, frames_per_step, world):
+    """The `config` object: the same keys and values in both arms (the driver compares them)."""
+    return {"workload": wl["desc"], "frames_per_step": frames_per_step,
+            "sharding": f"frames by rank, {world} rank(s), no collective",
+            "cache": "inputs + outputs of a step exceed the 126 MB L2 (no flush needed)"
+                     if frames_per_step * wl["chain_bpp"] * wl["w"] * wl["h"] > 252e6 else "inputs + outputs of a step fit L2 partly: warm-cache"}
 
 
 def measured_traffic(workload, frames):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), with its
+    source -- a profile constant, not measured in this run -- or (None, None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f).get(workload)
-        return float(t["dram_bytes_per_frame"]) * frames if t else None
+        return (float(t["dram_bytes_per_frame"]) * frames, t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
+
+
+def profile_fractions(workload):
+    """Issue / ALU-pipe fractions of the dominant kernel from the committed ncu summaries (profiles/ncu_fractions.json),
+    for the stages that are not HBM-bound; constants with their source, not measured in this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_fractions.json")) as f:
+            return json.load(f).get(workload)
     except Exception:
         return None
 
@@ -129,6 +156,17 @@ def make_frames(wl, n):
     return [synth.make_frame(wl["w"], wl["h"], i, **wl["variant"]) for i in range(n)]
 
 
+_PAYLOADS = {}
+
+
+def distinct_payloads(wl):
+    """The workload's distinct synthetic payloads (generated once per process: 18 MP frames take seconds in numpy)."""
+    key = wl["desc"]
+    if key not in _PAYLOADS:
+        _PAYLOADS[key] = make_payloads(wl, make_frames(wl, distinct_frames(wl)))
+    return _PAYLOADS[key]
+
+
 def make_payloads(wl, frames):
     """VIDF payloads as uint8 rows of a common 16-byte aligned stride (+1 KiB tail for LJ92 staging)."""
     from mlvfs_b200 import synth
@@ -149,26 +187,36 @@ def headers_for(wl):
     return F.make_frame_headers(wl["w"], wl["h"], video_class=vc)
 
 
+def distinct_frames(wl):
+    return 4 if wl["w"] * wl["h"] > 4e6 else 8
+
+
+def write_clip(wl, path, nframes):
+    """A synthetic MLV of `nframes` VIDF blocks cycling through the workload's distinct frames."""
+    from mlvfs_b200 import synth
+    nd = distinct_frames(wl)
+    payloads, sizes = distinct_payloads(wl)
+    blobs = [payloads[i, :sizes[i]].tobytes() for i in range(nd)]
+    synth.write_mlv(path, (blobs[i % nd] for i in range(nframes)), headers_for(wl))
+
+
 # ----------------------------------------------------------------------------------------------
 # reference / CPU arm
 
 def reference_runner(wl):
     """Returns (kind, threads, fn(nframes) -> seconds) timing the reference CPU path on this workload."""
-    from mlvfs_b200 import synth
     from oracle import pyoracle as O
     ref = O.load_ref()
     cores = os.cpu_count() or 1
     hdr = headers_for(wl)
     ri = hdr.rawi_hdr.raw_info
     npix = wl["w"] * wl["h"]
-    nclip = 4 if npix > 4e6 else 8
-    frames = make_frames(wl, nclip)
+    nclip = distinct_frames(wl)
     o = wl["opts"]
     if ref is not None:
         threads = min(cores, 32)
         tmp = tempfile.mkdtemp(prefix="mlvb_ref_")
-        payloads, sizes = make_payloads(wl, frames)
-        synth.write_mlv(os.path.join(tmp, "W.MLV"), (payloads[i, :sizes[i]].tobytes() for i in range(nclip)), hdr)
+        write_clip(wl, os.path.join(tmp, "W.MLV"), nclip)
         ref.ref_set_mlv_dir(tmp.encode())
         ref.ref_set_options(o.get("chroma_smooth", 0), o.get("fix_bad_pixels", 0), o.get("fix_stripes", 0), o.get("dual_iso", 0),
                             o.get("hdr_interpolation_method", 0), o.get("hdr_no_fullres", 0), o.get("hdr_no_alias_map", 0),
@@ -206,6 +254,7 @@ def reference_runner(wl):
     # oracle port (no oracle/_ref on this machine): single-ISO chains only
     threads = min(cores, 16)
     state = {}
+    frames = make_frames(wl, nclip)
     kw = dict(chroma_smooth_method=o.get("chroma_smooth", 0), fix_bad_pixels=o.get("fix_bad_pixels", 0),
               fix_stripes=o.get("fix_stripes", 0))
     if o.get("dual_iso") or wl["codec"] != "raw":
@@ -233,7 +282,8 @@ def reference_runner(wl):
     return "port", threads, run
 
 
-def cpu_baseline(wl, budget_s=12.0):
+def cpu_sample(wl, budget_s):
+    """Bounded sample of the reference CPU path: about budget_s seconds of frames on all host threads."""
     kind, threads, run = reference_runner(wl)
     n = max(threads, 4)
     dt = run(n)                                   # calibration pass doubles as warm-up
@@ -247,166 +297,285 @@ def cpu_baseline(wl, budget_s=12.0):
 def run_reference(args, wl):
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     kind, threads, run = reference_runner(wl)
     per_step = max(threads * 2, 8)
-    run(per_step)
+    for _ in range(max(min(args.warmup, 1), 1)):
+        run(per_step)
     t = 0.0
     for _ in range(args.steps):
         t += run(per_step)
     fps = per_step * args.steps / t
-    print(json.dumps({
+    line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_step": per_step},
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": config_of(wl, args.frames_per_step or wl["frames"], world),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                          "sample": f"{per_step} frames/step x {args.steps} steps on {threads} host threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }
+    if not args.only:
+        others = {}
+        for name in sorted(WORKLOADS):
+            if name == args.workload:
+                continue
+            heavy = bool(WORKLOADS[name]["opts"].get("dual_iso"))
+            others[name] = dict(cpu_sample(WORKLOADS[name], 12.0 if heavy else 5.0), config={"workload": WORKLOADS[name]["desc"]})
+        line["workloads"] = others
+    print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 
-def run_ours(args, wl):
-    import torch
-    import mlvfs_b200 as M
+class Rig:
+    """Per-process state of our arm: device, optional process group, helpers."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- mlvfs_b200 has no CPU path")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- mlvfs_b200 has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
 
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s=1.0, e2e_s=1.5, sample_clocks=False):
+    """One workload on this rank's GPU: device-resident steps (timed + sustained), per-stage times, e2e."""
+    torch = rig.torch
     w, h = wl["w"], wl["h"]
     npix = w * h
-    B = args.frames_per_step or wl["frames"]
+    B = frames_per_step or wl["frames"]
     hdr = headers_for(wl)
     opts = M.Options(**wl["opts"])
-    distinct = min(B, 4 if npix > 4e6 else 8)
-    base, sizes = make_payloads(wl, make_frames(wl, distinct))
+    distinct = min(B, distinct_frames(wl))
+    base, sizes = distinct_payloads(wl)
     stride = base.shape[1]
     packed = np.ascontiguousarray(base[np.arange(B) % distinct])
     in_bytes = float(np.mean(sizes))
-    ctx = M.Context(device=local, slots=args.slots)
+    ctx = M.Context(device=rig.local, slots=slots)
     d_in = torch.from_numpy(packed).cuda()
     d_out = torch.empty((B, npix), dtype=torch.int16, device="cuda")
     stream = torch.cuda.Stream()
-    clip = "bench_%s.MLV" % args.workload
+    clip = "bench_%s.MLV" % name
 
     def step():
         ctx.process_batch_device(hdr, opts, clip, d_in.data_ptr(), stride, stride, d_out.data_ptr(), npix, B, stream.cuda_stream)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    W_ = max(args.warmup, 3)
+    W_ = max(warmup, 3)
     for _ in range(W_):
         step()
-    barrier()
+    rig.barrier()
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(rig.local) if sample_clocks else None
+    if sampler:
+        sampler.start()
     launches0 = ctx.launch_count()
     ctx.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    rig.barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    rig.barrier()
+    ms = rig.max_over_ranks(e0.elapsed_time(e1))
     stages = ctx.profile_end()
     launches = ctx.launch_count() - launches0
-    clocks = sampler.finish()
-    t = torch.tensor([ms], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = B * args.steps * world / (ms * 1e-3)
+    value = B * steps * rig.world / (ms * 1e-3)
 
-    # ---- e2e through the host-buffer ABI: pinned payloads in, finished frames out
+    # ---- sustained: the same step back to back for >= sustain_s (clocks and power settle; a 12 ms region cannot show that)
+    n_sus = max(steps, int(np.ceil(sustain_s * 1e3 / max(ms / steps, 1e-3))))
+    rig.barrier()
+    e0.record(stream)
+    for _ in range(n_sus):
+        step()
+    e1.record(stream)
+    rig.barrier()
+    ms_sus = rig.max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.finish() if sampler else None
+    sustained = {"value": B * n_sus * rig.world / (ms_sus * 1e-3), "unit": "frames/s", "steps": n_sus, "seconds": ms_sus * 1e-3}
+
+    # ---- e2e through the host-buffer ABI: pinned payloads in, finished frames out, chunks of frames per call
+    chunk = min(wl["e2e_chunk"], B)
+    nthreads = 3
     pin_in = M.PinnedBuffer(B * stride)
     pin_in.array[:] = packed.reshape(-1)
-    depth = args.slots
-    pin_out = [M.PinnedBuffer(npix * 2) for _ in range(depth)]
+    pin_out = [M.PinnedBuffer(chunk * npix * 2) for _ in range(nthreads)]
+    hdrs = [hdr] * chunk
+    nbytes = [sizes[f % distinct] for f in range(B)]
+    nchunks = B // chunk
+    errors = []
 
-    def e2e_step():
-        q = collections.deque()
-        for f in range(B):
-            if len(q) == depth:
-                ctx.wait(q.popleft())
-            tk = ctx.submit(hdr, C.c_void_p(pin_in.ptr + f * stride), stride, opts, clip, C.c_void_p(pin_out[f % depth].ptr))
-            if tk < 0:
-                raise RuntimeError(f"mlvb_submit failed: {tk}")
-            q.append(tk)
-        while q:
-            ctx.wait(q.popleft())
+    def e2e_pass():
+        """All B frames once: nthreads host threads, each pushing whole chunks through mlvb_process_frames."""
+        nxt = iter(range(nchunks))
+        lock = threading.Lock()
 
-    light = wl["codec"] == "raw" and not wl["opts"].get("dual_iso")
-    e2e_steps = max(1, min(args.steps, int(np.ceil(2000 / B)))) if light else 1
-    e2e_step()
-    barrier()
+        def worker(t):
+            dsts = [pin_out[t].ptr + k * npix * 2 for k in range(chunk)]
+            while True:
+                with lock:
+                    c = next(nxt, None)
+                if c is None:
+                    return
+                f0 = c * chunk
+                rc, _ = ctx.process_frames(hdrs, [pin_in.ptr + (f0 + k) * stride for k in range(chunk)], nbytes[f0:f0 + chunk],
+                                           opts, clip, dsts)
+                if rc != 0:
+                    errors.append(rc)
+
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(min(nthreads, nchunks))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    e2e_pass()                                            # warm-up: buffers, batch slots
+    t0 = time.perf_counter()
+    e2e_pass()
+    one_pass = time.perf_counter() - t0
+    e2e_steps = max(1, int(np.ceil(e2e_s / max(one_pass, 1e-4))))
+    rig.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
+        e2e_pass()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device="cuda")
-    if dist is not None:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = B * e2e_steps * world / float(t.item())
+    dt = rig.max_over_ranks(time.perf_counter() - t0)
+    if rig.dist is not None:
+        rig.dist.barrier()
+    if errors:
+        raise RuntimeError(f"mlvb_process_frames failed: {errors[:3]}")
+    e2e = nchunks * chunk * e2e_steps * rig.world / dt
     checksum = int(pin_out[0].array.view(np.uint16)[::4099].astype(np.uint64).sum())
 
-    if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        chain_bytes = wl["chain_bpp"] * npix if wl["codec"] == "raw" else in_bytes + 2 * npix
-        roof = None
-        if wl["stage"] in stages:
-            tot_ms, spans = stages[wl["stage"]]
-            per_launch_s = tot_ms * 1e-3 / args.steps          # one step = one batch through this stage
-            stage_bytes = (wl["stage_bpp"] * npix if wl["codec"] == "raw" else in_bytes + 2 * npix) * B
-            achieved = stage_bytes / per_launch_s / 1e9
-            roof = {"bound": "hbm", "kernel": wl["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": measured_traffic(args.workload, B), "peak_source": peak_src, "launch_ms": per_launch_s * 1e3,
-                    "algorithmic_bytes_per_launch": stage_bytes,
-                    "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
-                    "chain_achieved_gbs": chain_bytes * value / world / 1e9,
-                    "chain_frac": chain_bytes * value / world / 1e9 / peak}
-        line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u16 pixels / int32 EV-LUT arithmetic" + (" / fp64 blends" if wl["opts"].get("dual_iso") else ""),
-            "data": "synthetic",
-            "config": {"workload": wl["desc"], "frames_per_step": B, "sharding": f"frames by rank, {world} rank(s), no collective",
-                       "cache": f"inputs+outputs per step {B * chain_bytes / 1e6:.0f} MB "
-                                + ("> 126 MB L2 (no flush needed)" if B * chain_bytes > 252e6 else "(fits L2: treat as warm-cache)")},
-            "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * in_bytes), "d2h_bytes_per_step": B * npix * 2,
-                    "frames_in_flight": depth, "steps": e2e_steps, "checksum": checksum},
-            "gpu_launches": launches,
-            "roofline": roof,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(line))
+    res = {"value": value, "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": B, "steps": steps,
+           "sustained": sustained, "gpu_launches": launches,
+           "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(sum(nbytes[:nchunks * chunk])),
+                   "d2h_bytes_per_step": nchunks * chunk * npix * 2, "frames_per_call": chunk, "host_threads": min(nthreads, nchunks),
+                   "steps": e2e_steps, "seconds": dt, "api": "mlvb_process_frames (pinned host buffers)", "checksum": checksum}}
+    if clocks is not None:
+        res["clocks"] = clocks
+    peak, peak_src = measured_peak_gbs()
+    chain_bytes = wl["chain_bpp"] * npix if wl["codec"] == "raw" else in_bytes + 2 * npix
+    if wl["stage"] in stages:
+        tot_ms, spans = stages[wl["stage"]]
+        per_launch_s = tot_ms * 1e-3 / steps              # one step = one batch through this stage
+        stage_bytes = (wl["stage_bpp"] * npix if wl["codec"] == "raw" else in_bytes + 2 * npix) * B
+        achieved = stage_bytes / per_launch_s / 1e9
+        traffic, traffic_src = measured_traffic(name, B)
+        res["roofline"] = {"bound": "hbm", "kernel": wl["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                           "launch_ms": per_launch_s * 1e3, "algorithmic_bytes_per_launch": stage_bytes,
+                           "stage_ms_per_step": {k: v[0] / steps for k, v in stages.items()},
+                           "chain_achieved_gbs": chain_bytes * value / rig.world / 1e9,
+                           "chain_frac": chain_bytes * value / rig.world / 1e9 / peak,
+                           "sustained_chain_frac": chain_bytes * sustained["value"] / rig.world / 1e9 / peak}
+        fr = profile_fractions(name)
+        if fr:
+            res["roofline"]["not_hbm_bound"] = fr
     for p in pin_out:
         p.free()
     pin_in.free()
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return res
+
+
+def host_path(wl, gpus, nframes, prefetch=48, batch=16, readers=4, repeat=3):
+    """mlvb_frames (the frame-request path: frame cache -> process_frame -> per-GPU contexts with batched prefetch) on a
+    synthetic clip, ONE process using `gpus` GPUs.  Returns its JSON report."""
+    exe = os.path.join(ROOT, "mlvfs_b200", "mlvb_frames")
+    if not os.path.exists(exe):
+        return {"unavailable": "mlvfs_b200/mlvb_frames is not built"}
+    import shutil
+    need = int(1.1 * nframes * wl["w"] * wl["h"] * 1.75) + (64 << 20)
+    base = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.access(cand, os.W_OK) and shutil.disk_usage(cand).free > need:
+                base = cand
+                break
+        except OSError:
+            pass
+    if base is None:
+        return {"unavailable": f"no scratch directory with {need >> 20} MiB free for the synthetic clip"}
+    with tempfile.TemporaryDirectory(prefix="mlvb_host_", dir=base) as d:
+        write_clip(wl, os.path.join(d, "H.MLV"), nframes)
+        cmd = [exe, d, "H.MLV"] + wl["cli"] + [f"--prefetch={prefetch}", f"--batch={batch}", f"--readers={readers}", f"--gpus={gpus}",
+                                              f"--repeat={repeat}"]
+        try:
+            out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
+            rep = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as e:                                 # noqa: BLE001
+            return {"unavailable": f"mlvb_frames failed: {e}"}
+    return {"value": rep["sustained_fps"], "unit": "frames/s", "first_pass_fps": rep["fps"], "gpus": rep["gpus"], "frames": rep["frames"],
+            "passes": rep["passes"], "failed": rep["failed"], "prefetch": prefetch, "batch": batch, "readers": readers,
+            "device_batches": rep["device_batches"],
+            "what": "mlvb_frames: get_or_create_image_buffer -> process_frame / process_frame_batch, one process, clip in page cache"}
+
+
+def run_ours(args, wl):
+    import mlvfs_b200 as M
+    rig = Rig()
+    head = measure(rig, M, args.workload, wl, args.steps, args.warmup, args.slots, args.frames_per_step, sample_clocks=True)
+    others = {}
+    if not args.only:
+        for name in sorted(WORKLOADS):
+            if name == args.workload:
+                continue
+            o = WORKLOADS[name]
+            heavy = bool(o["opts"].get("dual_iso"))
+            r = measure(rig, M, name, o, steps=3 if heavy else 10, warmup=3, slots=args.slots, sustain_s=1.0, e2e_s=1.5)
+            r["config"] = {"workload": o["desc"], "frames_per_step": r.pop("frames_per_step")}
+            others[name] = r
+    hp = None
+    if not args.only and not args.no_host_path:
+        # the frame-request path in ONE process over all of this job's GPUs; the other ranks wait at the barrier
+        if rig.rank == 0:
+            hp = {args.workload: host_path(wl, rig.world, 256)}
+            if rig.world > 1:
+                hp[args.workload + "_1gpu"] = host_path(wl, 1, 256)
+            hp["C4"] = host_path(WORKLOADS["C4"], rig.world, 8 * rig.world, prefetch=8, batch=4, readers=4, repeat=2)
+        rig.barrier()
+    if rig.rank == 0:
+        B = head.pop("frames_per_step")
+        line = {
+            "metric": METRIC, "value": head["value"], "unit": "frames/s", "n_gpus": rig.world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": config_of(wl, B, rig.world),
+            "clocks": head.get("clocks"), "sustained": head["sustained"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": head.get("roofline"),
+        }
+        if others:
+            line["workloads"] = others
+        if hp:
+            line["host_path"] = hp
+        if rig.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample(wl, 10.0)
+        print(json.dumps(line))
+    if rig.dist is not None:
+        rig.dist.destroy_process_group()
 
 
 def main():
@@ -416,9 +585,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--only", action="store_true", help="only the headline workload: no other configs, no host path")
     ap.add_argument("--frames-per-step", type=int, default=0)
     ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-path", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

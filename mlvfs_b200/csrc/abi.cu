@@ -97,12 +97,13 @@ size_t aux_bytes_for(const FrameGeom &g, const mlvb_options &opts)
     return need;
 }
 
-Slot *acquire_slot(mlvb_context *ctx)
+Slot *acquire_slot(mlvb_context *ctx, bool may_block)
 {
     std::unique_lock<std::mutex> lk(ctx->mu);
     for (;;) {
         for (auto &c : ctx->slots)
             if (!c.busy) { c.busy = true; c.ticket = ctx->next_ticket++; return &c; }
+        if (!may_block) return nullptr;
         ctx->cv.wait(lk);
     }
 }
@@ -592,8 +593,19 @@ static void submit_worker(mlvb_context *ctx)
 
 constexpr int SUBMIT_WORKERS = 4;
 
+constexpr mlvb_ticket SUBMIT_WOULD_BLOCK = -100;          // internal: no free slot and the caller asked not to wait
+
+static mlvb_ticket submit_frame(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
+                                const mlvb_options *opts, const char *mlv_filename, uint16_t *dst, bool may_block);
+
 mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
                         const mlvb_options *opts, const char *mlv_filename, uint16_t *dst)
+{
+    return submit_frame(ctx, hdr, payload, payload_bytes, opts, mlv_filename, dst, true);
+}
+
+static mlvb_ticket submit_frame(mlvb_context *ctx, const struct frame_headers *hdr, const void *payload, size_t payload_bytes,
+                                const mlvb_options *opts, const char *mlv_filename, uint16_t *dst, bool may_block)
 {
     if (!ctx || !hdr || !payload || !opts || !dst) return MLVB_ERR_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MLVB_ERR_CUDA;
@@ -619,7 +631,8 @@ mlvb_ticket mlvb_submit(mlvb_context *ctx, const struct frame_headers *hdr, cons
         lzma_hdr.file_hdr.videoClass &= ~MLVB_VIDEO_CLASS_FLAG_LZMA;
     }
 
-    Slot *s = acquire_slot(ctx);
+    Slot *s = acquire_slot(ctx, may_block);
+    if (!s) return SUBMIT_WOULD_BLOCK;
     auto fail = [&](int rc) -> mlvb_ticket { release_slot(ctx, s); return rc; };
     int rc = slot_reserve(*s, std::max(payload_bytes, lzma_out), frame_bytes);
     if (rc) return fail(rc);
@@ -761,23 +774,30 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
                  !(hdrs[0].file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LZMA);
     for (int f = 1; f < nframes && batch; f++) batch = same_batch_shape(hdrs[0], hdrs[f]);
     if (!batch) {
-        const int depth = (int)ctx->slots.size();
-        std::vector<mlvb_ticket> tk(nframes, -1);
+        // Several threads may be in here at once, sharing the context's slots: a thread that already has frames in
+        // flight never WAITS for a slot (two such threads could wait for each other for ever) -- it retires its own
+        // oldest frame instead and tries again.
+        std::deque<std::pair<int, mlvb_ticket>> inflight;
         int rc_all = MLVB_OK;
-        for (int f = 0; f < nframes + depth; f++) {
-            const int done = f - depth;
-            if (done >= 0 && tk[done] >= 0) {
-                const int rc = mlvb_wait(ctx, tk[done], results ? &results[done] : nullptr);
-                if (rc) rc_all = rc;
+        auto retire_oldest = [&] {
+            const int f = inflight.front().first;
+            const int rc = mlvb_wait(ctx, inflight.front().second, results ? &results[f] : nullptr);
+            inflight.pop_front();
+            if (rc) rc_all = rc;
+        };
+        for (int f = 0; f < nframes; f++) {
+            mlvb_ticket t;
+            for (;;) {
+                t = submit_frame(ctx, &hdrs[f], payloads[f], payload_bytes[f], opts, mlv_filename, dsts[f], inflight.empty());
+                if (t != SUBMIT_WOULD_BLOCK) break;
+                retire_oldest();
             }
-            if (f < nframes) {
-                tk[f] = mlvb_submit(ctx, &hdrs[f], payloads[f], payload_bytes[f], opts, mlv_filename, dsts[f]);
-                if (tk[f] < 0) {
-                    rc_all = (int)tk[f];
-                    if (results) { results[f] = mlvb_frame_result(); results[f].status = (int)tk[f]; }
-                }
-            }
+            if (t < 0) {
+                rc_all = (int)t;
+                if (results) { results[f] = mlvb_frame_result(); results[f].status = (int)t; }
+            } else inflight.emplace_back(f, t);
         }
+        while (!inflight.empty()) retire_oldest();
         return rc_all;
     }
 

@@ -244,7 +244,7 @@ int apply_pixel_list(mlvb_context *ctx, const PixelList &L, uint16_t *d_img, con
                      int dual_iso, int edge_rules, cudaStream_t st);
 
 // slot lease for the synchronous drop-in entry points (dropin.cu)
-Slot *acquire_slot(mlvb_context *ctx);
+Slot *acquire_slot(mlvb_context *ctx, bool may_block = true);   // nullptr only when !may_block and every slot is busy
 void release_slot(mlvb_context *ctx, Slot *s);
 int slot_reserve(Slot &s, size_t packed_bytes, size_t frame_bytes);
 int reserve_device(void **p, size_t *cap, size_t bytes);
