@@ -361,7 +361,8 @@ class Rig:
         return float(t.item())
 
 
-def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s=1.0, e2e_s=1.5, sample_clocks=False):
+def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s=1.0, e2e_s=1.5, sample_clocks=False,
+            e2e_threads=3, e2e_chunk=0):
     """One workload on this rank's GPU: device-resident steps (timed + sustained), per-stage times, e2e."""
     torch = rig.torch
     w, h = wl["w"], wl["h"]
@@ -418,8 +419,8 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     sustained = {"value": B * n_sus * rig.world / (ms_sus * 1e-3), "unit": "frames/s", "steps": n_sus, "seconds": ms_sus * 1e-3}
 
     # ---- e2e through the host-buffer ABI: pinned payloads in, finished frames out, chunks of frames per call
-    chunk = min(wl["e2e_chunk"], B)
-    nthreads = 3
+    chunk = min(e2e_chunk or wl["e2e_chunk"], B)
+    nthreads = e2e_threads
     pin_in = M.PinnedBuffer(B * stride)
     pin_in.array[:] = packed.reshape(-1)
     pin_out = [M.PinnedBuffer(chunk * npix * 2) for _ in range(nthreads)]
@@ -502,7 +503,7 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     return res
 
 
-def host_path(wl, gpus, nframes, prefetch=48, batch=16, readers=4, repeat=3):
+def host_path(wl, gpus, nframes, prefetch=96, batch=16, readers=4, repeat=3):
     """mlvb_frames (the frame-request path: frame cache -> process_frame -> per-GPU contexts with batched prefetch) on a
     synthetic clip, ONE process using `gpus` GPUs.  Returns its JSON report."""
     exe = os.path.join(ROOT, "mlvfs_b200", "mlvb_frames")
@@ -538,7 +539,8 @@ def host_path(wl, gpus, nframes, prefetch=48, batch=16, readers=4, repeat=3):
 def run_ours(args, wl):
     import mlvfs_b200 as M
     rig = Rig()
-    head = measure(rig, M, args.workload, wl, args.steps, args.warmup, args.slots, args.frames_per_step, sample_clocks=True)
+    head = measure(rig, M, args.workload, wl, args.steps, args.warmup, args.slots, args.frames_per_step, sample_clocks=True,
+                   e2e_threads=args.e2e_threads, e2e_chunk=args.e2e_chunk)
     others = {}
     if not args.only:
         for name in sorted(WORKLOADS):
@@ -590,6 +592,8 @@ def main():
     ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-path", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=3)
+    ap.add_argument("--e2e-chunk", type=int, default=0)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

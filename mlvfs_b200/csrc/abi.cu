@@ -811,6 +811,7 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
 
     BatchSlot *b = acquire_batch_slot(ctx);
     cudaStream_t st = b->stream;
+    bool per_frame_status = false;                       // results[] already tell which frames failed
     int rc = [&]() -> int {
         int r = reserve_device((void **)&b->d_in, &b->in_cap, stride * nframes + 1024);
         if (!r) r = reserve_device((void **)&b->d_work, &b->work_cap, frame_px * 2 * nframes);
@@ -851,14 +852,16 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
             }
             if (results) { results[f] = res0; results[f].status = s; }
         }
+        per_frame_status = true;
         return rr;
     }();
-    if (rc && rc != MLVB_ERR_ARG) cudaStreamSynchronize(st);
-    else if (rc) cudaStreamSynchronize(st);
+    if (rc && !per_frame_status) {
+        cudaStreamSynchronize(st);                       // nothing of this batch may still be running when the slot is reused
+        if (results)
+            for (int f = 0; f < nframes; f++) { results[f] = mlvb_frame_result(); results[f].status = rc; }
+    }
     ctx->path_count[2] += 1;
     release_batch_slot(ctx, b);
-    if (rc && results)
-        for (int f = 0; f < nframes; f++) if (results[f].status == MLVB_OK) results[f].status = rc;
     return rc;
 }
 
