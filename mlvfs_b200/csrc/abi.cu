@@ -897,7 +897,7 @@ int mlvb_process_batch_device(mlvb_context *ctx, const struct frame_headers *hdr
         // a compressed batch reports corrupt streams synchronously (the decode dwarfs the sync)
         std::vector<int> status(nframes);
         MLVB_CUDA_OK(cudaMemcpyAsync(status.data(), ctx->d_batch_status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
-        MLVB_CUDA_OK(cudaStreamSynchronize(st));
+        MLVB_CUDA_OK(stream_wait(ctx, st));
         for (int f = 0; f < nframes; f++)
             if (status[f] != 0) { fprintf(stderr, "libmlvfs_b200: LJ92: frame %d failed (%d)\n", f, status[f]); rc = MLVB_ERR_ARG; }
     }

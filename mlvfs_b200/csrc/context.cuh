@@ -177,6 +177,24 @@ struct mlvb_context {
     int ensure_stat(size_t bytes);
 };
 
+// Wait for a stream from a host thread.  cudaStreamSynchronize spins by default, which costs a core per waiting
+// thread; the per-frame statistics read-backs of the dual-ISO path wait five times per frame on several threads
+// per GPU.  With blocking_sync the wait sleeps on a per-thread blocking event instead.
+inline cudaError_t stream_wait(const mlvb_context *ctx, cudaStream_t st)
+{
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(st);
+    constexpr int MAX_DEV = 64;
+    thread_local cudaEvent_t ev[MAX_DEV] = {};
+    const int dev = ctx->device;
+    if (dev < 0 || dev >= MAX_DEV) return cudaStreamSynchronize(st);
+    if (!ev[dev]) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming | cudaEventBlockingSync);
+        if (e != cudaSuccess) { ev[dev] = nullptr; return e; }
+    }
+    cudaError_t e = cudaEventRecord(ev[dev], st);
+    return e == cudaSuccess ? cudaEventSynchronize(ev[dev]) : e;
+}
+
 // stage ids reported by mlvb_profile_end
 enum { ST_UNPACK = 0, ST_PIXFIX = 1, ST_CHROMA = 2, ST_STRIPES = 3, ST_PATTERN = 4, ST_DUALISO = 5, ST_LJ92 = 6, ST_COUNT = 8 };
 

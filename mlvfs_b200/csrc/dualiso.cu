@@ -752,7 +752,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     uint8_t *hostA = (uint8_t *)stage.p;
     unsigned *hw = (unsigned *)(hostA + sizeof(StatsA)), *he = hw + 2 * 65536, *scores = he + 2 * HB;
     MLVB_CUDA_OK(cudaMemcpyAsync(hostA, D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     const StatsA *A = (const StatsA *)hostA;
 
     // identify_rggb_or_gbrg (hdr.c:467-494)
@@ -782,7 +782,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     if (ny_w > 0) diso_white_kernel<<<dim3(ceil_div(nx, 128), ny_w), 128, 0, st>>>(d_img, w, h, F, max_pix, n_class[0], n_class[1], D.hist_white);
     ctx->launches += 1;
     MLVB_CUDA_OK(cudaMemcpyAsync(hw, D.hist_white, 2 * 65536 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     int whites[2];
     for (int c = 0; c < 2; c++) {
         const long long kept = std::min<long long>(n_class[c], std::max(max_pix, 0));
@@ -812,7 +812,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     if (ngrid) diso_expo_pairs_kernel<<<dim3(ceil_div(nx, 128), ny_e), 128, 0, st>>>(d_img, w, h, F, E, D.pairs, D.hist_expo, HB);
     ctx->launches += 1;
     MLVB_CUDA_OK(cudaMemcpyAsync(he, D.hist_expo, 2 * HB * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     long long n = 0;
     for (int i = 0; i < HB; i++) n += he[i];
     auto med_idx = [](long long m) { return (m & 1) ? m / 2 : m / 2 - 1; };
@@ -833,7 +833,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     if (ncand > 4095) return MLVB_ERR_ARG;
     MLVB_CUDA_OK(cudaMemcpyAsync(scores, D.scores, ncand * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaMemcpyAsync(scores + ncand, D.nsel, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     const unsigned nsel = scores[ncand];
     if (nsel >= hi_cap && hi_cap > 0) {
         // the reference truncates its highlight list in raster order here (hdr.c:727-745); not reproduced
@@ -883,7 +883,7 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
             MLVB_CUDA_OK(cudaMalloc(&S->d_fullres_lim, 4 * sizeof(int)));
             diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(S->d_fullres_lim);
             diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(S->d_fullres_curve, S->d_fullres_lim, black);
-            MLVB_CUDA_OK(cudaStreamSynchronize(st));                    // complete before the set is published to other streams
+            MLVB_CUDA_OK(stream_wait(ctx, st));                            // complete before the set is published to other streams
             ctx->launches += 1;
             S->black = black; S->white = white;
             if (T->current) T->retired.push_back(std::move(T->current));
@@ -982,7 +982,7 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
     unsigned long long ev_num = 0;
     MLVB_CUDA_OK(cudaMemcpyAsync(&ev_sum, &D.statsA->ev_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
     MLVB_CUDA_OK(cudaMemcpyAsync(&ev_num, &D.statsA->ev_num, sizeof(ev_num), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     const double avg_ev = ev_sum / (double)ev_num;                        // 0/0 -> NaN -> "not HDR" (hdr.c:435-438)
     if (!(avg_ev > 0.5)) return 0;
 

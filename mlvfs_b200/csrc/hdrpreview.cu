@@ -107,7 +107,7 @@ int run_hdr_preview(mlvb_context *ctx, const struct frame_headers *hdr, const Fr
     ctx->launches += 1;
     std::vector<unsigned> hist(nb);
     MLVB_CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist, nb * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     unsigned count[4] = {0, 0, 0, 0};
     for (int y = 4; y < h - 4; y += 5) count[y % 4] += (unsigned)(w - (y + 1) % 2) / 4;   // histogram.c:58
     int m[4];
@@ -180,7 +180,7 @@ int run_deflicker(mlvb_context *ctx, const FrameGeom &g, const uint16_t *d_img, 
     ctx->launches += 1;
     std::vector<unsigned> hist(white + 1);
     MLVB_CUDA_OK(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));
+    MLVB_CUDA_OK(stream_wait(ctx, st));
     const int median = median_u16_bins(hist.data(), white, count);
     const int black = (uint16_t)g.black;
     const double correction = log2((double)(target - black) / (median - black));
