@@ -362,7 +362,7 @@ class Rig:
 
 
 def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s=1.0, e2e_s=1.5, sample_clocks=False,
-            e2e_threads=4, e2e_chunk=0):
+            e2e_threads=4, e2e_chunk=0, quick=False):
     """One workload on this rank's GPU: device-resident steps (timed + sustained), per-stage times, e2e."""
     torch = rig.torch
     w, h = wl["w"], wl["h"]
@@ -406,6 +406,10 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     launches = ctx.launch_count() - launches0
     value = B * steps * rig.world / (ms * 1e-3)
 
+    if quick:                                             # profiling runs (ncu): the timed steps only
+        ctx.close()
+        return {"value": value, "unit": "frames/s", "ms_per_step": ms / steps, "frames_per_step": B, "steps": steps,
+                "gpu_launches": launches, "stage_ms_per_step": {k: v[0] / steps for k, v in stages.items()}}
     # ---- sustained: the same step back to back for >= sustain_s (clocks and power settle; a 12 ms region cannot show that)
     n_sus = max(steps, int(np.ceil(sustain_s * 1e3 / max(ms / steps, 1e-3))))
     rig.barrier()
@@ -503,7 +507,7 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     return res
 
 
-def host_path(wl, gpus, nframes, prefetch=64, batch=8, readers=8, repeat=3):
+def host_path(wl, gpus, nframes, prefetch=64, batch=8, readers=8, repeat=3, workers=0):
     """mlvb_frames (the frame-request path: frame cache -> process_frame -> per-GPU contexts with batched prefetch) on a
     synthetic clip, ONE process using `gpus` GPUs.  Returns its JSON report."""
     exe = os.path.join(ROOT, "mlvfs_b200", "mlvb_frames")
@@ -524,7 +528,7 @@ def host_path(wl, gpus, nframes, prefetch=64, batch=8, readers=8, repeat=3):
     with tempfile.TemporaryDirectory(prefix="mlvb_host_", dir=base) as d:
         write_clip(wl, os.path.join(d, "H.MLV"), nframes)
         cmd = [exe, d, "H.MLV"] + wl["cli"] + [f"--prefetch={prefetch}", f"--batch={batch}", f"--readers={readers}", f"--gpus={gpus}",
-                                              f"--repeat={repeat}"]
+                                              f"--repeat={repeat}", f"--workers={workers}"]
         try:
             out = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=600)
             rep = json.loads(out.stdout.strip().splitlines()[-1])
@@ -532,13 +536,17 @@ def host_path(wl, gpus, nframes, prefetch=64, batch=8, readers=8, repeat=3):
             return {"unavailable": f"mlvb_frames failed: {e}"}
     return {"value": rep["sustained_fps"], "unit": "frames/s", "first_pass_fps": rep["fps"], "gpus": rep["gpus"], "frames": rep["frames"],
             "passes": rep["passes"], "failed": rep["failed"], "prefetch": prefetch, "batch": batch, "readers": readers,
-            "device_batches": rep["device_batches"],
+            "device_batches": rep["device_batches"], "builder_us_per_frame": rep.get("builder_us_per_frame"),
+            "reader_copy_us_per_frame": rep.get("reader_copy_us_per_frame"),
             "what": "mlvb_frames: get_or_create_image_buffer -> process_frame / process_frame_batch, one process, clip in page cache"}
 
 
 def run_ours(args, wl):
     import mlvfs_b200 as M
     rig = Rig()
+    if args.quick:
+        print(json.dumps(measure(rig, M, args.workload, wl, args.steps, args.warmup, args.slots, args.frames_per_step, quick=True)))
+        return
     head = measure(rig, M, args.workload, wl, args.steps, args.warmup, args.slots, args.frames_per_step, sample_clocks=True,
                    e2e_threads=args.e2e_threads, e2e_chunk=args.e2e_chunk)
     others = {}
@@ -558,7 +566,11 @@ def run_ours(args, wl):
             hp = {args.workload: host_path(wl, rig.world, 256)}
             if rig.world > 1:
                 hp[args.workload + "_1gpu"] = host_path(wl, 1, 256)
-            hp["C4"] = host_path(WORKLOADS["C4"], rig.world, 8 * rig.world, prefetch=8, batch=4, readers=4, repeat=2)
+            # look-ahead deep enough to keep two chunks per GPU in flight
+            hp["C4"] = host_path(WORKLOADS["C4"], rig.world, 12 * rig.world, prefetch=8 * rig.world, batch=4, readers=4, repeat=2,
+                                 workers=2 * rig.world)
+            if rig.world > 1:
+                hp["C4_1gpu"] = host_path(WORKLOADS["C4"], 1, 12, prefetch=8, batch=4, readers=4, repeat=2, workers=2)
         rig.barrier()
     if rig.rank == 0:
         B = head.pop("frames_per_step")
@@ -592,6 +604,7 @@ def main():
     ap.add_argument("--slots", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-path", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="warm-up + timed steps of the headline workload only (for ncu runs)")
     ap.add_argument("--e2e-threads", type=int, default=4)
     ap.add_argument("--e2e-chunk", type=int, default=0)
     args = ap.parse_args()

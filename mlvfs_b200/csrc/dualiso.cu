@@ -234,19 +234,24 @@ struct PixParams {
     AmazeView amz;
 };
 
-// 14 -> 20 bit (hdr.c:825-837) + exposure matching apply (hdr.c:784-808)
-__global__ void diso_to20_kernel(const uint16_t *__restrict__ img, uint32_t *__restrict__ raw32, const PixParams P)
+// 14 -> 20 bit (hdr.c:825-837) + exposure matching apply (hdr.c:784-808), one sample
+__device__ __forceinline__ int to20_sample(uint16_t v, int y, const PixParams &P)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= P.w) return;
-    const size_t i = x + (size_t)y * P.w;
-    int p = (int)(((uint32_t)img[i] << 6) & 0xFFFFF);
+    int p = (int)(((uint32_t)v << 6) & 0xFFFFF);
     if (p != 0) {
         if (P.is_bright[y % 4]) p = (int)((double)(p - P.black) * P.a + (double)P.black + P.b20 * P.a);
         else p = (int)((double)p - P.b20 + P.b20 * P.a);
         p = min(max(p, 0), 0xFFFFF);
     }
-    raw32[i] = (uint32_t)p;
+    return p;
+}
+
+__global__ void diso_to20_kernel(const uint16_t *__restrict__ img, uint32_t *__restrict__ raw32, const PixParams P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.w) return;
+    const size_t i = x + (size_t)y * P.w;
+    raw32[i] = (uint32_t)to20_sample(img[i], y, P);
 }
 
 __device__ __forceinline__ int mean2_ev(int a, int b, int white) { return (a >= white || b >= white) ? white : (a + b) / 2; }
@@ -257,14 +262,17 @@ __device__ __forceinline__ int mean3_ev(int a, int b, int c, int white)
 }
 
 // mean32_interpolate (or the edge-directed interpolation of amaze_interpolate, hdr.c:1182-1210) +
-// border_interpolate + fullres_reconstruction, one thread per pixel
-__global__ void diso_interp_kernel(const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark, uint32_t *__restrict__ bright,
-                                   uint32_t *__restrict__ fullres, const PixParams P)
+// border_interpolate + fullres_reconstruction, one thread per pixel.  FROM14: the 20-bit samples are converted on
+// the fly from the 14-bit frame (the mean23 path reads at most four of them per pixel: no raw32 plane, no extra pass);
+// the AMaZE path keeps the plane, its demosaic stage needs it anyway.
+template <bool FROM14>
+__global__ void diso_interp_kernel(const uint16_t *__restrict__ img14, const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark,
+                                   uint32_t *__restrict__ bright, uint32_t *__restrict__ fullres, const PixParams P)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     const int w = P.w, h = P.h;
     if (x >= w) return;
-#define R(xx, yy) ((int)raw32[(xx) + (size_t)(yy) * w])
+#define R(xx, yy) (FROM14 ? to20_sample(img14[(xx) + (size_t)(yy) * w], (yy), P) : (int)raw32[(xx) + (size_t)(yy) * w])
     const int br = P.is_bright[y % 4];
     uint32_t native, interp;
     // precedence = order of the loops in border_interpolate (hdr.c:1312-1352), later loops win
@@ -272,7 +280,7 @@ __global__ void diso_interp_kernel(const uint32_t *__restrict__ raw32, uint32_t 
     else if (y >= 2 && x >= w - 3) { interp = R(x - 2, y - 2); native = R(x - 2, y); }
     else if (y >= h - 4) { interp = R(x, y - 2); native = R(x, y); }
     else if (y < 3) { interp = R(x, y + 2); native = R(x, y); }
-    else if (P.method == 0) {
+    else if (!FROM14) {
         // edge-directed: average three neighbouring directions in EV space (hdr.c:1198-1206)
         const int s = (P.is_bright[y % 4] == P.is_bright[(y + 1) % 4]) ? -1 : 1;
         const int dir = P.amz.edir[x + (size_t)y * w];
@@ -426,13 +434,11 @@ __global__ void diso_alias2_kernel(const uint16_t *__restrict__ amap, const uint
     aux[i] = (uint16_t)top[5];
 }
 
-// pass 3: the 13-tap "gaussian" with its duplicated terms (hdr.c:1443-1464); writes amap with uint16 wrap
-__global__ void diso_alias3_kernel(const uint16_t *__restrict__ aux, const uint8_t *__restrict__ skip, uint16_t *__restrict__ amap, int w, int h)
+// pass 3: the 13-tap "gaussian" with its duplicated terms (hdr.c:1443-1464), uint16 wrap -- and pass 4: 2x2 max + clamp
+// (hdr.c:1466-1483), one thread per 2x2 block.  Pass 3 reads `aux` only and pass 4 stays inside its own block, so the
+// two run as one kernel: pixels outside pass 3's domain (border, skip mask) keep their pass-1 value in amap.
+__device__ __forceinline__ int alias_gauss(const uint16_t *__restrict__ aux, int x, int y, int w)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x < 6 || x >= w - 6 || y < 6 || y >= h - 6) return;
-    const size_t i = x + (size_t)y * w;
-    if (skip[i]) return;
 #define A(dx, dy) ((int)aux[(x + (dx)) + (size_t)(y + (dy)) * w])
     const int cross = A(0, -2) + A(-2, 0) + A(2, 0) + A(0, 2), diag = A(-2, -2) + A(2, -2) + A(-2, 2) + A(2, 2);
     const int far4 = A(0, -6) + A(-6, 0) + A(6, 0) + A(0, 6);
@@ -440,24 +446,40 @@ __global__ void diso_alias3_kernel(const uint16_t *__restrict__ aux, const uint8
     const int c = A(0, 0) + cross * 820 / 1024 + diag * 657 / 1024 + cross * 421 / 1024 + (2 * diag) * 337 / 1024 + diag * 173 / 1024 +
                   far4 * 139 / 1024 + knight * 111 / 1024 + knight * 57 / 1024;
 #undef A
-    amap[i] = (uint16_t)c;
+    return (int)(uint16_t)c;
 }
 
-// pass 4: 2x2 max, clamp (hdr.c:1466-1483)
-__global__ void diso_alias4_kernel(uint16_t *__restrict__ amap, int w, int h)
+__global__ void diso_alias34_kernel(const uint16_t *__restrict__ aux, const uint8_t *__restrict__ skip, uint16_t *__restrict__ amap, int w, int h)
 {
-    const int x = 2 + 2 * (blockIdx.x * blockDim.x + threadIdx.x), y = 2 + 2 * blockIdx.y;
-    if (x >= w - 2 || y >= h - 2) return;
-    uint16_t *p = amap + x + (size_t)y * w;
-    const int c = min(max(max((int)p[0], (int)p[1]), max((int)p[w], (int)p[w + 1])), ALIAS_MAP_MAX);
-    p[0] = p[1] = p[w] = p[w + 1] = (uint16_t)c;
+    // blocks at even (x, y); pass 4 covers 2 <= x < w - 2, 2 <= y < h - 2, pass 3 covers 6 <= x < w - 6, 6 <= y < h - 6
+    const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x), y = 2 * blockIdx.y;
+    if (x >= w || y >= h) return;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int xx = x + (k & 1), yy = y + (k >> 1);
+        v[k] = -1;
+        if (xx < w && yy < h) {
+            const size_t i = xx + (size_t)yy * w;
+            const bool p3 = xx >= 6 && xx < w - 6 && yy >= 6 && yy < h - 6 && !skip[i];
+            v[k] = p3 ? alias_gauss(aux, xx, yy, w) : (int)amap[i];
+        }
+    }
+    const bool p4 = x >= 2 && x < w - 2 && y >= 2 && y < h - 2;         // then x + 1 < w and y + 1 < h as well (w, h even or not)
+    if (p4 && x + 1 < w && y + 1 < h) {
+        const int c = min(max(max(v[0], v[1]), max(v[2], v[3])), ALIAS_MAP_MAX);
+        v[0] = v[1] = v[2] = v[3] = c;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int xx = x + (k & 1), yy = y + (k >> 1);
+        if (xx < w && yy < h) amap[xx + (size_t)yy * w] = (uint16_t)v[k];
+    }
 }
 
-// 3x3 "blur" of the overexposure flags (hdr.c:1636-1655): in -> out
-__global__ void diso_over_blur_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out, int w, int h)
+// 3x3 "blur" of the overexposure flags (hdr.c:1636-1655), evaluated where final_blend reads it
+__device__ __forceinline__ int over_blurred(const uint16_t *__restrict__ in, int x, int y, int w, int h)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
     const size_t i = x + (size_t)y * w;
     int v = in[i];
     if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
@@ -465,7 +487,7 @@ __global__ void diso_over_blur_kernel(const uint16_t *__restrict__ in, uint16_t 
         v = O(0, 0) + (O(0, -1) + O(-1, 0) + O(1, 0) + O(0, 1)) * 820 / 1024 + (O(-1, -1) + O(1, -1) + O(-1, 1) + O(1, 1)) * 657 / 1024;
 #undef O
     }
-    out[i] = (uint16_t)v;
+    return (int)(uint16_t)v;
 }
 
 // final_blend (hdr.c:1691-1752) + convert_20_to_16bit (hdr.c:1760-1772)
@@ -473,12 +495,13 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
                                   const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint16_t *__restrict__ over,
                                   const uint16_t *__restrict__ amap, uint16_t *__restrict__ out16, const PixParams P)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
-    if (i >= np) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= P.w) return;
+    const size_t i = x + (size_t)y * P.w;
     const int b = (int)bright[i];
     double f = curve_at(P.fullres_curve, P.fullres_lim, b & 0xFFFFF), c = 0.0;
     if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
-    const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
+    const double ovf = fmax(fmin((double)over_blurred(over, x, y, P.w, P.h) / 200.0, 1.0), 0.0);
     c = fmax(c, ovf);
     const double noo = fmax(ovf, 1.0 - f);
     f = fmax(f, c);
@@ -690,18 +713,21 @@ struct PinnedLease {
     void *p = nullptr;
     explicit PinnedLease(DualIsoTables *t) : T(t)
     {
+        if (!T) return;                                   // an empty lease (the caller brings its own)
         {
             std::lock_guard<std::mutex> lk(T->mu);
             if (!T->pinned_free.empty()) { p = T->pinned_free.back(); T->pinned_free.pop_back(); }
         }
         if (!p && cudaHostAlloc(&p, PINNED_STAGE_BYTES, cudaHostAllocDefault) != cudaSuccess) p = nullptr;
     }
-    ~PinnedLease()
+    void release()
     {
         if (!p) return;
         std::lock_guard<std::mutex> lk(T->mu);
         T->pinned_free.push_back(p);
+        p = nullptr;
     }
+    ~PinnedLease() { release(); }
 };
 
 void dual_iso_reset_tables(mlvb_context *ctx)
@@ -714,8 +740,19 @@ void dual_iso_reset_tables(mlvb_context *ctx)
 
 // hdr_interpolate on a device-resident 14-bit frame (in place -> 16-bit).  Returns 1 converted,
 // 0 not dual ISO / failed (frame keeps its 14-bit content), < 0 MLVB_ERR_*.
+static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h, int black14, int interp_method, int use_fullres,
+                                int use_alias_map, int cs_method, void *d_aux, cudaStream_t st, PinnedLease *stats_on_host);
+
 int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int black14, int interp_method, int use_fullres,
                         int use_alias_map, int cs_method, void *d_aux, cudaStream_t st)
+{
+    return hdr_interpolate_impl(ctx, d_img, w, h, black14, interp_method, use_fullres, use_alias_map, cs_method, d_aux, st, nullptr);
+}
+
+// stats_on_host: phase A's statistics of this very frame are already in that pinned stage (run_cr2hdr20 took them in
+// the same pass as hdr_check because no pixel repair runs in between): no second pass over the frame, no second wait
+static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h, int black14, int interp_method, int use_fullres,
+                                int use_alias_map, int cs_method, void *d_aux, cudaStream_t st, PinnedLease *stats_on_host)
 {
     if (w <= 0 || h <= 0) return 0;
     if (w < 16 || h < 16 || (w & 1)) return MLVB_ERR_UNSUPPORTED;
@@ -743,16 +780,19 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     (void)npix_full;
 
     // ---------------- phase A
-    MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    if (launch_stats_a(true, d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA, ctx->sm_count, st))
-        return MLVB_ERR_UNSUPPORTED;
-    ctx->launches += 1;
-    PinnedLease stage(T);
+    PinnedLease own_stage(stats_on_host ? nullptr : T);
+    PinnedLease &stage = stats_on_host ? *stats_on_host : own_stage;
     if (!stage.p) return MLVB_ERR_CUDA;
     uint8_t *hostA = (uint8_t *)stage.p;
     unsigned *hw = (unsigned *)(hostA + sizeof(StatsA)), *he = hw + 2 * 65536, *scores = he + 2 * HB;
-    MLVB_CUDA_OK(cudaMemcpyAsync(hostA, D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(stream_wait(ctx, st));
+    if (!stats_on_host) {
+        MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
+        if (launch_stats_a(true, d_img, w, h, black14, 0x7FFFFFFF, T->d_raw2evf + (MLVB_MAX_BLACK - black14), D.statsA, ctx->sm_count, st))
+            return MLVB_ERR_UNSUPPORTED;
+        ctx->launches += 1;
+        MLVB_CUDA_OK(cudaMemcpyAsync(hostA, D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
+        MLVB_CUDA_OK(stream_wait(ctx, st));
+    }
     const StatsA *A = (const StatsA *)hostA;
 
     // identify_rggb_or_gbrg (hdr.c:467-494)
@@ -905,9 +945,10 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     const size_t np = (size_t)w * h;
     const dim3 g2(ceil_div(w, 256), h);
     const int g1 = ceil_div(np, 256);
-    diso_to20_kernel<<<g2, 256, 0, st>>>(d_img, D.raw32, P);
     P.method = interp_method ? 1 : 0;
     if (P.method == 0) {
+        diso_to20_kernel<<<g2, 256, 0, st>>>(d_img, D.raw32, P);
+        ctx->launches += 1;
         // the GBRG row skip changed h after the scratch was carved for the full frame: re-carve the AMaZE part
         // for this geometry inside the same region (never larger than the full-frame request)
         AmazeScratch A;
@@ -919,9 +960,10 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
         P.amz.red = A.red; P.amz.green = A.green; P.amz.blue = A.blue; P.amz.squeezed = A.squeezed; P.amz.edir = A.edir;
         P.amz.ws = w + 16;
     }
-    diso_interp_kernel<<<g2, 256, 0, st>>>(D.raw32, D.dark, D.bright, D.fullres, P);
+    if (P.method == 0) diso_interp_kernel<false><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
+    else diso_interp_kernel<true><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
     diso_mix_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
-    ctx->launches += 3;
+    ctx->launches += 2;
     const uint32_t *frs = D.fullres, *hrs = D.halfres;
     if (cs_method == 2 || cs_method == 3 || cs_method == 5) {
         int rc;
@@ -941,13 +983,11 @@ int run_hdr_interpolate(mlvb_context *ctx, uint16_t *d_img, int w, int h, int bl
     if (use_alias_map) {
         diso_alias1_kernel<<<g1, 256, 0, st>>>(frs, hrs, D.skip, D.amap, D.aux, P);
         diso_alias2_kernel<<<g2, 256, 0, st>>>(D.amap, D.skip, D.aux, w, h);
-        diso_alias3_kernel<<<g2, 256, 0, st>>>(D.aux, D.skip, D.amap, w, h);
-        diso_alias4_kernel<<<dim3(ceil_div(w / 2, 128), std::max((h - 2) / 2, 1)), 128, 0, st>>>(D.amap, w, h);
-        ctx->launches += 4;
+        diso_alias34_kernel<<<dim3(ceil_div((w + 1) / 2, 128), (h + 1) / 2), 128, 0, st>>>(D.aux, D.skip, D.amap, w, h);
+        ctx->launches += 3;
     }
-    diso_over_blur_kernel<<<g2, 256, 0, st>>>(D.over, D.over2, w, h);
-    diso_final_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
-    ctx->launches += 2;
+    diso_final_kernel<<<g2, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over, D.amap, d_img, P);
+    ctx->launches += 1;
     MLVB_CUDA_OK(cudaGetLastError());
     return 1;
 }
@@ -974,19 +1014,8 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
             MLVB_CUDA_OK(cudaMemcpy(T->d_test_a, T->test_a.data(), T->test_a.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
-    if (launch_stats_a(false, d_img, g.w, g.h, g.black, g.white, T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA, ctx->sm_count, st))
-        return MLVB_ERR_UNSUPPORTED;
-    ctx->launches += 1;
-    double ev_sum = 0;
-    unsigned long long ev_num = 0;
-    MLVB_CUDA_OK(cudaMemcpyAsync(&ev_sum, &D.statsA->ev_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(cudaMemcpyAsync(&ev_num, &D.statsA->ev_num, sizeof(ev_num), cudaMemcpyDeviceToHost, st));
-    MLVB_CUDA_OK(stream_wait(ctx, st));
-    const double avg_ev = ev_sum / (double)ev_num;                        // 0/0 -> NaN -> "not HDR" (hdr.c:435-438)
-    if (!(avg_ev > 0.5)) return 0;
-
-    // fix_focus_pixels(.., 1) and fix_bad_pixels(.., 1): horizontal interpolation only (hdr.c:1944-1948)
+    // fix_focus_pixels(.., 1) and fix_bad_pixels(.., 1) run between hdr_check and the row-field statistics
+    // (hdr.c:1944-1948).  When neither has anything to do, both statistics come from one pass over the frame.
     int rc;
     std::shared_ptr<PixelList> focus, bad;
     {
@@ -994,6 +1023,25 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
         rc = get_focus_pixel_map(ctx, hdr, g, &focus);
         if (rc) return rc;
     }
+    const bool one_pass = !(focus && focus->nlevels) && !fix_bad_pixels_mode;
+    MLVB_CUDA_OK(cudaMemsetAsync(D.statsA, 0, sizeof(StatsA), st));
+    if (launch_stats_a(one_pass, d_img, g.w, g.h, g.black, g.white, T->d_raw2evf + (MLVB_MAX_BLACK - g.black), D.statsA, ctx->sm_count, st))
+        return MLVB_ERR_UNSUPPORTED;
+    ctx->launches += 1;
+    PinnedLease stage(T);
+    if (!stage.p) return MLVB_ERR_CUDA;
+    StatsA *hostA = (StatsA *)stage.p;
+    if (one_pass) MLVB_CUDA_OK(cudaMemcpyAsync(hostA, D.statsA, sizeof(StatsA), cudaMemcpyDeviceToHost, st));
+    else {
+        MLVB_CUDA_OK(cudaMemcpyAsync(&hostA->ev_sum, &D.statsA->ev_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+        MLVB_CUDA_OK(cudaMemcpyAsync(&hostA->ev_num, &D.statsA->ev_num, sizeof(hostA->ev_num), cudaMemcpyDeviceToHost, st));
+    }
+    MLVB_CUDA_OK(stream_wait(ctx, st));
+    const double avg_ev = hostA->ev_sum / (double)hostA->ev_num;          // 0/0 -> NaN -> "not HDR" (hdr.c:435-438)
+    if (!(avg_ev > 0.5)) return 0;
+    if (one_pass)
+        return hdr_interpolate_impl(ctx, d_img, g.w, g.h, g.black, interp_method, use_fullres, use_alias_map, cs_method, d_aux, st, &stage);
+
     if (focus && focus->nlevels) {
         rc = apply_pixel_list(ctx, *focus, d_img, g, g.npix, 1, 1, 1, st);
         if (rc) return rc;
@@ -1009,6 +1057,7 @@ int run_cr2hdr20(mlvb_context *ctx, const struct frame_headers *hdr, const Frame
             if (rc) return rc;
         }
     }
+    stage.release();                                                      // back to the pool before the next stage leases one
     return run_hdr_interpolate(ctx, d_img, g.w, g.h, g.black, interp_method, use_fullres, use_alias_map, cs_method, d_aux, st);
 }
 

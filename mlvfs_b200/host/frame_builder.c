@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <time.h>
+
 #include "mlv_index.h"
 
 #define MAX_GPUS 16
@@ -26,6 +28,22 @@ static char g_mlv_dir[4096];
 static mlvb_context *g_ctx[MAX_GPUS];
 static int g_nctx = 0, g_owns_ctx = 0, g_chunk = 1;
 static dng_header_writer g_header_writer = dng_get_header_data;
+
+/* where a frame's host time goes (summed over all threads; frame_builder_get_stats) */
+static uint64_t g_ns_read = 0, g_ns_gpu = 0, g_ns_header = 0, g_ns_prime = 0, g_n_frames = 0, g_n_calls = 0;
+
+static uint64_t now_ns(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
+}
+
+void frame_builder_get_stats(struct frame_builder_stats *out)
+{
+    out->read_ns = g_ns_read; out->gpu_ns = g_ns_gpu; out->header_ns = g_ns_header; out->prime_ns = g_ns_prime;
+    out->frames = g_n_frames; out->gpu_calls = g_n_calls;
+}
 
 void frame_builder_configure(const struct frame_builder_config *cfg)
 {
@@ -156,6 +174,7 @@ static int prime_clip(struct mlv_clip *clip, const char *mlv_file, const mlvb_op
     char key[4300];
     primed_key(key, sizeof(key), mlv_file, opts);
     int ok = 1;
+    const uint64_t t_prime = now_ns();
     pthread_mutex_lock(&g_primed_mu);                    /* held across the priming: clips are primed one at a time */
     int hit = 0;
     for (int i = 0; i < g_nprimed && !hit; i++) hit = !strcmp(g_primed[i], key);
@@ -178,6 +197,7 @@ static int prime_clip(struct mlv_clip *clip, const char *mlv_file, const mlvb_op
         }
     }
     pthread_mutex_unlock(&g_primed_mu);
+    __sync_fetch_and_add(&g_ns_prime, now_ns() - t_prime);
     return ok;
 }
 
@@ -189,8 +209,14 @@ static int build_one(mlvb_context *ctx, struct mlv_clip *clip, const char *mlv_f
     const size_t payload_bytes = mlv_clip_payload_size(hdrs);
     uint8_t *payload = mlvb_host_alloc(payload_bytes + 16);
     memset(res, 0, sizeof(*res));
+    const uint64_t t0 = now_ns();
     int ok = payload && mlv_clip_read_payload(clip, hdrs, payload, payload_bytes) == (ssize_t)payload_bytes;
+    const uint64_t t1 = now_ns();
     if (ok) ok = mlvb_process_frame(ctx, hdrs, payload, payload_bytes, opts, mlv_file, data, res) == MLVB_OK;
+    __sync_fetch_and_add(&g_ns_read, t1 - t0);
+    __sync_fetch_and_add(&g_ns_gpu, now_ns() - t1);
+    __sync_fetch_and_add(&g_n_frames, 1);
+    __sync_fetch_and_add(&g_n_calls, 1);
     mlvb_host_free(payload);
     return ok;
 }
@@ -199,6 +225,7 @@ static int build_one(mlvb_context *ctx, struct mlv_clip *clip, const char *mlv_f
  * exposure_bias (main.c:895-906) */
 static uint8_t *finish_header(struct frame_headers *hdrs, const mlvb_frame_result *res, const char *dng_filename, double fps)
 {
+    const uint64_t t0 = now_ns();
     uint8_t *header = calloc(1, MLVB_DNG_HEADER_SIZE);
     if (!header) return NULL;
     hdrs->rawi_hdr.raw_info.black_level = res->black_level;
@@ -212,6 +239,7 @@ static uint8_t *finish_header(struct frame_headers *hdrs, const mlvb_frame_resul
         g_header_writer(hdrs, header, 0, MLVB_DNG_HEADER_SIZE, fps, base);
         free(base);
     }
+    __sync_fetch_and_add(&g_ns_header, now_ns() - t0);
     return header;
 }
 
@@ -273,6 +301,7 @@ int process_frame_batch(struct image_buffer **bufs, int n)
     size_t *bytes = calloc((size_t)n, sizeof(size_t));
     int *slot = calloc((size_t)n, sizeof(int));                  /* batch position -> bufs index */
     int m = 0, ok = hdrs && res && payloads && dsts && bytes && slot;
+    const uint64_t t_read = now_ns();
     for (int k = 0; k < n && ok; k++) {
         int frame;
         if (!resolve(bufs[k]->dng_filename, dir, other, sizeof(other), &frame) || strcmp(other, mlv_file)) continue;
@@ -290,7 +319,12 @@ int process_frame_batch(struct image_buffer **bufs, int n)
     }
     if (ok && m) {
         /* the whole chunk goes to the GPU that owns its first frame */
+        const uint64_t t_gpu = now_ns();
         mlvb_process_frames(context_for_frame(frame0), m, hdrs, payloads, bytes, &cfg.options, mlv_file, dsts, res);
+        __sync_fetch_and_add(&g_ns_read, t_gpu - t_read);
+        __sync_fetch_and_add(&g_ns_gpu, now_ns() - t_gpu);
+        __sync_fetch_and_add(&g_n_frames, (uint64_t)m);
+        __sync_fetch_and_add(&g_n_calls, 1);
         for (int j = 0; j < m; j++) {
             struct image_buffer *ib = bufs[slot[j]];
             uint8_t *header = res[j].status == MLVB_OK ? finish_header(&hdrs[j], &res[j], ib->dng_filename, cfg.fps) : NULL;

@@ -46,6 +46,11 @@ void frame_builder_shutdown(void);                                      /* destr
  * mlvb_reset_clip_state / free_focus_pixel_maps when the frame builder is in use). */
 void frame_builder_reset_clip_state(void);
 
+/* where the builder threads' time went, summed over threads: reading payloads into pinned memory, inside the GPU
+ * library (copies + kernels + waiting), writing DNG headers, priming clips */
+struct frame_builder_stats { uint64_t read_ns, gpu_ns, header_ns, prime_ns, frames, gpu_calls; };
+void frame_builder_get_stats(struct frame_builder_stats *out);
+
 /* The callback for get_or_create_image_buffer (same type as the reference's process_frame). */
 int process_frame(struct image_buffer *image_buffer);
 /* The batch builder for resource_manager_set_batch_builder: a chunk of look-ahead frames as one device batch. */

@@ -28,6 +28,7 @@ static FILE *g_dump;
 static int g_failed = 0;
 static FILE *g_dump_headers;
 static int g_hashing = 0;
+static uint64_t g_copy_ns = 0, g_copy_frames = 0;
 
 /* FNV-1a over 64-bit words (the byte-wise form costs ~5 ms per 1080p frame and would be the slowest stage) */
 static uint64_t fnv1a_words(const void *p, size_t n)
@@ -59,7 +60,14 @@ static void *reader(void *arg)
         struct image_buffer *ib = get_or_create_image_buffer(path, &process_frame, &created);
         if (!ib || !ib->data) { __sync_fetch_and_add(&g_failed, 1); continue; }
         if (ib->size > sink_cap) { free(sink); sink = malloc(ib->size); sink_cap = sink ? ib->size : 0; }
-        if (sink) memcpy(sink, ib->data, ib->size);          /* main.c:1463-1483 copies the requested range to the FUSE buffer */
+        if (sink) {                                          /* main.c:1463-1483 copies the requested range to the FUSE buffer */
+            struct timespec c0, c1;
+            clock_gettime(CLOCK_MONOTONIC, &c0);
+            memcpy(sink, ib->data, ib->size);
+            clock_gettime(CLOCK_MONOTONIC, &c1);
+            __sync_fetch_and_add(&g_copy_ns, (uint64_t)((c1.tv_sec - c0.tv_sec) * 1000000000ll + (c1.tv_nsec - c0.tv_nsec)));
+            __sync_fetch_and_add(&g_copy_frames, 1);
+        }
         g_hash[i] = g_hashing ? fnv1a_words(sink ? sink : (const uint8_t *)ib->data, ib->size) : ib->data[ib->size / 4];
         if (g_dump) {
             pthread_mutex_lock(&g_mu);
@@ -159,15 +167,21 @@ int main(int argc, char **argv)
     uint64_t all = 1469598103934665603ull, built = 0, hits = 0;
     for (int i = 0; i < g_nframes; i++) { all ^= g_hash[i]; all *= 1099511628211ull; }
     resource_manager_prefetch_stats(&built, &hits);
+    struct frame_builder_stats fs;
+    frame_builder_get_stats(&fs);
+    const double per = fs.frames ? 1e-3 / (double)fs.frames : 0.0;      /* -> microseconds of builder-thread time per frame */
     uint64_t device_batches = 0;
     for (int i = 0; i < gpus; i++) device_batches += mlvb_path_count(frame_builder_context(i), 2);
     printf("{\"frames\": %d, \"failed\": %d, \"seconds\": %.6f, \"fps\": %.2f, \"sustained_fps\": %.2f, \"passes\": %d, "
            "\"readers\": %d, \"prefetch\": %d, \"gpus\": %d, \"batch\": %d, "
            "\"prefetch_built\": %llu, \"prefetch_hits\": %llu, \"prefetch_batches\": %llu, \"device_batches\": %llu, "
+           "\"builder_us_per_frame\": {\"read\": %.1f, \"gpu_call\": %.1f, \"header\": %.1f, \"prime\": %.1f}, \"reader_copy_us_per_frame\": %.1f, "
            "\"hash\": \"%016llx\", \"frame0_hash\": \"%016llx\"}\n",
            g_nframes, g_failed, dt, g_nframes / dt, repeat > 1 ? g_nframes * (repeat - 1) / dt_sustained : g_nframes / dt, repeat,
            readers, prefetch, gpus, batch, (unsigned long long)built, (unsigned long long)hits,
            (unsigned long long)resource_manager_prefetch_batches(), (unsigned long long)device_batches,
+           fs.read_ns * per, fs.gpu_ns * per, fs.header_ns * per, fs.prime_ns * per,
+           g_copy_frames ? 1e-3 * (double)g_copy_ns / (double)g_copy_frames : 0.0,
            (unsigned long long)all, (unsigned long long)g_hash[0]);
     if (g_dump) fclose(g_dump);
     if (g_dump_headers) fclose(g_dump_headers);
