@@ -223,7 +223,7 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
         if (rc || nframes == 1) return rc;
         // the other frames are independent: a few host threads, each with its own stream and scratch, so that one
         // frame's statistics read-backs and scalar epilogues overlap the kernels of the others
-        const int nlanes = std::min(nframes - 1, getenv("MLVB_BATCH_LANES") ? std::max(atoi(getenv("MLVB_BATCH_LANES")), 1) : 4);
+        const int nlanes = std::min(nframes - 1, ctx->batch_lane_count);
         const size_t need = aux_bytes_for(g, opts);
         if (!ctx->batch_fork) MLVB_CUDA_OK(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
         while ((int)ctx->batch_lanes.size() < nlanes) {
@@ -316,6 +316,13 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
         // box those cores are what the copies and the other ranks need.  Events are created blocking by default.
         const char *bs = getenv("MLVB_BLOCKING_SYNC");
         ctx->blocking_sync = !(bs && *bs == '0');
+        ctx->sync_submit = getenv("MLVB_SYNC_SUBMIT") != nullptr;
+        ctx->no_wide = getenv("MLVB_NO_WIDE") != nullptr;
+        ctx->wide_segments = getenv("MLVB_WIDE_SEGMENTS") != nullptr;
+        const char *bl = getenv("MLVB_BATCH_LANES");
+        if (bl) ctx->batch_lane_count = std::min(std::max(atoi(bl), 1), 16);
+        const char *su = getenv("MLVB_SPIN_US");
+        if (su) ctx->spin_us = std::max(atoi(su), 0);
     }
     const unsigned ev_flags = cudaEventDisableTiming | (ctx->blocking_sync ? cudaEventBlockingSync : 0);
     for (auto &s : ctx->slots) {
@@ -591,7 +598,7 @@ static void submit_worker(mlvb_context *ctx)
     }
 }
 
-constexpr int SUBMIT_WORKERS = 4;
+constexpr int SUBMIT_WORKERS = 8;
 
 constexpr mlvb_ticket SUBMIT_WOULD_BLOCK = -100;          // internal: no free slot and the caller asked not to wait
 
@@ -656,7 +663,7 @@ static mlvb_ticket submit_frame(mlvb_context *ctx, const struct frame_headers *h
     // The full dual-ISO pipeline waits on the host several times per frame (statistics read-backs): once the clip's
     // per-clip state exists (its first frame went through synchronously, below), such frames go to the submit workers
     // so that the frames in flight overlap.  payload (when pinned) and dst must stay valid until mlvb_wait.
-    const bool blocking = opts->dual_iso == 2 && !ctx->profiling && getenv("MLVB_SYNC_SUBMIT") == nullptr;
+    const bool blocking = opts->dual_iso == 2 && !ctx->profiling && !ctx->sync_submit;
     std::string key;
     if (blocking) {
         char tag[64];

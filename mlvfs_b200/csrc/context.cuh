@@ -4,6 +4,7 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <chrono>
 #include <deque>
 #include <set>
 #include <thread>
@@ -164,6 +165,9 @@ struct mlvb_context {
     std::condition_variable hb_cv;
     std::vector<BatchSlot> host_batches;
     bool blocking_sync = true;             // waits sleep on the event instead of spinning ($MLVB_BLOCKING_SYNC=0: spin)
+    bool sync_submit = false, no_wide = false, wide_segments = false;   // $MLVB_SYNC_SUBMIT, $MLVB_NO_WIDE, $MLVB_WIDE_SEGMENTS (read once)
+    int batch_lane_count = 8;              // dual-ISO frames of a device batch in flight at once ($MLVB_BATCH_LANES)
+    int spin_us = 150;                     // stream_wait polls this long before it sleeps ($MLVB_SPIN_US)
 
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> path_count[3] = {{0}, {0}, {0}};   // fused strip kernel, fused wide kernel, host batches (mlvb_path_count)
@@ -178,8 +182,9 @@ struct mlvb_context {
 };
 
 // Wait for a stream from a host thread.  cudaStreamSynchronize spins by default, which costs a core per waiting
-// thread; the per-frame statistics read-backs of the dual-ISO path wait five times per frame on several threads
-// per GPU.  With blocking_sync the wait sleeps on a per-thread blocking event instead.
+// thread for as long as the wait lasts; a blocking event sleeps but wakes up tens of microseconds late, and the
+// dual-ISO path waits four times per frame for kernels that take 20 .. 60 us.  So: poll for a short while (most waits
+// end there), then sleep on a per-thread blocking event.  $MLVB_BLOCKING_SYNC=0: plain cudaStreamSynchronize.
 inline cudaError_t stream_wait(const mlvb_context *ctx, cudaStream_t st)
 {
     if (!ctx->blocking_sync) return cudaStreamSynchronize(st);
@@ -192,7 +197,14 @@ inline cudaError_t stream_wait(const mlvb_context *ctx, cudaStream_t st)
         if (e != cudaSuccess) { ev[dev] = nullptr; return e; }
     }
     cudaError_t e = cudaEventRecord(ev[dev], st);
-    return e == cudaSuccess ? cudaEventSynchronize(ev[dev]) : e;
+    if (e != cudaSuccess) return e;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        e = cudaEventQuery(ev[dev]);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(ctx->spin_us)) break;
+    }
+    return cudaEventSynchronize(ev[dev]);
 }
 
 // stage ids reported by mlvb_profile_end

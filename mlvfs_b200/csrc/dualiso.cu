@@ -382,7 +382,7 @@ __device__ __forceinline__ bool fullres_above_thr(const double *__restrict__ cur
 
 // half-res blend (hdr.c:1562-1611) + overexposure flags (hdr.c:1627-1633) + alias-map skip mask
 __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, uint32_t *__restrict__ halfres,
-                                uint16_t *__restrict__ over, uint8_t *__restrict__ skip, const PixParams P)
+                                uint8_t *__restrict__ over, uint8_t *__restrict__ skip, const PixParams P)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
     if (i >= np) return;
@@ -477,9 +477,12 @@ __global__ void diso_alias34_kernel(const uint16_t *__restrict__ aux, const uint
     }
 }
 
-// 3x3 "blur" of the overexposure flags (hdr.c:1636-1655), evaluated where final_blend reads it
-__device__ __forceinline__ int over_blurred(const uint16_t *__restrict__ in, int x, int y, int w, int h)
+// 3x3 "blur" of the overexposure flags (hdr.c:1636-1655): in -> out.  The flags are 0 / 100 and final_blend only
+// uses min(blurred / 200, 1): both planes are bytes, the blurred value saturates at 200.
+__global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h)
 {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
     const size_t i = x + (size_t)y * w;
     int v = in[i];
     if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
@@ -487,12 +490,12 @@ __device__ __forceinline__ int over_blurred(const uint16_t *__restrict__ in, int
         v = O(0, 0) + (O(0, -1) + O(-1, 0) + O(1, 0) + O(0, 1)) * 820 / 1024 + (O(-1, -1) + O(1, -1) + O(-1, 1) + O(1, 1)) * 657 / 1024;
 #undef O
     }
-    return (int)(uint16_t)v;
+    out[i] = (uint8_t)min(v, 200);
 }
 
 // final_blend (hdr.c:1691-1752) + convert_20_to_16bit (hdr.c:1760-1772)
 __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, const uint32_t *__restrict__ fullres,
-                                  const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint16_t *__restrict__ over,
+                                  const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint8_t *__restrict__ over,
                                   const uint16_t *__restrict__ amap, uint16_t *__restrict__ out16, const PixParams P)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -501,7 +504,7 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
     const int b = (int)bright[i];
     double f = curve_at(P.fullres_curve, P.fullres_lim, b & 0xFFFFF), c = 0.0;
     if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
-    const double ovf = fmax(fmin((double)over_blurred(over, x, y, P.w, P.h) / 200.0, 1.0), 0.0);
+    const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
     c = fmax(c, ovf);
     const double noo = fmax(ovf, 1.0 - f);
     f = fmax(f, c);
@@ -600,7 +603,8 @@ struct DisoScratch {        // carved out of the slot's aux buffer
     int2 *pairs, *sel;
     unsigned *nsel, *scores;
     uint32_t *raw32, *dark, *bright, *fullres, *halfres, *frs, *hrs;
-    uint16_t *over, *over2, *amap, *aux;
+    uint8_t *over, *over2;
+    uint16_t *amap, *aux;
     uint8_t *skip;
     double *mix_curve;      // [2^20]
     int *mix_lim;           // [4]
@@ -625,7 +629,7 @@ size_t carve(uint8_t *base, int w, int h, int interp_method, DisoScratch *S)
     s.raw32 = (uint32_t *)take(npix * 4); s.dark = (uint32_t *)take(npix * 4); s.bright = (uint32_t *)take(npix * 4);
     s.fullres = (uint32_t *)take(npix * 4); s.halfres = (uint32_t *)take(npix * 4);
     s.frs = (uint32_t *)take(npix * 4); s.hrs = (uint32_t *)take(npix * 4);
-    s.over = (uint16_t *)take(npix * 2); s.over2 = (uint16_t *)take(npix * 2);
+    s.over = (uint8_t *)take(npix); s.over2 = (uint8_t *)take(npix);
     s.amap = (uint16_t *)take(npix * 2); s.aux = (uint16_t *)take(npix * 2);
     s.skip = (uint8_t *)take(npix);
     s.mix_curve = (double *)take((size_t)N20 * sizeof(double));
@@ -986,8 +990,9 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
         diso_alias34_kernel<<<dim3(ceil_div((w + 1) / 2, 128), (h + 1) / 2), 128, 0, st>>>(D.aux, D.skip, D.amap, w, h);
         ctx->launches += 3;
     }
-    diso_final_kernel<<<g2, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over, D.amap, d_img, P);
-    ctx->launches += 1;
+    diso_over_blur_kernel<<<g2, 256, 0, st>>>(D.over, D.over2, w, h);
+    diso_final_kernel<<<g2, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
+    ctx->launches += 2;
     MLVB_CUDA_OK(cudaGetLastError());
     return 1;
 }

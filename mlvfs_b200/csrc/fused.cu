@@ -397,7 +397,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
     }
     // batches large enough to keep one persistent CTA per SM busy take the wide kernel (fused_wide.cuh)
     bool wide = ctx->ev2raw_octaves_ok && ctx->sm_count > 0 && (g.w % 64) == 0 && ((uintptr_t)d_out % 16) == 0 &&
-                (out_stride_px % 8) == 0 && (payload_stride % 16) == 0 && getenv("MLVB_NO_WIDE") == nullptr &&
+                (out_stride_px % 8) == 0 && (payload_stride % 16) == 0 && !ctx->no_wide &&
                 (long long)nframes * ceil_div(g.w, FW_STRIP_PX) * (g.h / 2) >= wide_min_rows(ctx);
     // (v - black) * gain fits 32 bits, and so does (v - black) * gain + (black << 16) (the high-half form of FW_GAIN_X)
     for (int i = 0; i < 8 && P.stripes; i++)
@@ -427,7 +427,7 @@ int try_fused_single_iso(mlvb_context *ctx, const struct frame_headers *hdr, con
         // one contiguous run of a strip's quad rows per warp (nseg = 0); MLVB_WIDE_SEGMENTS=1 keeps the equal-segment split
         const long long all_rows = (long long)nframes * Q.nstrips * (g.h / 2);
         const int nwarps = ctx->sm_count * FW_WARPS;
-        if (all_rows < (1LL << 30) && nwarps >= Q.nstrips && getenv("MLVB_WIDE_SEGMENTS") == nullptr) {
+        if (all_rows < (1LL << 30) && nwarps >= Q.nstrips && !ctx->wide_segments) {
             Q.nseg = 0;             // the kernel cuts each strip's column of nframes x h/2 rows among that strip's warps
             Q.seg_rows = 0;
         } else {

@@ -45,6 +45,9 @@ namespace {
 #if !defined(FW_NO_GAIN_X) && !defined(FW_GAIN_X) && defined(FW_PACK_PRMT) && !defined(FW_GAIN_HI) && !defined(FW_GAIN_MAD)
 #define FW_GAIN_X
 #endif
+#if defined(FW_CLAMP_X2) && !defined(FW_GAIN_X)
+#error "FW_CLAMP_X2 needs FW_GAIN_X (samples are packed before the clamp)"
+#endif
 #if defined(FW_GAIN_X) && !defined(FW_PACK_PRMT)
 #error "FW_GAIN_X needs FW_PACK_PRMT (the packing PRMT takes the high halves)"
 #endif
@@ -176,7 +179,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ int imin3(int a, int b, int c) { return __vimin3_s32(a, b, c); }   // one VIMNMX3
 __device__ __forceinline__ int imax3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-struct WideConst { uint32_t black, thr, white; uint32_t coef[8], k1[8], coefh[8], k4, kx[8], whitex; uint32_t shl[4], shr[2]; int one, mone; };
+struct WideConst { uint32_t black, thr, white, white2; uint32_t coef[8], k1[8], coefh[8], k4, kx[8], whitex; uint32_t shl[4], shr[2]; int one, mone; };
 
 // a * m + b on the FMA pipe (IMAD with a register multiplier the compiler cannot fold): the min/max network
 // keeps the ALU pipe busy, the bookkeeping additions go next door.  m is +1 or -1.
@@ -188,6 +191,24 @@ __device__ __forceinline__ int fma_add(int a, int m, int b)
     int d;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
     return d;
+#endif
+}
+// -DFW_ADD_FMA: the two-input additions of the chain (ev - ge, ge + median, + black) as one IMAD each on the FMA pipe
+// instead of one IADD3 each on the ALU pipe -- the same number of issue slots, taken from the pipe that has room
+__device__ __forceinline__ int add2(int a, int b, const WideConst &K)
+{
+#ifdef FW_ADD_FMA
+    return fma_add(a, K.one, b);
+#else
+    return (int)((unsigned)a + (unsigned)b);
+#endif
+}
+__device__ __forceinline__ int sub2(int a, int b, const WideConst &K)     // a - b
+{
+#ifdef FW_ADD_FMA
+    return fma_add(b, K.mone, a);
+#else
+    return (int)((unsigned)a - (unsigned)b);
 #endif
 }
 // the middle of three = a + b + c - min - max; exact in wrap-around arithmetic (a permutation of the three)
@@ -284,15 +305,34 @@ __host__ __device__ constexpr bool wide_in_hi()
     return false;
 #endif
 }
+// -DFW_CLAMP_X2 (with FW_GAIN_X): the clamp to white is taken after the packing PRMT, on both 16-bit halves of the
+// output word at once (one packed unsigned min per two samples instead of one min per sample).  Equal results:
+// min(X, white << 16 | 0xFFFF) >> 16 == min(X >> 16, white), and samples that are not corrected are below white.
 template <int STRIPES, int IDX>
 __device__ __forceinline__ uint32_t wide_gain_x(uint32_t v, const WideConst &K)
 {
-    if constexpr (!wide_in_hi<STRIPES, IDX>()) return wide_gain<STRIPES, IDX>(v, K);
-    else {
+    if constexpr (!wide_in_hi<STRIPES, IDX>()) {
+#ifdef FW_CLAMP_X2
+        if (STRIPES == 2 && IDX < 2) return v;            // clamp only: done on the packed word
+#endif
+        return wide_gain<STRIPES, IDX>(v, K);
+    } else {
         uint32_t x = v << 16;
+#ifdef FW_CLAMP_X2
+        if (v > K.thr) x = v * K.coef[IDX] + K.kx[IDX];
+#else
         if (v > K.thr) x = min(v * K.coef[IDX] + K.kx[IDX], K.whitex);
+#endif
         return x;
     }
+}
+template <int STRIPES>
+__device__ __forceinline__ uint32_t wide_clamp2(uint32_t packed, const WideConst &K)
+{
+#ifdef FW_CLAMP_X2
+    if (STRIPES) return __vminu2(packed, K.white2);
+#endif
+    return packed;
 }
 // low half of the result = sample A, high half = sample B; AH / BH: the sample sits in the high half of its register
 template <bool AH, bool BH>
@@ -308,8 +348,8 @@ __device__ __forceinline__ void wide_ingest_col(const uint32_t (&T)[FW_NW], cons
     const uint32_t g2 = wide_px<2 * C>(B, K.shl, K.shr[0]), b = wide_px<2 * C + 1>(B, K.shl, K.shr[0]);
     const int ge = wadd(FW_R2E(g1), FW_R2E(g2)) / 2;
     R.ge[C] = ge;
-    R.dr[C] = wsub(FW_R2E(r), ge);
-    R.db[C] = wsub(FW_R2E(b), ge);
+    R.dr[C] = sub2(FW_R2E(r), ge, K);
+    R.db[C] = sub2(FW_R2E(b), ge, K);
     R.r[C] = r;
     R.b[C] = b;
 #ifdef FW_PACK_PRMT
@@ -381,19 +421,19 @@ __device__ __forceinline__ void wide_finish_col(const WideRow &M, int mr, int mb
     bool go = ge >= ge_thr;
     if (C < 2) go = go && !edge_first;
     if (C >= FW_COLS - 2) go = go && !edge_last;
-    const int er = wadd(ge, mr), eb = wadd(ge, mb);
+    const int er = add2(mr, ge, K), eb = add2(mb, ge, K);
     go = go && er > MLVB_EV_RES && eb > MLVB_EV_RES;
     // branch-free: both lookups always run (indices clamped into the table), the result is selected -- no
     // reconvergence barrier between the columns of a lane, so their instruction streams interleave freely
-    const uint32_t nr = wide_ev2raw(er, K.shr[1]) + K.black, nb = wide_ev2raw(eb, K.shr[1]) + K.black;
+    const uint32_t nr = (uint32_t)add2((int)wide_ev2raw(er, K.shr[1]), (int)K.black, K), nb = (uint32_t)add2((int)wide_ev2raw(eb, K.shr[1]), (int)K.black, K);
     r = go ? nr : r;
     b = go ? nb : b;
 #ifdef FW_PACK_PRMT
     constexpr bool EH = wide_in_hi<STRIPES, (2 * C) & 7>(), OH = wide_in_hi<STRIPES, (2 * C + 1) & 7>();   // even / odd pixel column
     r = wide_gain_x<STRIPES, (2 * C) & 7>(r, K);
     b = wide_gain_x<STRIPES, (2 * C + 1) & 7>(b, K);
-    top = wide_pack<EH, OH>(r, M.g1s[C]);           // all four samples are < 2^16
-    bot = wide_pack<EH, OH>(M.g2[C], b);
+    top = wide_clamp2<STRIPES>(wide_pack<EH, OH>(r, M.g1s[C]), K);           // all four samples are < 2^16
+    bot = wide_clamp2<STRIPES>(wide_pack<EH, OH>(M.g2[C], b), K);
 #else
     r = wide_gain<STRIPES, (2 * C) & 7>(r, K);
     b = wide_gain<STRIPES, (2 * C + 1) & 7>(b, K);
@@ -528,6 +568,7 @@ fused3_wide_kernel(const __grid_constant__ WideParams P)
 
     WideConst K;
     K.black = (uint32_t)P.black16; K.thr = (uint32_t)P.black16 + 64u; K.white = (uint32_t)P.white16;
+    K.white2 = K.white | (K.white << 16);
 #pragma unroll
     for (int i = 0; i < 8; i++) { K.coef[i] = P.gain[i].coef; K.k1[i] = P.gain[i].k1; K.coefh[i] = P.coefh[i]; }
     K.k4 = P.k4; K.whitex = P.whitex;

@@ -39,6 +39,8 @@ static uint64_t now_ns(void)
     return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
 }
 
+void frame_builder_reset_stats(void) { g_ns_read = g_ns_gpu = g_ns_header = g_ns_prime = g_n_frames = g_n_calls = 0; }
+
 void frame_builder_get_stats(struct frame_builder_stats *out)
 {
     out->read_ns = g_ns_read; out->gpu_ns = g_ns_gpu; out->header_ns = g_ns_header; out->prime_ns = g_ns_prime;

@@ -50,6 +50,7 @@ void frame_builder_reset_clip_state(void);
  * library (copies + kernels + waiting), writing DNG headers, priming clips */
 struct frame_builder_stats { uint64_t read_ns, gpu_ns, header_ns, prime_ns, frames, gpu_calls; };
 void frame_builder_get_stats(struct frame_builder_stats *out);
+void frame_builder_reset_stats(void);
 
 /* The callback for get_or_create_image_buffer (same type as the reference's process_frame). */
 int process_frame(struct image_buffer *image_buffer);

@@ -158,6 +158,7 @@ int main(int argc, char **argv)
         clock_gettime(CLOCK_MONOTONIC, &t1);
         const double d = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
         if (pass == 0) dt = d; else dt_sustained += d;
+        if (pass == 0 && repeat > 1) { frame_builder_reset_stats(); g_copy_ns = g_copy_frames = 0; }   /* the breakdown covers the warm passes */
         if (pass + 1 < repeat) {                               /* every pass builds every frame again */
             resource_manager_set_prefetch(0, 0, NULL);
             free_all_image_buffers();

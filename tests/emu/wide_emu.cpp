@@ -54,6 +54,10 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh)
     return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
 }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t __vminu2(uint32_t a, uint32_t b)
+{
+    return min(a & 0xFFFFu, b & 0xFFFFu) | (min(a >> 16, b >> 16) << 16);
+}
 template <class T> static inline T __ldg(const T *p) { return *p; }
 template <class T> static inline void __stcs(T *p, T v) { *p = v; }
 static inline void __syncwarp() { g_wx->bar.arrive_and_wait(); }
