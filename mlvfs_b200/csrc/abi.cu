@@ -321,6 +321,12 @@ int mlvb_context_create(int device, int nslots, mlvb_context **out)
         ctx->wide_segments = getenv("MLVB_WIDE_SEGMENTS") != nullptr;
         const char *bl = getenv("MLVB_BATCH_LANES");
         if (bl) ctx->batch_lane_count = std::min(std::max(atoi(bl), 1), 16);
+        // plenty of host cores per GPU: a waiting thread may poll for as long as a statistics kernel runs (lowest
+        // latency); few cores per GPU (8 GPUs on a 32-core box, one process each): poll briefly, then sleep
+        int ngpu = 1;
+        if (cudaGetDeviceCount(&ngpu) != cudaSuccess || ngpu < 1) ngpu = 1;
+        const unsigned cores = std::thread::hardware_concurrency();
+        ctx->spin_us = (cores >= 8u * (unsigned)ngpu) ? 5000 : 150;
         const char *su = getenv("MLVB_SPIN_US");
         if (su) ctx->spin_us = std::max(atoi(su), 0);
     }

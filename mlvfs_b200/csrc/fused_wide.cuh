@@ -45,6 +45,12 @@ namespace {
 #if !defined(FW_NO_GAIN_X) && !defined(FW_GAIN_X) && defined(FW_PACK_PRMT) && !defined(FW_GAIN_HI) && !defined(FW_GAIN_MAD)
 #define FW_GAIN_X
 #endif
+#if !defined(FW_NO_CLAMP_X2) && !defined(FW_CLAMP_X2) && defined(FW_GAIN_X)
+#define FW_CLAMP_X2
+#endif
+#if !defined(FW_NO_ADD_FMA) && !defined(FW_ADD_FMA)
+#define FW_ADD_FMA
+#endif
 #if defined(FW_CLAMP_X2) && !defined(FW_GAIN_X)
 #error "FW_CLAMP_X2 needs FW_GAIN_X (samples are packed before the clamp)"
 #endif

@@ -21,8 +21,8 @@ EV = 32768
 
 
 # the shipped defaults, and the plain forms they replaced (every -DFW_NO_* switch of fused_wide.cuh)
-BUILDS = {"default": [], "plain": ["-DFW_NO_MIDPAIR", "-DFW_NO_PACK_PRMT", "-DFW_NO_EXTRACT_SHL", "-DFW_NO_GAIN_X"],
-          "addfma_clamp2": ["-DFW_ADD_FMA", "-DFW_CLAMP_X2"],      # two-input adds on the FMA pipe, packed clamp to white
+BUILDS = {"default": [], "plain": ["-DFW_NO_MIDPAIR", "-DFW_NO_PACK_PRMT", "-DFW_NO_EXTRACT_SHL", "-DFW_NO_GAIN_X", "-DFW_NO_CLAMP_X2", "-DFW_NO_ADD_FMA"],
+          "r01n": ["-DFW_NO_ADD_FMA", "-DFW_NO_CLAMP_X2"],         # round 1's build: per-sample clamp, plain two-input adds
           "cols8": ["-DFW_COLS_CFG=8"]}         # 8 quad columns per lane (480-pixel strips): built, measured slower, kept honest
 
 
