@@ -46,6 +46,7 @@ namespace {
 struct CudaCtx {
     int tid, nthr;
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void syncwarp() { __syncwarp(); }
     __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }
 };
 

@@ -79,9 +79,10 @@ AMZ_HD Geom tile_geom(int width, int height, int top, int left)        // :296-3
 AMZ_HD int tiles_along(int extent) { return (extent + 16 + (TS - 32) - 1) / (TS - 32); }   // top = -16, -16+128, ... < extent
 
 struct Shared {                       // block-shared scratch of the sequential passes
-    float row[2][TS];
-    int oth[TSH], old[TSH];
+    float row[2][2][TS];              // [pass: hvwt / pmwt refinement][row parity][half-row site]: the previous row, updated
     int rowcnt[TS];
+    int scan[2][32];                  // Nyquist vote: per-lane transition functions (two buffers for the warp scan)
+    int votecnt;
     int anynyq;
 };
 
@@ -282,59 +283,65 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     }
     C.sync();
 
-    // ---- variance-based choice + bounding, in place (:748-803): thread per column, rows in order ----
-    // Everything a row reads except the two left-neighbour lanes and the row two above is still original when the
-    // previous row is processed, so the operands of row rr+1 are loaded before row rr's barrier: the L2 latency of
-    // the next row hides behind this row's work instead of adding to every one of the ~150 sequential steps.
+    // ---- variance-based choice + bounding (:748-803) ----
+    // The reference runs this in place, four columns at a time: lanes 0 and 1 of a vector see the already updated
+    // hcd two columns to their left (lanes 2 and 3 of the previous vector, which themselves read originals only),
+    // and vcd sees the updated row two above.  Nothing else it reads has been rewritten.  So:
+    //   h: every cell from ORIGINAL values only -- a lane 0 / 1 cell first re-derives its left neighbour's updated
+    //      value (the same expression on that column's originals).  All cells in parallel, reading a copy of hcd
+    //      taken before anything is overwritten; no row-by-row barriers.
+    //   v: a recurrence down each column (row rr needs the updated row rr - 2 of its own column only): one thread per
+    //      column walks the rows, the updated values of the two parities in registers; threads never read each
+    //      other's cells, so no barriers either.
     {
         const int ncol = 4 * cdiv(cc1 - 8, 4);                            // columns 4 .. 4+ncol-1
-        const int cc = 4 + tid, lane = tid & 3;
-        const bool active = tid < ncol;
-        struct VarIn { float c0, cl, cr, cu, cd, h0, hm2, hp2, ha, ham2, hap2, v0, vm2, vp2, va, vam2, vap2; };
-        auto load_row = [&](int rr) {
-            VarIn L;
-            const int i = rr * TS + cc;
-            L.c0 = cfa[i]; L.cl = cfa[i - 1]; L.cr = cfa[i + 1]; L.cu = cfa[i - V1]; L.cd = cfa[i + V1];
-            L.h0 = W.hcd[i]; L.hm2 = W.hcd[i - 2]; L.hp2 = W.hcd[i + 2];
-            L.ha = W.hcdalt[i]; L.ham2 = W.hcdalt[i - 2]; L.hap2 = W.hcdalt[i + 2];
-            L.v0 = W.vcd[i]; L.vm2 = W.vcd[i - V2]; L.vp2 = W.vcd[i + V2];   // vm2 is only used for rows 4, 5 (rows 2, 3 are never updated)
-            L.va = W.vcdalt[i]; L.vam2 = W.vcdalt[i - V2]; L.vap2 = W.vcdalt[i + V2];
-            return L;
+        const int nrow = rr1 - 8;                                         // rows 4 .. rr1-5
+        float *const horig = W.Dgrb2;                                     // free until the G pass writes it
+        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * TS; idx += nthr) horig[4 * TS + idx] = W.hcd[4 * TS + idx];
+        C.sync();
+        auto h_from_originals = [&](int i, float sgn, float hm2) {        // hm2: original or updated left neighbour
+            const float h0 = horig[i], ha = W.hcdalt[i];
+            const float havar = var3(W.hcdalt[i - 2], ha, W.hcdalt[i + 2]);
+            const float h = (havar < var3(hm2, h0, horig[i + 2])) ? ha : h0;
+            return bound_cd(h, cfa[i], cfa[i - 1], cfa[i + 1], sgn);
         };
-        float vup[2] = {0.0f, 0.0f};                                      // updated vcd of rows rr-2 (same parity)
-        VarIn cur = {};
-        if (active && 4 < rr1 - 4) cur = load_row(4);
-        for (int rr = 4; rr < rr1 - 4; rr++) {
-            const int i = rr * TS + cc, buf = rr & 1;
-            VarIn nxt = {};
-            if (active && rr + 1 < rr1 - 4) nxt = load_row(rr + 1);
-            float h = 0.0f, v = 0.0f, c0 = 0.0f, sgn = 1.0f, hm2 = 0.0f, h0 = 0.0f, hp2 = 0.0f, havar = 0.0f, ha = 0.0f;
-            if (active) {
-                sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
-                c0 = cur.c0;
-                h0 = cur.h0; hm2 = cur.hm2; hp2 = cur.hp2;
-                ha = cur.ha;
-                havar = var3(cur.ham2, ha, cur.hap2);
-                h = (havar < var3(hm2, h0, hp2)) ? ha : h0;
-                h = bound_cd(h, c0, cur.cl, cur.cr, sgn);
-                const float v0 = cur.v0, vm2 = rr >= 6 ? vup[rr & 1] : cur.vm2, vp2 = cur.vp2;
-                const float va = cur.va;
-                v = (var3(cur.vam2, va, cur.vap2) < var3(vm2, v0, vp2)) ? va : v0;
-                v = bound_cd(v, c0, cur.cu, cur.cd, sgn);
+        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * ncol; idx += nthr) {
+            const int rr = 4 + idx / ncol, t = idx % ncol, cc = 4 + t, i = rr * TS + cc;
+            const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;             // the same for column cc - 2
+            float hm2 = horig[i - 2];
+            if ((t & 3) < 2 && t >= 2) hm2 = h_from_originals(i - 2, sgn, horig[i - 4]);
+            W.hcd[i] = h_from_originals(i, sgn, hm2);
+        }
+        C.sync();
+        if (tid < ncol) {
+            const int cc = 4 + tid;
+            float vup[2] = {0.0f, 0.0f};                                  // updated vcd of row rr-2 (same parity)
+            struct VIn { float c0, cu, cd, v0, vm2, vp2, va, vam2, vap2, h; };
+            auto load_v = [&](int rr) {
+                VIn Q;
+                const int i = rr * TS + cc;
+                Q.c0 = cfa[i]; Q.cu = cfa[i - V1]; Q.cd = cfa[i + V1];
+                Q.v0 = W.vcd[i]; Q.vm2 = W.vcd[i - V2]; Q.vp2 = W.vcd[i + V2];   // vm2 only matters for rows 4, 5 (rows 2, 3 are never updated)
+                Q.va = W.vcdalt[i]; Q.vam2 = W.vcdalt[i - V2]; Q.vap2 = W.vcdalt[i + V2];
+                Q.h = W.hcd[i];
+                return Q;
+            };
+            VIn cur = {}, nx1 = {};
+            if (4 < rr1 - 4) cur = load_v(4);
+            if (5 < rr1 - 4) nx1 = load_v(5);
+            for (int rr = 4; rr < rr1 - 4; rr++) {
+                VIn nx2 = {};
+                if (rr + 2 < rr1 - 4) nx2 = load_v(rr + 2);               // two rows ahead: rows rr+1, rr+2 are still original
+                const int i = rr * TS + cc;
+                const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
+                const float vm2 = rr >= 6 ? vup[rr & 1] : cur.vm2;
+                float v = (var3(cur.vam2, cur.va, cur.vap2) < var3(vm2, cur.v0, cur.vp2)) ? cur.va : cur.v0;
+                v = bound_cd(v, cur.c0, cur.cu, cur.cd, sgn);
                 vup[rr & 1] = v;
-                if (lane >= 2) S.row[buf][tid] = h;
+                W.vcd[i] = v;
+                W.cddiffsq[i] = sq(v - cur.h);
+                cur = nx1; nx1 = nx2;
             }
-            C.sync();
-            if (active) {
-                if (lane < 2 && tid >= 2) {                               // left neighbour is lane 2/3 of the previous vector: updated
-                    const float hm2u = S.row[buf][tid - 2];
-                    h = (havar < var3(hm2u, h0, hp2)) ? ha : h0;
-                    h = bound_cd(h, c0, cur.cl, cur.cr, sgn);
-                }
-                W.hcd[i] = h; W.vcd[i] = v;
-                W.cddiffsq[i] = sq(v - h);
-            }
-            cur = nxt;
         }
     }
     C.sync();
@@ -386,32 +393,76 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
 
     if (anynyq) {
         // ---- 3x3 vote, raster-sequential and in place (:998-1010) ----
-        for (int rr = 8; rr < rr1 - 8; rr++) {
-            if (S.rowcnt[rr - 2] + S.rowcnt[rr - 1] + S.rowcnt[rr] + S.rowcnt[rr + 1] + S.rowcnt[rr + 2] == 0) continue;   // stays all zero
-            const int par = fc(rr, 2) & 1, ns = cdiv(cc1 - 16 - par, 2);
-            for (int k = tid; k < ns; k += nthr) {
-                const int i = rr * TS + 8 + par + 2 * k;
-                S.oth[k] = nyquist[(i - V2) >> 1] + nyquist[(i - M1) >> 1] + nyquist[(i + P1) >> 1] + nyquist[(i + 2) >> 1] +
-                           nyquist[(i - P1) >> 1] + nyquist[(i + M1) >> 1] + nyquist[(i + V2) >> 1];
-                S.old[k] = nyquist[i >> 1];
-            }
-            C.sync();
-            if (tid == 0) {
-                int x = nyquist[(rr * TS + 8 + par - 2) >> 1], cnt = 0;
-                for (int k = 0; k < ns; k++) {
-                    const int n = S.oth[k] + S.old[k] + x;
-                    x = n > 4 ? 1 : (n < 4 ? 0 : S.old[k]);
-                    nyquist[(rr * TS + 8 + par + 2 * k) >> 1] = (unsigned char)x;
-                    cnt += x;
+        // A cell's new value depends on the new value of the cell two columns to its left: x' = vote(sum of the seven
+        // other neighbours + own old value + x'_left).  For a fixed row that is a two-state automaton, so the row is
+        // a scan over function composition: warp 0 alone walks the rows (rows still run in order -- each reads the
+        // voted row above), three neighbouring cells per lane, the lanes' composed transition functions combined by
+        // a warp scan through shared memory.  The other warps wait at the barrier below.
+        if (tid < 32) {
+            const int lane = tid;
+            for (int rr = 8; rr < rr1 - 8; rr++) {
+                if (S.rowcnt[rr - 2] + S.rowcnt[rr - 1] + S.rowcnt[rr] + S.rowcnt[rr + 1] + S.rowcnt[rr + 2] == 0) continue;   // stays all zero
+                const int par = fc(rr, 2) & 1, ns = cdiv(cc1 - 16 - par, 2);
+                const int per = cdiv(ns, 32);                             // cells per lane (3 for a full tile), lane's cells are adjacent
+                int f0[4], f1[4], oldv[4];                                // per cell: next state for x'_left = 0 / 1
+                int F0 = 0, F1 = 1;                                       // the lane's composed function
+                for (int j = 0; j < per && j < 4; j++) {
+                    const int k = lane * per + j;
+                    f0[j] = 0; f1[j] = 1; oldv[j] = 0;
+                    if (k < ns) {
+                        const int i = rr * TS + 8 + par + 2 * k;
+                        const int oth = nyquist[(i - V2) >> 1] + nyquist[(i - M1) >> 1] + nyquist[(i + P1) >> 1] + nyquist[(i + 2) >> 1] +
+                                        nyquist[(i - P1) >> 1] + nyquist[(i + M1) >> 1] + nyquist[(i + V2) >> 1];
+                        const int old = nyquist[i >> 1], n = oth + old;
+                        oldv[j] = old;
+                        f0[j] = n > 4 ? 1 : (n < 4 ? 0 : old);
+                        f1[j] = n + 1 > 4 ? 1 : (n + 1 < 4 ? 0 : old);
+                    }
+                    F0 = F0 ? f1[j] : f0[j];
+                    F1 = F1 ? f1[j] : f0[j];
                 }
-                // cells of this row outside the voted range keep their test result
-                const int i0 = rr * TS;
-                for (int c2 = 6 + par; c2 < 8 + par; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
-                for (int c2 = 8 + par + 2 * ns; c2 < cc1 - 6; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
-                S.rowcnt[rr] = cnt;
+                // inclusive scan of "apply the lanes to the left first": two bits per lane, double-buffered
+                int buf = 0;
+                S.scan[0][lane] = F0 | (F1 << 1);
+                C.syncwarp();
+                for (int d = 1; d < 32; d <<= 1) {
+                    int mine = S.scan[buf][lane];
+                    if (lane >= d) {
+                        const int left = S.scan[buf][lane - d];           // covers the lanes before mine's range
+                        const int m0 = (left & 1) ? (mine >> 1) & 1 : mine & 1, m1 = (left & 2) ? (mine >> 1) & 1 : mine & 1;
+                        mine = m0 | (m1 << 1);
+                    }
+                    S.scan[buf ^ 1][lane] = mine;
+                    buf ^= 1;
+                    C.syncwarp();
+                }
+                int x = nyquist[(rr * TS + 8 + par - 2) >> 1];             // the cell left of the voted range keeps its value
+                if (lane > 0) { const int pre = S.scan[buf][lane - 1]; x = x ? (pre >> 1) & 1 : pre & 1; }
+                int cnt = 0;
+                for (int j = 0; j < per && j < 4; j++) {
+                    const int k = lane * per + j;
+                    if (k < ns) {
+                        x = x ? f1[j] : f0[j];
+                        nyquist[(rr * TS + 8 + par + 2 * k) >> 1] = (unsigned char)x;
+                        cnt += x;
+                    }
+                }
+                if (lane == 0) {
+                    // cells of this row outside the voted range keep their test result
+                    const int i0 = rr * TS;
+                    for (int c2 = 6 + par; c2 < 8 + par; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
+                    for (int c2 = 8 + par + 2 * ns; c2 < cc1 - 6; c2 += 2) cnt += nyquist[(i0 + c2) >> 1];
+                    S.votecnt = 0;
+                }
+                C.syncwarp();
+                if (cnt) C.atomic_add(&S.votecnt, cnt);
+                C.syncwarp();
+                if (lane == 0) S.rowcnt[rr] = S.votecnt;
+                C.syncwarp();
             }
-            C.sync();
         }
+        C.sync();
+
         // ---- area interpolation inside Nyquist regions (:1016-1045) ----
         for (int par = 0; par < 2; par++) {
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
@@ -436,78 +487,68 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         C.sync();
     }
 
-    // ---- hvwt refinement from the diagonal neighbours, row after row (:1054-1058), then
-    //      pmwt refinement + R+B estimate the same way (:1264-1274); both through the shared row buffer ----
-    for (int pass = 0; pass < 2; pass++) {
+    // ---- hvwt refinement from the diagonal neighbours, row after row (:1054-1058), and
+    //      pmwt refinement + R+B estimate the same way (:1264-1274) ----
+    // Each is a recurrence over the rows (a row reads the UPDATED row above and the ORIGINAL row below) with no
+    // dependency inside a row, and the two do not touch each other's planes: warp 0 walks hvwt while warp 1 walks
+    // pmwt, each with its own shared row buffer and warp-level synchronisation only (a block barrier per row would
+    // make all eight warps wait ~290 times per tile).  The originals of the next row are loaded before the current
+    // row's barrier.
+    if (tid < 64) {
+        const int pass = tid >> 5, lane = tid & 31;
         float *const P = pass ? pmwt : hvwt;
         const int r0 = pass ? 10 : 8;
-        for (int k = tid; k < TSH; k += nthr) S.row[(r0 - 1) & 1][k] = P[(r0 - 1) * TSH + k];
-        C.sync();
-        // a row reads its own and the next row's original values plus the previous row's updated ones (through the
-        // shared row buffer): with one site per thread the originals of row rr+1 are loaded before row rr's barrier
+        float (*rowbuf)[TS] = S.row[pass];
+        for (int k = lane; k < TSH; k += 32) rowbuf[(r0 - 1) & 1][k] = P[(r0 - 1) * TSH + k];
+        C.syncwarp();
         struct RefIn { float t, dl, dr, c, m, p; bool in; };
         auto load_ref = [&](int rr, int k) {
-            RefIn L = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
-            const int par = fc(rr, 2) & 1;
-            const int ns = pass ? 4 * cdiv(cc1 - 20 - par, 8) : cdiv(cc1 - 16 - par, 2);
-            const int k0 = (r0 + par) >> 1;
-            L.t = P[rr * TSH + k];
-            L.in = k >= k0 && k < k0 + ns;
-            if (L.in) {
-                L.dl = P[(rr + 1) * TSH + k - 1 + par]; L.dr = P[(rr + 1) * TSH + k + par];
-                if (pass) { L.c = cfa[rr * TS + 2 * k + par]; L.m = W.rbm[rr * TSH + k]; L.p = W.rbp[rr * TSH + k]; }
-            }
-            return L;
-        };
-        const bool one_site = nthr >= TSH;                                  // every thread owns at most one half-row site
-        RefIn cur_in = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
-        if (one_site && tid < TSH && r0 < rr1 - r0) cur_in = load_ref(r0, tid);
-        for (int rr = r0; rr < rr1 - r0; rr++) {
+            RefIn Q = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
+            if (k >= TSH) return Q;
             const int par = fc(rr, 2) & 1;
             // processed sites: scalar bound for hvwt, whole 4-site vectors for pmwt
             const int ns = pass ? 4 * cdiv(cc1 - 20 - par, 8) : cdiv(cc1 - 16 - par, 2);
             const int k0 = (r0 + par) >> 1;                                // half index of the first processed site
-            const float *prev = S.row[(rr - 1) & 1];
-            float *cur = S.row[rr & 1];
-            if (one_site) {
-                RefIn nxt_in = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, false};
-                if (tid < TSH) {
-                    const int k = tid;
-                    if (rr + 1 < rr1 - r0) nxt_in = load_ref(rr + 1, k);
-                    float t = cur_in.t;
-                    if (cur_in.in) {
-                        const float ul = prev[k - 1 + par], ur = prev[k + par];
-                        const float s4 = ul + ur + cur_in.dl + cur_in.dr;
-                        const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
-                        t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
-                        P[rr * TSH + k] = t;
-                        if (pass) W.rbint[rr * TSH + k] = 0.5f * (cur_in.c + cur_in.m * (1.0f - t) + cur_in.p * t);
-                    }
-                    cur[k] = t;
-                }
-                cur_in = nxt_in;
-            } else {
-                for (int k = tid; k < TSH; k += nthr) {
-                    float t = P[rr * TSH + k];
-                    if (k >= k0 && k < k0 + ns) {
-                        // diagonal neighbours: previous row (updated) at half indices k-1+par, k+par; next row (original)
-                        const float ul = prev[k - 1 + par], ur = prev[k + par];
-                        const float dl = P[(rr + 1) * TSH + k - 1 + par], dr = P[(rr + 1) * TSH + k + par];
-                        const float s4 = ul + ur + dl + dr;
-                        const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
-                        t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
-                        P[rr * TSH + k] = t;
-                        if (pass) {
-                            const int i = rr * TS + 2 * k + par;
-                            W.rbint[rr * TSH + k] = 0.5f * (cfa[i] + W.rbm[rr * TSH + k] * (1.0f - t) + W.rbp[rr * TSH + k] * t);
-                        }
-                    }
-                    cur[k] = t;
-                }
+            Q.t = P[rr * TSH + k];
+            Q.in = k >= k0 && k < k0 + ns;
+            if (Q.in) {
+                Q.dl = P[(rr + 1) * TSH + k - 1 + par]; Q.dr = P[(rr + 1) * TSH + k + par];
+                if (pass) { Q.c = cfa[rr * TS + 2 * k + par]; Q.m = W.rbm[rr * TSH + k]; Q.p = W.rbp[rr * TSH + k]; }
             }
-            C.sync();
+            return Q;
+        };
+        constexpr int NS = (TSH + 31) / 32;                                // sites per lane: k = lane, lane + 32, lane + 64
+        RefIn cur_in[NS] = {}, nxt_in[NS] = {};
+        if (r0 < rr1 - r0)
+            for (int j = 0; j < NS; j++) cur_in[j] = load_ref(r0, lane + 32 * j);
+        for (int rr = r0; rr < rr1 - r0; rr++) {
+            const int par = fc(rr, 2) & 1;
+            const float *prev = rowbuf[(rr - 1) & 1];
+            float *cur = rowbuf[rr & 1];
+            if (rr + 1 < rr1 - r0)
+                for (int j = 0; j < NS; j++) nxt_in[j] = load_ref(rr + 1, lane + 32 * j);
+            for (int j = 0; j < NS; j++) {
+                const int k = lane + 32 * j;
+                if (k >= TSH) continue;
+                float t = cur_in[j].t;
+                if (cur_in[j].in) {
+                    // diagonal neighbours: previous row (updated) at half indices k-1+par, k+par; next row (original)
+                    const float ul = prev[k - 1 + par], ur = prev[k + par];
+                    const float s4 = ul + ur + cur_in[j].dl + cur_in[j].dr;
+                    const float alt = pass ? 0.25f * s4 : expdec(s4, 2);
+                    t = ab(0.5f - t) < ab(0.5f - alt) ? alt : t;
+                    P[rr * TSH + k] = t;
+                    if (pass) W.rbint[rr * TSH + k] = 0.5f * (cur_in[j].c + cur_in[j].m * (1.0f - t) + cur_in[j].p * t);
+                }
+                cur[k] = t;
+            }
+            C.syncwarp();
+            for (int j = 0; j < NS; j++) cur_in[j] = nxt_in[j];
         }
-        if (pass) break;
+    }
+    C.sync();
+    {
+
         // ---- G at R/B sites with the final hvwt (:1063-1074) ----
         for (int par = 0; par < 2; par++) {
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;

@@ -262,6 +262,34 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         row[x] = (uint16_t)v;
         E[3] = ev_of_raw(v);
     };
+    // A stretch of `cnt` entries at consecutive columns x0, x0 + 1, .. (all interior): what --really-bad-pix makes of
+    // every bright row of a dual-ISO frame (cs.c:289-304 flags each of its pixels), one recurrence of thousands of
+    // steps.  Same arithmetic as interp_h step by step; the loop carries the three repaired EVs to the left and the
+    // three original EVs to the right in registers, fetches the next original ahead of its use, and has no per-entry
+    // list lookups or window rebuilds, so a step costs little more than its own dependency chain.
+    auto walk_dense = [&](int x0, int cnt) {
+        int e0 = ev_of_raw(row[x0 - 3]), e1 = ev_of_raw(row[x0 - 2]), e2 = ev_of_raw(row[x0 - 1]);
+        int r2 = row[x0 + 2], r3 = row[x0 + 3];
+        int o1 = ev_of_raw(row[x0 + 1]), o2 = ev_of_raw(r2), o3 = ev_of_raw(r3);
+        for (int x = x0; x < x0 + cnt; x++) {
+            const int rn = x + 1 < x0 + cnt ? (int)row[x + 4] : 0;              // the next original, needed one step later
+            const int d1 = wabs(wsub(o3, o1)), d2 = wabs(wsub(e2, e0));
+            const int sum = wadd(d1, d2);
+            int v;
+            if (sum == 0) v = r2;                                               // row[x + 2] (cs.c:96-99)
+            else {
+                int c1, c2;
+                if (d1 >= 0 && d2 >= 0 && sum > 0 && sum < (1 << 22)) { c1 = div8(sum - d1, sum); c2 = div8(sum - d2, sum); }
+                else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }
+                const int ev = (wmul(o2, c1) >> 8) + (wmul(e1, c2) >> 8);
+                v = (raw_of_ev(ev) + black) & 0xFFFF;
+            }
+            row[x] = (uint16_t)v;
+            e0 = e1; e1 = e2; e2 = ev_of_raw(v);
+            o1 = o2; o2 = o3; r2 = r3; r3 = rn; o3 = ev_of_raw(rn);
+        }
+        lastx = -100;                                                           // the next entry rebuilds its EV window from the row
+    };
     const unsigned total = nlong * (unsigned)nframes;
     for (unsigned t = blockIdx.x * warps_per_block + warp; t < total; t += gridDim.x * warps_per_block) {
         const unsigned ridx = t % nlong, frame = t / nlong;
@@ -287,11 +315,13 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         };
         // ascending rows (a detected bad-pixel list is in raster order) are repaired window by window in shared memory;
         // anything else (a focus-pixel map in file order) by one lane directly on the frame
-        bool ascending = true;
+        bool ascending = true, strict = true;                                 // strict: no column listed twice
         for (unsigned mb = m0; mb < m1; mb += 32) {
             const unsigned m = mb + lane;
             const bool bad = m + 1 < m1 && A.list[m + 1].x < A.list[m].x;
+            const bool dup = m + 1 < m1 && A.list[m + 1].x == A.list[m].x;
             ascending = ascending && !__any_sync(0xFFFFFFFFu, bad);
+            strict = strict && !__any_sync(0xFFFFFFFFu, dup);
         }
         if (!ascending) {
             if (lane == 0) {
@@ -335,7 +365,15 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
                         lastx = -100;                                           // (re)build the EV window from the staged pixels
                         int j = i, xx = x;
                         while (true) {
-                            one_entry(xx);
+                            // strictly increasing columns: entries j .. j + len - 1 are consecutive iff the last one is
+                            // len - 1 columns to the right of the first -- the longest such stretch by halving
+                            int len = 1;
+                            if (strict && xx > 2) {
+                                len = nin - j;
+                                while (len > 1 && ((int)xs[j + len - 1] - 1 - xx != len - 1 || xx + len - 1 >= w - 3)) len >>= 1;
+                            }
+                            if (len >= 8) { walk_dense(xx, len); j += len - 1; xx += len - 1; }
+                            else one_entry(xx);
                             if (++j >= nin) break;
                             const int xnext = (int)xs[j] - 1;
                             if (xnext - xx > 3) break;

@@ -7,6 +7,7 @@
 // dependencies; `poison` fills the workspace with NaN first (a reused workspace holds another tile's data).
 #include <barrier>
 #include <cstdlib>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -15,8 +16,9 @@
 namespace {
 struct HostCtx {
     int tid, nthr;
-    std::barrier<> *bar;
+    std::barrier<> *bar, *wbar;                    // block barrier; this thread's warp barrier (32 threads)
     void sync() { bar->arrive_and_wait(); }
+    void syncwarp() { wbar->arrive_and_wait(); }
     void atomic_add(int *p, int v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 };
 }  // namespace
@@ -32,11 +34,13 @@ extern "C" void amaze_emu(const float *raw, float *red, float *green, float *blu
             amaze::Geom G = amaze::tile_geom(width, height, top, left);
             amaze::Shared S;
             std::barrier<> bar(nthr);
+            std::vector<std::unique_ptr<std::barrier<>>> wbars;     // nthr is a multiple of 32 (like the CUDA launch)
+            for (int wdx = 0; wdx < nthr / 32; wdx++) wbars.emplace_back(new std::barrier<>(32));
             std::vector<std::thread> th;
             for (int t = 0; t < nthr; t++) {
                 const int tid = order == 0 ? t : order == 1 ? nthr - 1 - t : (t * 37 + 11) % nthr;
                 th.emplace_back([&, tid]() {
-                    HostCtx C{tid, nthr, &bar};
+                    HostCtx C{tid, nthr, &bar, wbars[tid / 32].get()};
                     amaze::tile_body(C, W, G, S, raw, red, green, blue, stride);
                 });
             }
