@@ -41,10 +41,20 @@ int amz_blocks()
     return v;
 }
 
+#ifdef AMZ_PROFILE
+__device__ unsigned long long g_amz_prof[32];      // cycles per section of the tile program, summed over tiles (thread 0 of each block)
+#endif
+
 namespace {
 
 struct CudaCtx {
     int tid, nthr;
+#ifdef AMZ_PROFILE
+    long long last;
+    __device__ __forceinline__ void mark(int k) { if (tid == 0) { const long long now = clock64(); atomicAdd(&g_amz_prof[k], (unsigned long long)(now - last)); last = now; } }
+#else
+    __device__ __forceinline__ void mark(int) {}
+#endif
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
     __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }
@@ -70,6 +80,9 @@ amz_tiles_kernel(const float *__restrict__ raw, float *__restrict__ red, float *
     __shared__ unsigned s_tile;
     const amaze::Ws W = amaze::carve(ws_base + (size_t)blockIdx.x * amaze::WS_BYTES);
     CudaCtx C{(int)threadIdx.x, (int)blockDim.x};
+#ifdef AMZ_PROFILE
+    C.last = clock64();
+#endif
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(counter, 1u);
         __syncthreads();
@@ -77,6 +90,9 @@ amz_tiles_kernel(const float *__restrict__ raw, float *__restrict__ red, float *
         if (t >= (unsigned)(ntx * nty)) break;
         const int ty = t / ntx, tx = t - ty * ntx;
         const amaze::Geom G = amaze::tile_geom(width, height, -16 + ty * (amaze::TS - 32), -16 + tx * (amaze::TS - 32));
+#ifdef AMZ_PROFILE
+        C.mark(31);                                                      // tile fetch
+#endif
         amaze::tile_body(C, W, G, S, raw, red, green, blue, stride);
         __syncthreads();
     }
@@ -198,6 +214,21 @@ int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int whi
                                                                   d_fullres_lim);
     if (launches) *launches += 4;
     MLVB_CUDA_OK(cudaGetLastError());
+#ifdef AMZ_PROFILE
+    {   // debug build only (make EXTRA=-DAMZ_PROFILE): cycles of thread 0 per section of the tile program, summed over tiles
+        static int calls = 0;
+        if (++calls == 8) {
+            unsigned long long prof[32];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(prof, g_amz_prof, sizeof(prof));
+            unsigned long long tot = 0;
+            for (int k = 0; k < 32; k++) tot += prof[k];
+            for (int k = 0; k < 32; k++)
+                if (prof[k]) fprintf(stderr, "amz section %2d: %6.2f %%  (%.1f us per tile)\n", k, 100.0 * prof[k] / tot,
+                                     prof[k] / 1.965e3 / (8.0 * ntx * nty));
+        }
+    }
+#endif
     return MLVB_OK;
 }
 

@@ -155,6 +155,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     for (int k = tid; k < TS; k += nthr) S.rowcnt[k] = 0;
     if (tid == 0) S.anynyq = 0;
     C.sync();
+    C.mark(0);
 
     // ---- load + mirrored borders (:378-469); the bottom border may run past row 159 like the reference's ----
     {
@@ -180,6 +181,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(1);
 
     // ---- gradients, directional weights (:553-567) and diagonal gradients (:581-606) ----
     {
@@ -203,6 +205,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(2);
 
     // ---- H/V colour differences (:633-689) and the diagonal R/B estimates (:1115-1180) ----
     {
@@ -282,6 +285,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(3);
 
     // ---- variance-based choice + bounding (:748-803) ----
     // The reference runs this in place, four columns at a time: lanes 0 and 1 of a vector see the already updated
@@ -299,6 +303,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         float *const horig = W.Dgrb2;                                     // free until the G pass writes it
         for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * TS; idx += nthr) horig[4 * TS + idx] = W.hcd[4 * TS + idx];
         C.sync();
+        C.mark(4);
         auto h_from_originals = [&](int i, float sgn, float hm2) {        // hm2: original or updated left neighbour
             const float h0 = horig[i], ha = W.hcdalt[i];
             const float havar = var3(W.hcdalt[i - 2], ha, W.hcdalt[i + 2]);
@@ -313,6 +318,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             W.hcd[i] = h_from_originals(i, sgn, hm2);
         }
         C.sync();
+        C.mark(5);
         if (tid < ncol) {
             const int cc = 4 + tid;
             float vup[2] = {0.0f, 0.0f};                                  // updated vcd of row rr-2 (same parity)
@@ -345,6 +351,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(6);
 
     // ---- H/V weight (:876-920) and Nyquist texture test (:967-996) ----
     for (int par = 0; par < 2; par++) {
@@ -389,6 +396,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(7);
     const bool anynyq = S.anynyq != 0;                                    // block-uniform
 
     if (anynyq) {
@@ -462,6 +470,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             }
         }
         C.sync();
+        C.mark(8);
 
         // ---- area interpolation inside Nyquist regions (:1016-1045) ----
         for (int par = 0; par < 2; par++) {
@@ -485,6 +494,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             }
         }
         C.sync();
+        C.mark(9);
     }
 
     // ---- hvwt refinement from the diagonal neighbours, row after row (:1054-1058), and
@@ -547,6 +557,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(10);
     {
 
         // ---- G at R/B sites with the final hvwt (:1063-1074) ----
@@ -566,6 +577,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             }
         }
         C.sync();
+        C.mark(11);
         // ---- refine Nyquist sites with the local G curvature (:1085-1102) ----
         if (anynyq) {
 #define AMZ_D2H(k) W.Dgrb2[2 * ((k) >> 1)]
@@ -589,6 +601,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
 #undef AMZ_D2H
 #undef AMZ_D2V
             C.sync();
+            C.mark(12);
         }
     }
 
@@ -634,6 +647,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(13);
 
     // ---- split G-B out of the G-R plane at the B sites (:1358-1362) ----
     {
@@ -645,6 +659,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(14);
 
     // ---- chroma at the opposite-colour sites from the four diagonal neighbours (:1369-1383) ----
     for (int par = 0; par < 2; par++) {
@@ -666,6 +681,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         }
     }
     C.sync();
+    C.mark(15);
 
     // ---- write red, blue (:1400-1445) and green (:1451-1455) ----
     {

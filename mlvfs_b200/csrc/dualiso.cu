@@ -373,6 +373,15 @@ __device__ __forceinline__ double curve_at(const double *__restrict__ curve, con
     if (i >= __ldg(lim + 1)) return 1.0;
     return __ldg(curve + i);
 }
+// The same value without a branch: the fetch always happens, from an index clamped into the non-flat range (a neighbour
+// of what the other lanes fetch), and the flat ends are selected afterwards.  Lets the compiler issue the gathers of
+// several pixels of one thread back to back.
+__device__ __forceinline__ double curve_at_nb(const double *__restrict__ curve, int lo, int hi, int i)
+{
+    const int j = hi > lo ? min(max(i, lo), hi - 1) : 0;
+    const double v = __ldg(curve + j);
+    return i < lo ? 0.0 : (i >= hi ? 1.0 : v);
+}
 __device__ __forceinline__ bool fullres_above_thr(const double *__restrict__ curve, const int *__restrict__ lim, int i)
 {
     const int lo = __ldg(lim + 2), hi = __ldg(lim + 3);
@@ -384,16 +393,52 @@ __device__ __forceinline__ bool fullres_above_thr(const double *__restrict__ cur
 __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_t *__restrict__ bright, uint32_t *__restrict__ halfres,
                                 uint8_t *__restrict__ over, uint8_t *__restrict__ skip, const PixParams P)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, np = (size_t)P.w * P.h;
-    if (i >= np) return;
-    const int b = (int)bright[i], d = (int)dark[i];
-    const double k = curve_at(P.mix_curve, P.mix_lim, b & 0xFFFFF);
-    // a term with weight exactly 0.0 contributes exactly 0 (the table values are finite): its gather is skipped
-    const double evb = k < 1.0 ? (double)__ldg(P.raw2ev + b) : 0.0, evd = k > 0.0 ? (double)__ldg(P.raw2ev + d) : 0.0;
-    const int mixed = (int)(evb * (1.0 - k) + evd * k);
-    halfres[i] = (uint32_t)__ldg(P.ev2raw + mixed);
-    over[i] = (b >= P.white_darkened || d >= P.white) ? 100 : 0;
-    skip[i] = fullres_above_thr(P.fullres_curve, P.fullres_lim, b & 0xFFFFF);
+    // two pixels per thread (i and i + half), each stage for both before the next: see diso_final_kernel
+    constexpr int K = 2;
+    const size_t np = (size_t)P.w * P.h, half = (np + K - 1) / K;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= half) return;
+    const int mlo = __ldg(P.mix_lim), mhi = __ldg(P.mix_lim + 1);
+    const int tlo = __ldg(P.fullres_lim + 2), thi = __ldg(P.fullres_lim + 3);
+    size_t i[K];
+    bool ok[K];
+    int b[K], d[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        ok[k] = t + k * half < np;
+        i[k] = ok[k] ? t + k * half : t;
+        b[k] = (int)bright[i[k]]; d[k] = (int)dark[i[k]];
+    }
+    double kk[K], fc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        kk[k] = curve_at_nb(P.mix_curve, mlo, mhi, b[k] & 0xFFFFF);
+        // fullres_above_thr: a plain comparison when the curve crosses the threshold once, else the table value
+        fc[k] = tlo == thi ? 0.0 : __ldg(P.fullres_curve + (b[k] & 0xFFFFF));
+    }
+    double evb[K], evd[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        // a term with weight exactly 0.0 contributes exactly 0 (the table values are finite): fetched from index 0
+        evb[k] = (double)__ldg(P.raw2ev + (kk[k] < 1.0 ? b[k] : 0));
+        evd[k] = (double)__ldg(P.raw2ev + (kk[k] > 0.0 ? d[k] : 0));
+    }
+    int mixed[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double eb = kk[k] < 1.0 ? evb[k] : 0.0, ed = kk[k] > 0.0 ? evd[k] : 0.0;
+        mixed[k] = (int)(eb * (1.0 - kk[k]) + ed * kk[k]);
+    }
+    uint32_t hr[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) hr[k] = (uint32_t)__ldg(P.ev2raw + mixed[k]);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (!ok[k]) continue;
+        halfres[i[k]] = hr[k];
+        over[i[k]] = (b[k] >= P.white_darkened || d[k] >= P.white) ? 100 : 0;
+        skip[i[k]] = tlo == thi ? ((b[k] & 0xFFFFF) >= tlo) : (fc[k] > FULLRES_THR);
+    }
 }
 
 // alias map, pass 1 (hdr.c:1397-1415)
@@ -498,28 +543,63 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
                                   const uint32_t *__restrict__ frs, const uint32_t *__restrict__ hrs, const uint8_t *__restrict__ over,
                                   const uint16_t *__restrict__ amap, uint16_t *__restrict__ out16, const PixParams P)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    // Two rows per thread, every stage written for both pixels before the next one: the kernel is a chain of four
+    // dependent memory accesses per pixel (sample -> curve -> EV tables -> inverse table) and waits on their latency,
+    // so a thread keeps two chains in flight.  Gathers whose weight is exactly 0.0 are fetched from index 0 instead of
+    // being branched around (a finite value times 0.0 adds nothing, as before).
+    constexpr int K = 2;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y0 = blockIdx.y * K;
     if (x >= P.w) return;
-    const size_t i = x + (size_t)y * P.w;
-    const int b = (int)bright[i];
-    double f = curve_at(P.fullres_curve, P.fullres_lim, b & 0xFFFFF), c = 0.0;
-    if (P.use_alias) c = fmax(fmin((double)amap[i] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
-    const double ovf = fmax(fmin((double)over[i] / 200.0, 1.0), 0.0);
-    c = fmax(c, ovf);
-    const double noo = fmax(ovf, 1.0 - f);
-    f = fmax(f, c);
-    const int sig = (int)((dark[i] + bright[i]) / 2);
-    f = fmax(0.0, fmin(f, (double)(sig - P.black) / (double)(4 * DARK_NOISE)));
-    // the three EV gathers are weighted by (1 - f), f * noo and f * (1 - noo); a weight of exactly 0.0 contributes
-    // exactly 0 (finite table values), so that gather is skipped -- most pixels need one of the three
-    const double hrev = f < 1.0 ? (double)__ldg(P.raw2ev + hrs[i]) : 0.0;
-    const double frsev = (f > 0.0 && noo > 0.0) ? (double)__ldg(P.raw2ev + frs[i]) : 0.0;
-    const double frev = (f > 0.0 && noo < 1.0) ? (double)__ldg(P.raw2ev + fullres[i]) : 0.0;
-    const double fev = noo * frsev + (1.0 - noo) * frev;
-    int o = (int)(hrev * (1.0 - f) + fev * f);
-    o = min(max(o, -10 * EVR), 14 * EVR - 1);
-    const uint32_t v20 = (uint32_t)__ldg(P.ev2raw + o);
-    out16[i] = (uint16_t)min(max((int)((double)v20 / 16.0 + 0.5), 0), 0xFFFF);
+    const int flo = __ldg(P.fullres_lim), fhi = __ldg(P.fullres_lim + 1);
+    size_t i[K];
+    bool ok[K];
+    uint32_t b[K], d[K], fr[K], fs[K], hs[K];
+    int ov[K], am[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        ok[k] = y0 + k < P.h;
+        i[k] = x + (size_t)(ok[k] ? y0 + k : y0) * P.w;
+        b[k] = bright[i[k]]; d[k] = dark[i[k]]; fr[k] = fullres[i[k]]; fs[k] = frs[i[k]]; hs[k] = hrs[i[k]];
+        ov[k] = over[i[k]];
+        am[k] = P.use_alias ? (int)amap[i[k]] : 0;
+    }
+    double f[K], noo[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) f[k] = curve_at_nb(P.fullres_curve, flo, fhi, (int)b[k] & 0xFFFFF);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double c = 0.0;
+        if (P.use_alias) c = fmax(fmin((double)am[k] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
+        const double ovf = fmax(fmin((double)ov[k] / 200.0, 1.0), 0.0);
+        c = fmax(c, ovf);
+        noo[k] = fmax(ovf, 1.0 - f[k]);
+        f[k] = fmax(f[k], c);
+        const int sig = (int)((d[k] + b[k]) / 2);
+        f[k] = fmax(0.0, fmin(f[k], (double)(sig - P.black) / (double)(4 * DARK_NOISE)));
+    }
+    // the three EV gathers are weighted by (1 - f), f * noo and f * (1 - noo)
+    double hrev[K], frsev[K], frev[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        hrev[k] = (double)__ldg(P.raw2ev + (f[k] < 1.0 ? hs[k] : 0u));
+        frsev[k] = (double)__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] > 0.0) ? fs[k] : 0u));
+        frev[k] = (double)__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] < 1.0) ? fr[k] : 0u));
+    }
+    int o[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double h0 = f[k] < 1.0 ? hrev[k] : 0.0, s0 = (f[k] > 0.0 && noo[k] > 0.0) ? frsev[k] : 0.0;
+        const double r0 = (f[k] > 0.0 && noo[k] < 1.0) ? frev[k] : 0.0;
+        const double fev = noo[k] * s0 + (1.0 - noo[k]) * r0;
+        o[k] = (int)(h0 * (1.0 - f[k]) + fev * f[k]);
+        o[k] = min(max(o[k], -10 * EVR), 14 * EVR - 1);
+    }
+    uint32_t v20[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) v20[k] = (uint32_t)__ldg(P.ev2raw + o[k]);
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        if (ok[k]) out16[i[k]] = (uint16_t)min(max((int)((double)v20[k] / 16.0 + 0.5), 0), 0xFFFF);
 }
 
 // ------------------------------------------------------------------ host: tables and scalar epilogues
@@ -966,7 +1046,7 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
     }
     if (P.method == 0) diso_interp_kernel<false><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
     else diso_interp_kernel<true><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
-    diso_mix_kernel<<<g1, 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
+    diso_mix_kernel<<<ceil_div((np + 1) / 2, 256), 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
     ctx->launches += 2;
     const uint32_t *frs = D.fullres, *hrs = D.halfres;
     if (cs_method == 2 || cs_method == 3 || cs_method == 5) {
@@ -991,7 +1071,7 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
         ctx->launches += 3;
     }
     diso_over_blur_kernel<<<g2, 256, 0, st>>>(D.over, D.over2, w, h);
-    diso_final_kernel<<<g2, 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
+    diso_final_kernel<<<dim3(ceil_div(w, 256), (h + 1) / 2), 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
     ctx->launches += 2;
     MLVB_CUDA_OK(cudaGetLastError());
     return 1;

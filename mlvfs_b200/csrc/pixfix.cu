@@ -279,8 +279,16 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
             if (sum == 0) v = r2;                                               // row[x + 2] (cs.c:96-99)
             else {
                 int c1, c2;
-                if (d1 >= 0 && d2 >= 0 && sum > 0 && sum < (1 << 22)) { c1 = div8(sum - d1, sum); c2 = div8(sum - d2, sum); }
-                else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }
+                if ((unsigned)(d1 | d2) < (1u << 21)) {
+                    // 0 <= d1, d2 < 2^21: one division gives both weights.  c1 = floor(256 d2 / sum) from a float
+                    // estimate corrected by its remainder; d1 + d2 = sum, so c2 = floor(256 d1 / sum) = 256 - ceil(256 d2 / sum)
+                    const int n8 = d2 << 8;
+                    int q = __float2int_rz(__fdividef((float)n8, (float)sum));
+                    int r = n8 - q * sum;
+                    if (r >= sum) { q++; r -= sum; } else if (r < 0) { q--; r += sum; }
+                    c1 = q;
+                    c2 = 256 - q - (r != 0);
+                } else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }   // wrap-around cases (pixels at black)
                 const int ev = (wmul(o2, c1) >> 8) + (wmul(e1, c2) >> 8);
                 v = (raw_of_ev(ev) + black) & 0xFFFF;
             }

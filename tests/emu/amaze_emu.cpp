@@ -19,6 +19,7 @@ struct HostCtx {
     std::barrier<> *bar, *wbar;                    // block barrier; this thread's warp barrier (32 threads)
     void sync() { bar->arrive_and_wait(); }
     void syncwarp() { wbar->arrive_and_wait(); }
+    void mark(int) {}
     void atomic_add(int *p, int v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 };
 }  // namespace
