@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #define MAX_CHUNKS 100
@@ -33,6 +34,9 @@ struct mlv_clip {
     int nframes;
     struct frame_headers *frames;   /* one fully resolved header bundle per video frame */
     uint8_t *has_rawi;
+    off_t size0;                    /* size and mtime of the first chunk when the index was built: a clip that was */
+    struct timespec mtime0;         /* re-recorded or is still growing is indexed again (the reference re-reads per request) */
+    int retired;                    /* replaced by a newer index; kept (callers may still hold it) until close_all */
 };
 
 static pthread_mutex_t g_clips_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -81,15 +85,28 @@ static void read_into(int fd, uint64_t off, void *dst, size_t want, uint32_t blo
         fprintf(stderr, "mlv_index: short header read at %llu\n", (unsigned long long)off);
 }
 
+static void free_clip(struct mlv_clip *c)
+{
+    if (!c) return;
+    for (int i = 0; i < c->nchunks; i++) close(c->fd[i]);
+    free(c->frames);
+    free(c->has_rawi);
+    free(c->path);
+    free(c);
+}
+
 static struct mlv_clip *build_clip(const char *path)
 {
     struct mlv_clip *c = calloc(1, sizeof(*c));
     if (!c) return NULL;
+    struct block_ref *blk = NULL, *tmp = NULL;
     c->nchunks = open_chunks(path, c->fd);
-    if (!c->nchunks) { free(c); return NULL; }
+    if (!c->nchunks) goto fail;
     c->path = strdup(path);
+    if (!c->path) goto fail;
+    struct stat st;
+    if (fstat(c->fd[0], &st) == 0) { c->size0 = st.st_size; c->mtime0 = st.st_mtim; }
 
-    struct block_ref *blk = NULL;
     size_t nblk = 0, cap = 0;
     uint64_t guid = 0;
     for (int ch = 0; ch < c->nchunks; ch++) {
@@ -113,8 +130,9 @@ static struct mlv_clip *build_clip(const char *path)
             if (memcmp(h.blockType, "NULL", 4)) {
                 if (nblk == cap) {
                     cap = cap ? cap * 2 : 1024;
-                    blk = realloc(blk, cap * sizeof(*blk));
-                    if (!blk) { free(c); return NULL; }
+                    struct block_ref *grown = realloc(blk, cap * sizeof(*blk));
+                    if (!grown) goto fail;
+                    blk = grown;
                 }
                 struct block_ref *b = &blk[nblk++];
                 b->time = t; b->offset = pos; b->chunk = (uint16_t)ch; b->size = h.blockSize;
@@ -125,12 +143,15 @@ static struct mlv_clip *build_clip(const char *path)
             pos += h.blockSize;
         }
     }
-    struct block_ref *tmp = malloc((nblk ? nblk : 1) * sizeof(*tmp));
+    tmp = malloc((nblk ? nblk : 1) * sizeof(*tmp));
+    if (!tmp) goto fail;
     sort_blocks(blk, tmp, nblk);
     free(tmp);
+    tmp = NULL;
 
     c->frames = calloc(c->nframes ? c->nframes : 1, sizeof(struct frame_headers));
     c->has_rawi = calloc(c->nframes ? c->nframes : 1, 1);
+    if (!c->frames || !c->has_rawi) goto fail;
     struct frame_headers cur;
     memset(&cur, 0, sizeof(cur));
     int rawi = 0, f = 0;
@@ -157,13 +178,30 @@ static struct mlv_clip *build_clip(const char *path)
     }
     free(blk);
     return c;
+fail:
+    fprintf(stderr, "mlv_index: cannot index '%s'\n", path);
+    free(blk);
+    free(tmp);
+    free_clip(c);
+    return NULL;
+}
+
+static int clip_is_stale(const struct mlv_clip *c)
+{
+    struct stat st;
+    if (stat(c->path, &st) != 0) return 0;                           /* vanished: keep serving the open descriptors */
+    return st.st_size != c->size0 || st.st_mtim.tv_sec != c->mtime0.tv_sec || st.st_mtim.tv_nsec != c->mtime0.tv_nsec;
 }
 
 struct mlv_clip *mlv_clip_open(const char *mlv_path)
 {
     pthread_mutex_lock(&g_clips_mu);
     struct mlv_clip *c = g_clips;
-    while (c && strcmp(c->path, mlv_path)) c = c->next;
+    while (c && (c->retired || strcmp(c->path, mlv_path))) c = c->next;
+    if (c && clip_is_stale(c)) {                                     /* re-recorded or still growing: index it again */
+        c->retired = 1;
+        c = NULL;
+    }
     if (!c) {
         c = build_clip(mlv_path);
         if (c) { c->next = g_clips; g_clips = c; }
@@ -217,11 +255,7 @@ void mlv_clip_close_all(void)
     pthread_mutex_lock(&g_clips_mu);
     while (g_clips) {
         struct mlv_clip *n = g_clips->next;
-        for (int i = 0; i < g_clips->nchunks; i++) close(g_clips->fd[i]);
-        free(g_clips->frames);
-        free(g_clips->has_rawi);
-        free(g_clips->path);
-        free(g_clips);
+        free_clip(g_clips);
         g_clips = n;
     }
     pthread_mutex_unlock(&g_clips_mu);

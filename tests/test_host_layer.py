@@ -117,6 +117,21 @@ def test_index_cache_matches_reference_header_walk(host, ref, tmp_path):
     assert host.mlv_get_frame_headers(clip.encode(), 14, C.byref(bad)) == 0
 
 
+def test_index_is_rebuilt_when_the_clip_changes_on_disk(host, tmp_path):
+    """The reference walks the file on every request (main.c:429-558), so a clip that is re-recorded or still
+    growing is always seen as it is; the cached index has to notice the change (size / mtime of the first chunk)."""
+    clip = str(tmp_path / "GROW.MLV")
+    _write_clip_with_metadata(clip, 64, 32, 6)
+    assert host.mlv_get_frame_count(clip.encode()) == 6
+    time.sleep(0.02)
+    hdr, _ = _write_clip_with_metadata(clip, 64, 32, 11)
+    assert host.mlv_get_frame_count(clip.encode()) == 11
+    got = F.FrameHeaders()
+    assert host.mlv_get_frame_headers(clip.encode(), 10, C.byref(got)) == 1
+    assert host.mlv_get_frame_headers(clip.encode(), 11, C.byref(got)) == 0
+    assert host.mlv_get_frame_count(str(tmp_path / "MISSING.MLV").encode()) == 0
+
+
 class ImageBuffer(C.Structure):
     pass
 
