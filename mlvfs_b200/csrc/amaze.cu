@@ -55,6 +55,11 @@ struct CudaCtx {
 #else
     __device__ __forceinline__ void mark(int) {}
 #endif
+#if defined(AMZ_PF_L1)
+    __device__ __forceinline__ void prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+    __device__ __forceinline__ void prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
     __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }

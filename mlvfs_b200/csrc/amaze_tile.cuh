@@ -149,6 +149,17 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
                                 0.03687419286733595f, 0.03099732204057846f, 0.018413194161458882f};
     const float gausseven[2] = {0.13719494435797422f, 0.05640252782101291f};
     const float gquinc[4] = {0.169917f, 0.108947f, 0.069855f, 0.0287182f};
+    // Software prefetch (a hint: no effect on any value).  A strided pass over the tile advances nthr / row-width rows
+    // per iteration; every thread asks for the cell AMZ_PF_ROWS rows below the lowest row it reads now, so the swaths
+    // of successive iterations cover the planes ahead of the loads.  The work planes of the ~600 resident tile
+    // programs do not fit the L2 (amaze.cu), so without this every pass waits on DRAM with a handful of loads in
+    // flight per warp.
+#ifndef AMZ_PF_ROWS
+#define AMZ_PF_ROWS 6
+#endif
+    const int pfd = AMZ_PF_ROWS * TS;
+    auto pf = [&](const float *pl, int i) { if (AMZ_PF_ROWS && i < TS * TS) C.prefetch(pl + i); };          // full plane
+    auto pfh = [&](const float *pl, int i) { if (AMZ_PF_ROWS && i < TS * TS) C.prefetch(pl + (i >> 1)); };  // half plane, full index
 
     // ---- per-tile clears (:294-295) + pmwt (see header) ----
     for (int k = tid; k < TS * TSH; k += nthr) { pmwt[k] = 0.0f; W.rbint[k] = 0.0f; nyquist[k] = 0; }
@@ -175,6 +186,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             else if (lb)       { sr = rr + top;         sc = 32 - cc + left;                        vec = false; }           // :417-424
             else if (rb)       { sr = rr + top;         sc = width - cl - 2;                        vec = false; fcc = cl; } // :426-433
             else               { sr = rr + top;         sc = cc + left;                             vec = true; }            // :381-387
+            if (AMZ_PF_ROWS && sr + AMZ_PF_ROWS < height) C.prefetch(raw + (size_t)(sr + AMZ_PF_ROWS) * stride + sc);
             const float v = raw[(size_t)sr * stride + sc] / 65535.0f;
             cfa[rr * TS + cc] = v;
             if (vec || fc(fr, fcc) == 1) rgbgreen[rr * TS + cc] = v;
@@ -188,6 +200,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         const int cw = cdiv(cc1, 4) * 4, nrow = rr1 - 4;
         for (int idx = tid; idx < nrow * cw; idx += nthr) {
             const int rr = 2 + idx / cw, cc = idx % cw, i = rr * TS + cc;
+            pf(cfa, i + V2 + pfd);
             const float delh = ab(cfa[i + 1] - cfa[i - 1]), delv = ab(cfa[i + V1] - cfa[i - V1]);
             W.dirwts1[i] = AMZ_EPS + ab(cfa[i + 2] - cfa[i]) + ab(cfa[i] - cfa[i - 2]) + delh;
             W.dirwts0[i] = AMZ_EPS + ab(cfa[i + V2] - cfa[i]) + ab(cfa[i] - cfa[i - V2]) + delv;
@@ -214,6 +227,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int rr = 4 + idx / nc, cc = 4 + idx % nc, i = rr * TS + cc;
             const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
             const float *d0 = W.dirwts0, *d1 = W.dirwts1;
+            pf(cfa, i + V2 + pfd); pf(d0, i + V2 + pfd); pf(d1, i + pfd);
             const float c0 = cfa[i];
             const float cru = cfa[i - V1] * (d0[i - V2] + d0[i]) / (d0[i - V2] * (AMZ_EPS + c0) + d0[i] * (AMZ_EPS + cfa[i - V2]));
             const float crd = cfa[i + V1] * (d0[i + V2] + d0[i]) / (d0[i + V2] * (AMZ_EPS + c0) + d0[i] * (AMZ_EPS + cfa[i + V2]));
@@ -242,6 +256,8 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int ns = 4 * cdiv(cc1 - 16 - par, 8), nr = (nrow8 + 1 - par) / 2;      // rows 8+par, 10+par, ...
             for (int idx = tid; idx < nr * ns; idx += nthr) {
                 const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+                pf(cfa, i + M2 + 2 * pfd); pfh(W.delm, i + M2 + 2 * pfd); pfh(W.delp, i + M2 + 2 * pfd);
+                pfh(W.Dgrbsq1m, i + V2 + 2 * pfd); pfh(W.Dgrbsq1p, i + V2 + 2 * pfd);
                 const float c0 = cfa[i];
                 float t1, t2, w;
                 t1 = cfa[i + M1]; t2 = cfa[i + M2];
@@ -301,7 +317,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         const int ncol = 4 * cdiv(cc1 - 8, 4);                            // columns 4 .. 4+ncol-1
         const int nrow = rr1 - 8;                                         // rows 4 .. rr1-5
         float *const horig = W.Dgrb2;                                     // free until the G pass writes it
-        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * TS; idx += nthr) horig[4 * TS + idx] = W.hcd[4 * TS + idx];
+        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * TS; idx += nthr) { pf(W.hcd, 4 * TS + idx + pfd); horig[4 * TS + idx] = W.hcd[4 * TS + idx]; }
         C.sync();
         C.mark(4);
         auto h_from_originals = [&](int i, float sgn, float hm2) {        // hm2: original or updated left neighbour
@@ -313,6 +329,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * ncol; idx += nthr) {
             const int rr = 4 + idx / ncol, t = idx % ncol, cc = 4 + t, i = rr * TS + cc;
             const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;             // the same for column cc - 2
+            pf(horig, i + pfd); pf(W.hcdalt, i + pfd); pf(cfa, i + pfd);
             float hm2 = horig[i - 2];
             if ((t & 3) < 2 && t >= 2) hm2 = h_from_originals(i - 2, sgn, horig[i - 4]);
             W.hcd[i] = h_from_originals(i, sgn, hm2);
@@ -338,6 +355,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             for (int rr = 4; rr < rr1 - 4; rr++) {
                 VIn nx2 = {};
                 if (rr + 2 < rr1 - 4) nx2 = load_v(rr + 2);               // two rows ahead: rows rr+1, rr+2 are still original
+                { const int ip = (rr + 4) * TS + cc + pfd; pf(cfa, ip); pf(W.vcd, ip); pf(W.vcdalt, ip); pf(W.hcd, ip - V2); }
                 const int i = rr * TS + cc;
                 const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
                 const float vm2 = rr >= 6 ? vup[rr & 1] : cur.vm2;
@@ -359,6 +377,8 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         for (int idx = tid; idx < nr * ns; idx += nthr) {
             const int rr = 6 + par + 2 * (idx / ns), cc = 6 + par + 2 * (idx % ns), i = rr * TS + cc;
             const float *vcd = W.vcd, *hcd = W.hcd, *d0 = W.dirwts0, *d1 = W.dirwts1;
+            pf(vcd, i + V3 + 2 * pfd); pf(hcd, i + 2 * pfd); pf(d0, i + V1 + 2 * pfd); pf(d1, i + 2 * pfd);
+            pf(W.dgintv, i + V2 + 2 * pfd); pf(W.dginth, i + 2 * pfd);
             float t = vcd[i];
             const float uave = t + vcd[i - V1] + vcd[i - V2] + vcd[i - V3], dave = t + vcd[i + V1] + vcd[i + V2] + vcd[i + V3];
             float Du = sq(t - uave) + sq(vcd[i - V1] - uave) + sq(vcd[i - V2] - uave) + sq(vcd[i - V3] - uave);
@@ -383,6 +403,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         for (int idx = tid; idx < nr * nq; idx += nthr) {
             const int rr = 6 + par + 2 * (idx / nq), cc = 6 + par + 2 * (idx % nq), i = rr * TS + cc;
             const float *q = W.cddiffsq, *d = W.delhvsqsum;
+            pf(q, i + V2 + 2 * pfd); pf(d, i + V2 + 2 * pfd);
             float nyqtest = (gaussodd[0] * q[i] + gaussodd[1] * (q[i - M1] + q[i + P1] + q[i - P1] + q[i + M1]) +
                              gaussodd[2] * (q[i - V2] + q[i - 2] + q[i + 2] + q[i + V2]) +
                              gaussodd[3] * (q[i - M2] + q[i + P2] + q[i - P2] + q[i + M2]));
@@ -477,6 +498,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
             for (int idx = tid; idx < nr * ns; idx += nthr) {
                 const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+                pf(cfa, i + 7 * TS + 2 * pfd);
                 if (!nyquist[i >> 1]) continue;
                 float sumh = 0, sumv = 0, sumsqh = 0, sumsqv = 0, areawt = 0;
                 for (int a = -6; a < 7; a += 2)
@@ -537,6 +559,13 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             float *cur = rowbuf[rr & 1];
             if (rr + 1 < rr1 - r0)
                 for (int j = 0; j < NS; j++) nxt_in[j] = load_ref(rr + 1, lane + 32 * j);
+            if (AMZ_PF_ROWS && rr + 2 + AMZ_PF_ROWS < TS) {                 // a half-plane row is 2.5 lines, a cfa row 5
+                const int rp = rr + 2 + AMZ_PF_ROWS;
+                if (lane < 3) C.prefetch(P + rp * TSH + 32 * lane);
+                else if (pass && lane < 6) C.prefetch(W.rbm + rp * TSH + 32 * (lane - 3));
+                else if (pass && lane < 9) C.prefetch(W.rbp + rp * TSH + 32 * (lane - 6));
+                else if (pass && lane < 14) C.prefetch(cfa + rp * TS + 32 * (lane - 9));
+            }
             for (int j = 0; j < NS; j++) {
                 const int k = lane + 32 * j;
                 if (k >= TSH) continue;
@@ -565,6 +594,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
             for (int idx = tid; idx < nr * ns; idx += nthr) {
                 const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+                pf(W.hcd, i + 2 * pfd); pf(W.vcd, i + 2 * pfd); pfh(hvwt, i + 2 * pfd); pf(cfa, i + 2 * pfd); pf(rgbgreen, i + V1 + 2 * pfd);
                 const float d = W.hcd[i] * (1.0f - hvwt[i1]) + W.vcd[i] * hvwt[i1];
                 W.Dgrb0[i1] = d;
                 const float g = cfa[i] + d;
@@ -586,6 +616,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
                 const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
                 for (int idx = tid; idx < nr * ns; idx += nthr) {
                     const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+                    pf(W.Dgrb2, i + V2 + 2 * pfd);
                     if (!nyquist[i >> 1]) continue;
                     const float gvarh = AMZ_EPSSQ + (gquinc[0] * AMZ_D2H(i) + gquinc[1] * (AMZ_D2H(i - M1) + AMZ_D2H(i + P1) + AMZ_D2H(i - P1) + AMZ_D2H(i + M1)) +
                                                      gquinc[2] * (AMZ_D2H(i - V2) + AMZ_D2H(i - 2) + AMZ_D2H(i + 2) + AMZ_D2H(i + V2)) +
@@ -610,6 +641,8 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         const int ns = cdiv(cc1 - 24 - par, 2), nr = (rr1 - 24 + 1 - par) / 2;
         for (int idx = tid; idx < nr * ns; idx += nthr) {
             const int rr = 12 + par + 2 * (idx / ns), cc = 12 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+            pfh(pmwt, i + 2 * pfd); pfh(hvwt, i + 2 * pfd); pfh(W.rbint, i + V1 + 2 * pfd); pf(cfa, i + V1 + 2 * pfd);
+            pf(W.dirwts0, i + V1 + 2 * pfd); pf(W.dirwts1, i + 2 * pfd);
             if (ab(0.5f - pmwt[i1]) < ab(0.5f - hvwt[i1])) continue;
             const float *rbint = W.rbint, *d0 = W.dirwts0, *d1 = W.dirwts1;
             const float rb = rbint[i1];
@@ -668,6 +701,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         for (int idx = tid; idx < nr * ns; idx += nthr) {
             const int rr = 14 + par + 2 * (idx / ns), cc = 14 + par + 2 * (idx % ns), i = rr * TS + cc;
 #define AMZ_G(o) D[(i + (o)) >> 1]
+            pfh(D, i + M3 + 2 * pfd);
             const float wtnw = 1.0f / (AMZ_EPS + ab(AMZ_G(-M1) - AMZ_G(M1)) + ab(AMZ_G(-M1) - AMZ_G(-M3)) + ab(AMZ_G(M1) - AMZ_G(-M3)));
             const float wtne = 1.0f / (AMZ_EPS + ab(AMZ_G(P1) - AMZ_G(-P1)) + ab(AMZ_G(P1) - AMZ_G(P3)) + ab(AMZ_G(-P1) - AMZ_G(P3)));
             const float wtsw = 1.0f / (AMZ_EPS + ab(AMZ_G(-P1) - AMZ_G(P1)) + ab(AMZ_G(-P1) - AMZ_G(M3)) + ab(AMZ_G(P1) - AMZ_G(-P3)));
@@ -690,6 +724,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const int rr = 16 + idx / nc, cc = 16 + idx % nc, i = rr * TS + cc;
             const size_t o = (size_t)(rr + top) * stride + cc + left;
             const bool is_green = ((rr + cc) & 1) != 0;
+            pf(rgbgreen, i + pfd); pfh(hvwt, i + V1 + pfd); pfh(W.Dgrb0, i + V1 + pfd); pfh(W.Dgrb1, i + V1 + pfd);
             const float g = rgbgreen[i];
             if (is_green) {
                 const float wu = hvwt[(i - V1) >> 1], wr = 1.0f - hvwt[(i + 1) >> 1], wl = 1.0f - hvwt[(i - 1) >> 1], wd = hvwt[(i + V1) >> 1];

@@ -20,6 +20,7 @@ struct HostCtx {
     void sync() { bar->arrive_and_wait(); }
     void syncwarp() { wbar->arrive_and_wait(); }
     void mark(int) {}
+    void prefetch(const void *) {}
     void atomic_add(int *p, int v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 };
 }  // namespace
