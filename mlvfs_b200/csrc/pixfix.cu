@@ -11,6 +11,7 @@
 // Level 0 (virtually everything on real sensors) runs grid-wide; deeper levels run in one CTA that
 // walks the levels with a barrier in between.
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "scan.cuh"
@@ -193,7 +194,10 @@ fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, uns
 // never wait for global memory.
 constexpr int LONG_WARPS_MAX = 16;
 constexpr int LONG_CHUNK = 256;            // list entries staged per warp at a time
-constexpr int LONG_WIN = 1024;             // pixels of a row staged per warp at a time
+constexpr int LONG_WIN = 4096;             // pixels of a row staged per warp at a time
+constexpr int LONG_WARM = 128;             // warm-up steps of a speculative piece of a dense run (walk_dense_warp)
+constexpr int LONG_DENSE_MIN = 192;        // shortest stretch of consecutive entries handed to walk_dense_warp
+constexpr size_t LONG_WARP_BYTES = (LONG_WIN + 8 + LONG_CHUNK) * sizeof(uint16_t);   // window, entry columns
 
 template <bool SMEM_EV2RAW>
 __global__ void __launch_bounds__(LONG_WARPS_MAX * 32)
@@ -215,7 +219,7 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp >= warps_per_block) return;
     // per warp: a window of LONG_WIN pixels of the row being repaired (+ 8 spare) and LONG_CHUNK staged entry columns
-    uint16_t *win = s_rows + (size_t)warp * (LONG_WIN + 8 + LONG_CHUNK);
+    uint16_t *win = s_rows + (size_t)warp * (LONG_WARP_BYTES / sizeof(uint16_t));
     uint16_t *xs = win + LONG_WIN + 8;
     uint16_t *row = win;                                                        // row[x] = win[x - wx0], set per window
     auto ev_of_raw = [&](int v) { return v < 16384 ? s_r2e[v] : __ldg(A.lut.raw2ev + v); };
@@ -262,44 +266,146 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         row[x] = (uint16_t)v;
         E[3] = ev_of_raw(v);
     };
-    // A stretch of `cnt` entries at consecutive columns x0, x0 + 1, .. (all interior): what --really-bad-pix makes of
-    // every bright row of a dual-ISO frame (cs.c:289-304 flags each of its pixels), one recurrence of thousands of
-    // steps.  Same arithmetic as interp_h step by step; the loop carries the three repaired EVs to the left and the
-    // three original EVs to the right in registers, fetches the next original ahead of its use, and has no per-entry
-    // list lookups or window rebuilds, so a step costs little more than its own dependency chain.
+    // ---- dense stretches: `cnt` entries at consecutive interior columns x0, x0 + 1, .. -- what --really-bad-pix makes
+    // of every bright row of a dual-ISO frame (cs.c:289-304 flags each of its pixels): one recurrence thousands of steps
+    // long.  One step (cs.c:87-109, the arithmetic of interp_h) is a function of the EVs of the three repaired pixels
+    // to the left (e0, e1, e2), the EVs of the three originals to the right (o1, o2, o3) and the original at x + 2.
+    // A single warp issues the whole step as one dependent chain, so the step is written for few instructions: tables
+    // and window through 32-bit shared addresses, one reciprocal for both weights, rare cases behind branches.
+    const uint32_t sa_r2e = (uint32_t)__cvta_generic_to_shared(s_r2e), sa_m13 = (uint32_t)__cvta_generic_to_shared(s_m13);
+    auto lds_s32 = [](uint32_t a) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+    auto lds_u16 = [](uint32_t a) { unsigned short v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; };
+    auto win_u16 = [](uint32_t a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return (int)v; };
+    auto ev_fast = [&](int v) {
+        if (__builtin_expect(v >= 16384, 0)) return (int)__ldg(A.lut.raw2ev + v);
+        return lds_s32(sa_r2e + 4u * (unsigned)v);
+    };
+    auto raw_fast = [&](int e) {
+        const int c = clamp_ev(e);
+        if (!SMEM_EV2RAW) return (int)__ldg(A.lut.ev2raw + c);
+        return lds_u16(sa_m13 + 2u * (unsigned)(c & (MLVB_EV_RES - 1))) >> (13 - (c >> 15));
+    };
+    // v = the repaired sample at x; sa_x = shared address of the window's pixel x
+    auto dense_step = [&](uint32_t sa_x, int e0, int e1, int e2, int o1, int o2, int o3) {
+        const int d1 = wabs(wsub(o3, o1)), d2 = wabs(wsub(e2, e0));
+        const int sum = wadd(d1, d2);
+        if (__builtin_expect(sum == 0, 0)) return win_u16(sa_x + 4);             // row[x + 2] (cs.c:96-99)
+        int c1, c2;
+        if (__builtin_expect((unsigned)(d1 | d2) < (1u << 21), 1)) {
+            // 0 <= d1, d2 < 2^21: one division gives both weights.  c1 = floor(256 d2 / sum) from a float estimate
+            // (within 1 of the quotient: 24-bit operands, approximate reciprocal) corrected by its remainder;
+            // d1 + d2 = sum, so c2 = floor(256 d1 / sum) = 256 - ceil(256 d2 / sum)
+            const int n8 = d2 << 8;
+            float rs;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(__int2float_rn(sum)));
+            int q = __float2int_rz(__int2float_rn(n8) * rs);
+            int r = n8 - q * sum;
+            if (r >= sum) { q++; r -= sum; } else if (r < 0) { q--; r += sum; }
+            c1 = q;
+            c2 = 256 - q - (r != 0);
+        } else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }   // wrap-around cases (pixels at black)
+        const int ev = (wmul(o2, c1) >> 8) + (wmul(e1, c2) >> 8);
+        return (raw_fast(ev) + black) & 0xFFFF;
+    };
+    // one lane, in the window (the generic path's in-place semantics: results replace the window's pixels)
     auto walk_dense = [&](int x0, int cnt) {
-        int e0 = ev_of_raw(row[x0 - 3]), e1 = ev_of_raw(row[x0 - 2]), e2 = ev_of_raw(row[x0 - 1]);
-        int r2 = row[x0 + 2], r3 = row[x0 + 3];
-        int o1 = ev_of_raw(row[x0 + 1]), o2 = ev_of_raw(r2), o3 = ev_of_raw(r3);
-        for (int x = x0; x < x0 + cnt; x++) {
-            const int rn = x + 1 < x0 + cnt ? (int)row[x + 4] : 0;              // the next original, needed one step later
-            const int d1 = wabs(wsub(o3, o1)), d2 = wabs(wsub(e2, e0));
-            const int sum = wadd(d1, d2);
-            int v;
-            if (sum == 0) v = r2;                                               // row[x + 2] (cs.c:96-99)
-            else {
-                int c1, c2;
-                if ((unsigned)(d1 | d2) < (1u << 21)) {
-                    // 0 <= d1, d2 < 2^21: one division gives both weights.  c1 = floor(256 d2 / sum) from a float
-                    // estimate corrected by its remainder; d1 + d2 = sum, so c2 = floor(256 d1 / sum) = 256 - ceil(256 d2 / sum)
-                    const int n8 = d2 << 8;
-                    int q = __float2int_rz(__fdividef((float)n8, (float)sum));
-                    int r = n8 - q * sum;
-                    if (r >= sum) { q++; r -= sum; } else if (r < 0) { q--; r += sum; }
-                    c1 = q;
-                    c2 = 256 - q - (r != 0);
-                } else { c1 = ((sum - d1) << 8) / sum; c2 = ((sum - d2) << 8) / sum; }   // wrap-around cases (pixels at black)
-                const int ev = (wmul(o2, c1) >> 8) + (wmul(e1, c2) >> 8);
-                v = (raw_of_ev(ev) + black) & 0xFFFF;
-            }
+        uint32_t sa = (uint32_t)__cvta_generic_to_shared(row + x0);
+        int e0 = ev_fast(win_u16(sa - 6)), e1 = ev_fast(win_u16(sa - 4)), e2 = ev_fast(win_u16(sa - 2));
+        int o1 = ev_fast(win_u16(sa + 2)), o2 = ev_fast(win_u16(sa + 4)), o3 = ev_fast(win_u16(sa + 6));
+        for (int x = x0; x < x0 + cnt; x++, sa += 2) {
+            const int rn = x + 1 < x0 + cnt ? win_u16(sa + 8) : 0;              // the next original, needed one step later
+            const int v = dense_step(sa, e0, e1, e2, o1, o2, o3);
             row[x] = (uint16_t)v;
-            e0 = e1; e1 = e2; e2 = ev_of_raw(v);
-            o1 = o2; o2 = o3; r2 = r3; r3 = rn; o3 = ev_of_raw(rn);
+            e0 = e1; e1 = e2; e2 = ev_fast(v);
+            o1 = o2; o2 = o3; o3 = ev_fast(rn);
         }
         lastx = -100;                                                           // the next entry rebuilds its EV window from the row
     };
+    // The same stretch walked by the whole warp.  The recurrence forgets: a repaired pixel is a blend of its two
+    // neighbours at x - 2 / x + 2 rounded to a sample value, so a walk started some dozens of columns early from the
+    // wrong state (the unrepaired pixels) runs into the true trajectory and stays on it (median ~45 columns on the
+    // synthetic dual-ISO frames, > 128 for ~5 % of the starts).  Lane k therefore walks piece k of the stretch
+    // speculatively after LONG_WARM warm-up steps, all lanes at once; results go straight to the frame in global
+    // memory `grow`, the staged window keeps the originals every lane reads to its right.  Then the pieces are
+    // checked in order: piece k is the reference's result iff the state it assumed at its first column (the EVs of the
+    // three samples to the left) equals the state piece k - 1 ended in; a piece that fails is walked again from the
+    // true state by its lane until it meets its own earlier results three columns in a row (same state: the rest of
+    // the piece stands), and the check moves on.  Exact by construction; the speculation only decides how much is
+    // redone -- in the worst case the stretch is walked serially once more.
+    struct EvState { int e0, e1, e2; };
+    auto spec_piece = [&](uint16_t *grow, int xb, int p0, int p1, EvState &at_p0, EvState &at_end) {
+        uint32_t sa = (uint32_t)__cvta_generic_to_shared(row + xb);
+        int e0 = ev_fast(win_u16(sa - 6)), e1 = ev_fast(win_u16(sa - 4)), e2 = ev_fast(win_u16(sa - 2));
+        int o1 = ev_fast(win_u16(sa + 2)), o2 = ev_fast(win_u16(sa + 4)), o3 = ev_fast(win_u16(sa + 6));
+        for (int x = xb; x < p0; x++, sa += 2) {                                // warm-up: nothing is stored
+            const int rn = win_u16(sa + 8);
+            const int v = dense_step(sa, e0, e1, e2, o1, o2, o3);
+            e0 = e1; e1 = e2; e2 = ev_fast(v);
+            o1 = o2; o2 = o3; o3 = ev_fast(rn);
+        }
+        at_p0 = EvState{e0, e1, e2};
+        uint16_t *gp = grow + p0;
+        for (int x = p0; x < p1; x++, sa += 2, gp++) {
+            const int rn = win_u16(sa + 8);                                     // past the stretch: the zeroed spare of the window
+            const int v = dense_step(sa, e0, e1, e2, o1, o2, o3);
+            *gp = (uint16_t)v;
+            e0 = e1; e1 = e2; e2 = ev_fast(v);
+            o1 = o2; o2 = o3; o3 = ev_fast(rn);
+        }
+        at_end = EvState{e0, e1, e2};
+    };
+    auto redo_piece = [&](uint16_t *grow, int p0, int p1, EvState st, EvState &at_end) {
+        uint32_t sa = (uint32_t)__cvta_generic_to_shared(row + p0);
+        int e0 = st.e0, e1 = st.e1, e2 = st.e2;
+        int o1 = ev_fast(win_u16(sa + 2)), o2 = ev_fast(win_u16(sa + 4)), o3 = ev_fast(win_u16(sa + 6));
+        uint16_t *gp = grow + p0;
+        int same = 0, prev = *gp;                                               // this lane's earlier result at x
+        for (int x = p0; x < p1; x++, sa += 2, gp++) {
+            const int rn = win_u16(sa + 8);
+            const int pn = x + 1 < p1 ? (int)gp[1] : 0;
+            const int v = dense_step(sa, e0, e1, e2, o1, o2, o3);
+            same = v == prev ? same + 1 : 0;
+            if (same >= 3) return;                                              // back on the earlier trajectory: the end state stands
+            if (v != prev) *gp = (uint16_t)v;
+            prev = pn;
+            e0 = e1; e1 = e2; e2 = ev_fast(v);
+            o1 = o2; o2 = o3; o3 = ev_fast(rn);
+        }
+        at_end = EvState{e0, e1, e2};
+    };
+    auto walk_dense_warp = [&](uint16_t *grow, int x0, int cnt) {               // cnt <= LONG_WIN, whole warp
+        const int L = (cnt + 31) >> 5;
+        const int p0 = x0 + lane * L, p1 = min(p0 + L, x0 + cnt);
+        const bool has = p0 < x0 + cnt;
+        const int xb = max(x0, p0 - LONG_WARM);
+        EvState a = {0, 0, 0}, b = {0, 0, 0};
+        if (has) spec_piece(grow, xb, p0, p1, a, b);
+        __syncwarp();
+        // piece k is checked against piece k - 1; pieces that started at x0 itself started from the true state
+        auto from_lane = [&](const EvState &s, int src) {
+            return EvState{__shfl_sync(0xFFFFFFFFu, s.e0, src), __shfl_sync(0xFFFFFFFFu, s.e1, src), __shfl_sync(0xFFFFFFFFu, s.e2, src)};
+        };
+        auto differs = [](const EvState &u, const EvState &v) { return u.e0 != v.e0 || u.e1 != v.e1 || u.e2 != v.e2; };
+        EvState pb = from_lane(b, max(lane - 1, 0));
+        bool wrong = has && xb > x0 && differs(a, pb);
+        unsigned bad = __ballot_sync(0xFFFFFFFFu, wrong);
+        while (bad) {
+            const int j = __ffs(bad) - 1;                                       // j >= 1: lane 0 starts at x0
+            pb = from_lane(b, j - 1);
+            if (lane == j) {
+                redo_piece(grow, p0, p1, pb, b);
+                wrong = false;
+            }
+            __syncwarp();
+            pb = from_lane(b, j);
+            if (lane == j + 1) wrong = has && differs(a, pb);
+            bad = __ballot_sync(0xFFFFFFFFu, wrong);
+        }
+        __syncwarp();
+        lastx = -100;
+    };
     const unsigned total = nlong * (unsigned)nframes;
-    for (unsigned t = blockIdx.x * warps_per_block + warp; t < total; t += gridDim.x * warps_per_block) {
+    for (unsigned t = (unsigned)warp * gridDim.x + blockIdx.x; t < total; t += gridDim.x * warps_per_block) {   // rows spread evenly over the blocks
         const unsigned ridx = t % nlong, frame = t / nlong;
         const unsigned m0 = long_rows[2 * ridx], m1 = long_rows[2 * ridx + 1];
         const int y = A.list[m0].y - A.crop_y;
@@ -323,13 +429,19 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         };
         // ascending rows (a detected bad-pixel list is in raster order) are repaired window by window in shared memory;
         // anything else (a focus-pixel map in file order) by one lane directly on the frame
-        bool ascending = true, strict = true;                                 // strict: no column listed twice
-        for (unsigned mb = m0; mb < m1; mb += 32) {
-            const unsigned m = mb + lane;
-            const bool bad = m + 1 < m1 && A.list[m + 1].x < A.list[m].x;
-            const bool dup = m + 1 < m1 && A.list[m + 1].x == A.list[m].x;
-            ascending = ascending && !__any_sync(0xFFFFFFFFu, bad);
-            strict = strict && !__any_sync(0xFFFFFFFFu, dup);
+        bool ascending, strict;                                               // strict: no column listed twice
+        {
+            bool bad = false, dup = false;                                    // one vote after the loop: the loads pipeline
+            for (unsigned mb = m0; mb < m1; mb += 32) {
+                const unsigned m = mb + lane;
+                if (m + 1 < m1) {
+                    const int xa = A.list[m].x, xb = A.list[m + 1].x;
+                    bad |= xb < xa;
+                    dup |= xb == xa;
+                }
+            }
+            ascending = !__any_sync(0xFFFFFFFFu, bad);
+            strict = !__any_sync(0xFFFFFFFFu, dup);
         }
         if (!ascending) {
             if (lane == 0) {
@@ -347,13 +459,57 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
         // that holds the first entry of a run walks that run in list order, all runs of the chunk at once; a run that
         // continues from the previous chunk or window is picked up by lane 0 (the EV window is only a cache of the
         // staged pixels).
+        // A stretch of at least LONG_DENSE_MIN entries at consecutive interior columns is walked by the whole warp
+        // (walk_dense_warp).  Columns are strictly increasing, so entries m .. m + k - 1 are consecutive iff the last
+        // one sits k - 1 columns right of the first: the longest such stretch inside the window by bisection.
+        auto dense_stretch = [&](unsigned m, int xfirst, int xlim) {
+            if (!strict || xfirst <= 2) return 0;
+            int K = 1, khi = min((int)(m1 - m), min(xlim, w - 4) - xfirst + 1);
+            if (khi < LONG_DENSE_MIN) return 0;
+            // invariant: a stretch of K holds, one of khi + 1 does not; every lane probes one length per round
+            while (K < khi) {
+                const int span = khi - K, step = (span + 31) >> 5;              // probes K + step, K + 2 step, ... (<= khi)
+                const int probe = min(K + (lane + 1) * step, khi);
+                const bool ok = A.list[m + probe - 1].x - A.crop_x == xfirst + probe - 1;
+                const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
+                // consecutive-ness is monotone in the length: the lanes that succeed are a prefix
+                const int nok = __popc(okm);
+                const int newK = nok ? min(K + nok * step, khi) : K;
+                const int newhi = nok == 32 ? khi : min(K + (nok + 1) * step, khi) - 1;
+                K = newK; khi = max(newhi, K);
+            }
+            return K;
+        };
+        const bool vec_ok = (((uintptr_t)grow) & 15) == 0;                      // eight pixels as one 128-bit word
+        auto stage = [&](int wx0, int wlen) {
+            if (vec_ok && !(wx0 & 7)) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(grow + wx0);
+                uint4 *dst = reinterpret_cast<uint4 *>(win);
+#pragma unroll 4
+                for (int i = lane; i < (wlen >> 3); i += 32) dst[i] = src[i];
+                for (int i = (wlen & ~7) + lane; i < wlen; i += 32) win[i] = grow[wx0 + i];
+            } else
+                for (int i = lane; i < wlen; i += 32) win[i] = grow[wx0 + i];
+            if (lane < 8) win[wlen + lane] = 0;                                 // the spare a walk may read ahead into
+        };
         unsigned m = m0;
         while (m < m1) {
-            const int xf = min(max(A.list[m].x - A.crop_x, 0), w - 1);
-            const int wx0 = max(min(xf - 3, w - LONG_WIN), 0);
-            const int wlen = min(LONG_WIN, w - wx0);
-            const int xlim = wx0 + wlen >= w ? 0x3FFFFFFF : wx0 + wlen - 5;     // last column whose stencil fits
-            for (int i = lane; i < wlen; i += 32) win[i] = grow[wx0 + i];
+            const int xraw = A.list[m].x - A.crop_x;
+            const int xf = min(max(xraw, 0), w - 1);
+            const int wx0 = max((xf - 3) & ~7, 0);                              // 8-pixel aligned for the 128-bit staging
+            const int wmax = min(LONG_WIN, w - wx0);
+            const int xlim = wx0 + wmax >= w ? 0x3FFFFFFF : wx0 + wmax - 5;     // last column whose stencil fits
+            const int K = dense_stretch(m, xraw, xlim);
+            if (K >= LONG_DENSE_MIN) {
+                stage(wx0, min(wmax, xraw + K + 5 - wx0));                      // the stretch's stencils: x - 3 .. x + 4
+                row = win - wx0;
+                __syncwarp();
+                walk_dense_warp(grow, xraw, K);                                 // writes the frame itself; the window is dropped
+                m += (unsigned)K;
+                continue;
+            }
+            const int wlen = wmax;
+            stage(wx0, wlen);
             row = win - wx0;
             __syncwarp();
             bool window_full = false;
@@ -393,6 +549,8 @@ fix_long_rows_kernel(const FixArgs A, const unsigned *__restrict__ long_rows, un
                 m += (unsigned)nin;
                 if (nin == 0) m++;                                              // cannot happen (a window takes its first entry); never spin
                 window_full = nin < n;
+                // a long stretch begins here: hand it to the warp-wide walk (new window)
+                if (m < m1 && !window_full && dense_stretch(m, A.list[m].x - A.crop_x, 0x3FFFFFFF) >= LONG_DENSE_MIN) break;
             }
             for (int i = lane; i < wlen; i += 32) grow[wx0 + i] = win[i];
             __syncwarp();
@@ -545,7 +703,7 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
     // rows per SM with both tables in shared memory; if that cannot hold all long rows of the batch at once, keep
     // only the log table there (the exp table is then read through L1) to avoid a second round of serial chains
     (void)row_bytes;
-    const size_t warp_bytes = (LONG_WIN + 8 + LONG_CHUNK) * sizeof(uint16_t);     // staged pixel window + staged entry columns
+    const size_t warp_bytes = LONG_WARP_BYTES;                                    // staged pixel window + staged entry columns + results
     int long_warps = (int)std::min<size_t>(LONG_WARPS_MAX, (227 * 1024 - RUN_SMEM - 1024) / warp_bytes);
     bool long_ev2raw_smem = ev2raw_octaves_ok != 0;
     const char *force_smem = getenv("MLVB_LONG_SMEM");
@@ -565,7 +723,7 @@ int launch_pixel_fix_rows(uint16_t *d_img, int w, int h, size_t frame_stride, in
         }
     } else if (nlong) {
         const size_t smem = (long_ev2raw_smem ? RUN_SMEM : 16384 * sizeof(int)) + (size_t)long_warps * warp_bytes;
-        const int blocks = (int)std::min<long long>(sms, ceil_div((long long)nlong * nframes, long_warps));
+        const int blocks = (int)std::min<long long>(sms, (long long)nlong * nframes);
         if (long_ev2raw_smem) {
             MLVB_CUDA_OK(cudaFuncSetAttribute(fix_long_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             fix_long_rows_kernel<true><<<blocks, LONG_WARPS_MAX * 32, smem, st>>>(A, d_long_rows, nlong, nframes, long_warps);

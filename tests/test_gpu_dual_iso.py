@@ -147,6 +147,40 @@ def test_dual_iso_pixel_fix_long_rows(fresh_ctx, oracle):
     assert np.array_equal(got, want), int(np.count_nonzero(got != want))
 
 
+@pytest.mark.parametrize("content", ["frame", "steps", "noise", "flat", "ramp"])
+def test_dual_iso_dense_rows_are_walked_by_the_whole_warp(fresh_ctx, oracle, content):
+    """--really-bad-pix on a dual-ISO frame flags (nearly) every pixel of the bright rows: each such row is one
+    recurrence thousands of steps long (cs.c:87-109 applied in list order).  The CUDA path walks it in 32 speculative
+    pieces and re-walks those whose assumed start state was wrong, so the result must equal the serial walk whatever
+    the content: a normal frame (the speculation converges), two-column steps (the repaired value is carried along
+    the row: the speculation fails and pieces are redone), full-range noise, flat rows (sum == 0: copies) and a ramp.
+    Three windows of 1024 pixels per row, the last one partial."""
+    w, h = 2600, 48
+    hdr = F.make_frame_headers(w, h, file_guid=0xD15E + hash(content) % 1000)
+    img = synth.make_frame(w, h, 7, dual_iso=True)
+    want_list = oracle.badpix_detect(img, 2048, 1)
+    per_row = np.bincount(want_list[:, 1], minlength=h)
+    assert per_row.max() >= 2000, f"no dense row: the longest has {per_row.max()} entries"
+    first = M.fix_bad_pixels(hdr, img.copy(), 1, 1)                  # detects the map and repairs the frame it came from
+    assert np.array_equal(first, oracle.badpix_apply(img, 2048, want_list, dual_iso=1))
+    rng = np.random.default_rng(11)
+    x = np.arange(w)[None, :]
+    if content == "frame":
+        img2 = synth.make_frame(w, h, 8, dual_iso=True)
+    elif content == "steps":
+        img2 = (2200 + 9000 * ((x // 2) % 2) + rng.integers(0, 3, (h, w))).astype(np.uint16)
+    elif content == "noise":
+        img2 = rng.integers(1900, 16383, (h, w)).astype(np.uint16)
+    elif content == "flat":
+        img2 = np.full((h, w), 5000, np.uint16)
+        img2[:, ::97] = 9000
+    else:
+        img2 = (2100 + (x * 5) % 14000 + rng.integers(0, 2, (h, w))).astype(np.uint16)
+    got = M.fix_bad_pixels(hdr, img2.copy(), 1, 1)
+    want = oracle.badpix_apply(img2, 2048, want_list, dual_iso=1)
+    assert np.array_equal(got, want), (content, int(np.count_nonzero(got != want)))
+
+
 def test_dual_iso_frames_in_flight_match_one_at_a_time(fresh_ctx):
     """mlvb_submit hands dual-ISO frames to its submit workers once the clip's state exists; several frames in flight
     (pinned and pageable buffers mixed) must give exactly the frames that one-at-a-time processing gives."""
