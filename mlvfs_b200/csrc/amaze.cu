@@ -23,7 +23,7 @@
 
 int amz_threads()
 {
-    static const int v = [] { const char *e = getenv("MLVB_AMZ_THREADS"); int t = e ? atoi(e) : 256; return t >= 64 && t <= 1024 && t % 32 == 0 ? t : 256; }();
+    static const int v = [] { const char *e = getenv("MLVB_AMZ_THREADS"); int t = e ? atoi(e) : 256; return t >= 64 && t <= AMZ_THREADS_MAX && t % 32 == 0 ? t : 256; }();
     return v;
 }
 
@@ -77,7 +77,7 @@ __global__ void amz_squeeze_kernel(const uint32_t *__restrict__ raw32, float *__
     rawf[(size_t)yh * ws + x] = (float)p;
 }
 
-__global__ void __launch_bounds__(AMZ_THREADS_MAX)
+__global__ void __launch_bounds__(AMZ_THREADS_MAX, AMZ_MIN_BLOCKS)
 amz_tiles_kernel(const float *__restrict__ raw, float *__restrict__ red, float *__restrict__ green, float *__restrict__ blue,
                  int stride, int width, int height, int ntx, int nty, char *__restrict__ ws_base, unsigned *__restrict__ counter)
 {

@@ -4,7 +4,15 @@
 
 #include "common.cuh"
 
-#define AMZ_THREADS_MAX 1024
+// launch bounds of the tile kernel: 256 threads, 5 blocks per SM = 48 registers (216 bytes of spill, L1-resident).
+// Measured on C4: 64 registers x 4 blocks 162 frames/s; 48 x 4 blocks 171; 48 x 5 169; 40 x 6 170 -- the smaller
+// register file share leaves room for the other batch lanes' kernels next to the tile programs.
+#ifndef AMZ_THREADS_MAX
+#define AMZ_THREADS_MAX 256
+#endif
+#ifndef AMZ_MIN_BLOCKS
+#define AMZ_MIN_BLOCKS 5
+#endif
 #define AMZ_MAX_BLOCKS (148 * 6)      // upper bound of persistent tile blocks; each owns a 2.3 MB workspace
 int amz_threads();                    // threads per tile block and tile blocks per SM (tunable: MLVB_AMZ_THREADS,
 int amz_blocks();                     // MLVB_AMZ_BLOCKS_PER_SM), chosen for latency hiding on the global workspace

@@ -41,4 +41,26 @@ __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (
 __device__ __forceinline__ int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 __device__ __forceinline__ int wabs(int a) { return a > 0 ? a : (int)(0u - (unsigned)a); }
 
+// Exact integer <-> double conversions on the fp64 add pipe (I2F.F64 / F2I.F64 run on the quarter-rate conversion
+// unit).  0x43300000_xxxxxxxx is 2^52 + x, so one exact subtraction gives x; a signed value goes through x + 2^31.
+__device__ __forceinline__ double u2d(unsigned n) { return __hiloint2double(0x43300000, (int)n) - 4503599627370496.0; }
+__device__ __forceinline__ double i2d(int n)
+{
+    return __hiloint2double(0x43300000, (int)((unsigned)n ^ 0x80000000u)) - 4503601774854144.0;     // 2^52 + 2^31
+}
+// floor(x) for |x| < 2^31: 2^52 + 2^31 + x lies in [2^52, 2^53) where doubles are the integers, round-toward-zero
+// of a positive sum drops the fraction.  Equals (int)x for x >= 0, and wherever the result is clamped to >= 0.
+__device__ __forceinline__ int d2i_floor(double x)
+{
+    return (int)((unsigned)__double2loint(__dadd_rz(x, 4503601774854144.0)) ^ 0x80000000u);
+}
+// a / D for an integer-valued a and a constant D, correctly rounded like the IEEE division it replaces: q = a * R,
+// one remainder step with fused multiply-adds (R = 1 / D rounded).  MLVB_FAST_DIV_OK(D, amax) on the host checks every
+// numerator the callers can pass (dualiso.cu); the plain division is used when that check fails.
+__device__ __forceinline__ double div_const(double a, double D, double R)
+{
+    const double q = a * R;
+    return __fma_rn(__fma_rn(-q, D, a), R, q);
+}
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -34,6 +34,23 @@ constexpr int ALIAS_MAP_MAX = 15000;
 constexpr double FULLRES_THR = 0.8;
 constexpr int DARK_NOISE = 512;         // compute_noise sees an empty window: 8 DN * 64
 constexpr double DARK_NOISE_EV = 9.0;
+static_assert(4 * DARK_NOISE == 2048, "final blend multiplies by the exact reciprocal of 4 * DARK_NOISE");
+
+// div_const (common.cuh) against the IEEE quotient for every numerator the final blend can pass: alias-map values
+// (uint16) over ALIAS_MAP_MAX and overexposure weights (uint8) over 200.  std::fma is exact, like the device's DFMA.
+static bool fast_div_ok()
+{
+    static const bool ok = [] {
+        auto same = [](double a, double D) {
+            const double R = 1.0 / D, q = a * R, v = fma(fma(-q, D, a), R, q), want = a / D;
+            return memcmp(&v, &want, sizeof v) == 0;
+        };
+        for (int a = 0; a <= 65535; a++) if (!same((double)a, (double)ALIAS_MAP_MAX)) return false;
+        for (int a = 0; a <= 255; a++) if (!same((double)a, 200.0)) return false;
+        return true;
+    }();
+    return ok;
+}
 
 // ------------------------------------------------------------------ phase A: frame statistics
 
@@ -230,6 +247,7 @@ struct PixParams {
     // threshold is a plain comparison).  Outside [0], [1] the table value is exactly 0.0 / 1.0 and is not fetched.
     const int *fullres_lim, *mix_lim;
     int use_fullres, use_alias;
+    int fast_div;                                     // div_const verified on the host for every numerator (fast_div_ok)
     int method;                                       // 0 AMaZE + edge-directed, 1 mean23 (hdr.c:1888-1896)
     AmazeView amz;
 };
@@ -239,8 +257,9 @@ __device__ __forceinline__ int to20_sample(uint16_t v, int y, const PixParams &P
 {
     int p = (int)(((uint32_t)v << 6) & 0xFFFFF);
     if (p != 0) {
-        if (P.is_bright[y % 4]) p = (int)((double)(p - P.black) * P.a + (double)P.black + P.b20 * P.a);
-        else p = (int)((double)p - P.b20 + P.b20 * P.a);
+        // the result is clamped to >= 0, so floor and the reference's truncation agree
+        if (P.is_bright[y % 4]) p = d2i_floor(i2d(p - P.black) * P.a + (double)P.black + P.b20 * P.a);
+        else p = d2i_floor(u2d((unsigned)p) - P.b20 + P.b20 * P.a);
         p = min(max(p, 0), 0xFFFFF);
     }
     return p;
@@ -420,8 +439,8 @@ __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_
 #pragma unroll
     for (int k = 0; k < K; k++) {
         // a term with weight exactly 0.0 contributes exactly 0 (the table values are finite): fetched from index 0
-        evb[k] = (double)__ldg(P.raw2ev + (kk[k] < 1.0 ? b[k] : 0));
-        evd[k] = (double)__ldg(P.raw2ev + (kk[k] > 0.0 ? d[k] : 0));
+        evb[k] = i2d(__ldg(P.raw2ev + (kk[k] < 1.0 ? b[k] : 0)));
+        evd[k] = i2d(__ldg(P.raw2ev + (kk[k] > 0.0 ? d[k] : 0)));
     }
     int mixed[K];
 #pragma unroll
@@ -568,22 +587,25 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
     for (int k = 0; k < K; k++) f[k] = curve_at_nb(P.fullres_curve, flo, fhi, (int)b[k] & 0xFFFFF);
 #pragma unroll
     for (int k = 0; k < K; k++) {
+        // both quotients are >= 0 (integer numerators), so COERCE(x, 0, 1) is min(x, 1)
         double c = 0.0;
-        if (P.use_alias) c = fmax(fmin((double)am[k] / (double)ALIAS_MAP_MAX, 1.0), 0.0);
-        const double ovf = fmax(fmin((double)ov[k] / 200.0, 1.0), 0.0);
+        if (P.use_alias)
+            c = fmin(P.fast_div ? div_const(u2d((unsigned)am[k]), (double)ALIAS_MAP_MAX, 1.0 / (double)ALIAS_MAP_MAX)
+                                : (double)am[k] / (double)ALIAS_MAP_MAX, 1.0);
+        const double ovf = fmin(P.fast_div ? div_const(u2d((unsigned)ov[k]), 200.0, 1.0 / 200.0) : (double)ov[k] / 200.0, 1.0);
         c = fmax(c, ovf);
         noo[k] = fmax(ovf, 1.0 - f[k]);
         f[k] = fmax(f[k], c);
         const int sig = (int)((d[k] + b[k]) / 2);
-        f[k] = fmax(0.0, fmin(f[k], (double)(sig - P.black) / (double)(4 * DARK_NOISE)));
+        f[k] = fmax(0.0, fmin(f[k], i2d(sig - P.black) * (1.0 / (double)(4 * DARK_NOISE))));     // 4 * DARK_NOISE = 2^11: exact
     }
     // the three EV gathers are weighted by (1 - f), f * noo and f * (1 - noo)
     double hrev[K], frsev[K], frev[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
-        hrev[k] = (double)__ldg(P.raw2ev + (f[k] < 1.0 ? hs[k] : 0u));
-        frsev[k] = (double)__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] > 0.0) ? fs[k] : 0u));
-        frev[k] = (double)__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] < 1.0) ? fr[k] : 0u));
+        hrev[k] = i2d(__ldg(P.raw2ev + (f[k] < 1.0 ? hs[k] : 0u)));
+        frsev[k] = i2d(__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] > 0.0) ? fs[k] : 0u)));
+        frev[k] = i2d(__ldg(P.raw2ev + ((f[k] > 0.0 && noo[k] < 1.0) ? fr[k] : 0u)));
     }
     int o[K];
 #pragma unroll
@@ -599,7 +621,7 @@ __global__ void diso_final_kernel(const uint32_t *__restrict__ dark, const uint3
     for (int k = 0; k < K; k++) v20[k] = (uint32_t)__ldg(P.ev2raw + o[k]);
 #pragma unroll
     for (int k = 0; k < K; k++)
-        if (ok[k]) out16[i[k]] = (uint16_t)min(max((int)((double)v20[k] / 16.0 + 0.5), 0), 0xFFFF);
+        if (ok[k]) out16[i[k]] = (uint16_t)min(d2i_floor(u2d(v20[k]) * 0.0625 + 0.5), 0xFFFF);          // >= 0.5: floor = truncation
 }
 
 // ------------------------------------------------------------------ host: tables and scalar epilogues
@@ -987,6 +1009,7 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
     P.overlap = overlap;
     P.max_ev = log2(white / 64 - black / 64);
     P.use_fullres = use_fullres; P.use_alias = use_alias_map;
+    P.fast_div = fast_div_ok() ? 1 : 0;
 
     // 20-bit EV tables, rebuilt only when black changes (with this frame's white), hdr.c:1089-1093
     {
