@@ -136,17 +136,28 @@ amz_edge_dir_kernel(const uint32_t *__restrict__ raw32, const int *__restrict__ 
         else search = !(p < (uint32_t)white_darkened);                             // bright exposure clipped (hdr.c:1122-1133)
         if (search) {
             const int s = (isb[y & 3] == isb[(y + 1) & 3]) ? -1 : 1;
+            // Every direction reads the same four rows (y + 2s, y + s, y - 2s, y - 3s) at 11 consecutive columns around
+            // its own column offsets: 11 x 11 x 4 = 484 loads of only 19 + 15 + 19 + 23 = 76 distinct cells.  The cells go
+            // to registers once and the 11 direction costs come from them with compile-time indices.
+            // flat indexing like the reference: x + dx + j may leave the row
+            const int *ra = grayev + (long long)(y + 2 * s) * w + x, *rb = grayev + (long long)(y + s) * w + x;
+            const int *rc = grayev + (long long)(y - 2 * s) * w + x, *rd = grayev + (long long)(y - 3 * s) * w + x;
+            int A[19], B[15], Cc[19], Dd[23];
+#pragma unroll
+            for (int k = 0; k < 19; k++) { A[k] = __ldg(ra + k - 9); Cc[k] = __ldg(rc + k - 9); }
+#pragma unroll
+            for (int k = 0; k < 15; k++) B[k] = __ldg(rb + k - 7);
+#pragma unroll
+            for (int k = 0; k < 23; k++) Dd[k] = __ldg(rd + k - 11);
+            constexpr int DX[11][4] = {{-4, -2, 4, 6}, {-3, -1, 3, 4}, {-2, -1, 2, 3}, {-1, -1, 1, 2}, {-1, 0, 1, 1}, {0, 0, 0, 0},
+                                       {1, 0, -1, -1}, {1, 1, -1, -2}, {2, 1, -2, -3}, {3, 1, -3, -4}, {4, 2, -4, -6}};   // c_edge[d][0, 2, 4, 6]
             int e_best = 0x7FFFFFFF;
+#pragma unroll
             for (int d = 0; d <= 10; d++) {
-                // flat indexing like the reference: x + dx + j may leave the row
-                const int *r1 = grayev + (long long)(y + c_edge[d][1] * s) * w + x + c_edge[d][0];
-                const int *r2 = grayev + (long long)(y + c_edge[d][3] * s) * w + x + c_edge[d][2];
-                const int *r3 = grayev + (long long)(y + c_edge[d][5] * s) * w + x + c_edge[d][4];
-                const int *r4 = grayev + (long long)(y + c_edge[d][7] * s) * w + x + c_edge[d][6];
                 int e = 0;
 #pragma unroll
                 for (int j = -5; j <= 5; j++) {
-                    const int p1 = __ldg(r1 + j), p2 = __ldg(r2 + j), p3 = __ldg(r3 + j), p4 = __ldg(r4 + j);
+                    const int p1 = A[DX[d][0] + j + 9], p2 = B[DX[d][1] + j + 7], p3 = Cc[DX[d][2] + j + 9], p4 = Dd[DX[d][3] + j + 11];
                     e += abs(p1 - p2) + abs(p2 - p3) + abs(p3 - p4);
                 }
                 e += abs(d - 5) * (MLVB_EV_RES / 8);

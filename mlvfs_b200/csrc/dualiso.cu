@@ -220,8 +220,10 @@ __global__ void diso_score_kernel(const int2 *__restrict__ sel, const unsigned *
     unsigned s = 0;
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
         const int2 p = sel[i];
-        const int e = (int)((double)p.y - ((double)p.x * ta + tb));
-        s += (abs(e) < 50);
+        // abs((int)v) < 50 <=> |v| < 50 for the truncating conversion (|v| is far below 2^31 here): no F2I.F64,
+        // and the int -> double conversions on the add pipe (common.cuh)
+        const double v = i2d(p.y) - (i2d(p.x) * ta + tb);
+        s += (fabs(v) < 50.0);
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
     __shared__ unsigned sw[8];
@@ -273,6 +275,30 @@ __global__ void diso_to20_kernel(const uint16_t *__restrict__ img, uint32_t *__r
     raw32[i] = (uint32_t)to20_sample(img[i], y, P);
 }
 
+// mean23 path: the 20-bit sample and its EV, each converted / looked up once per pixel (the interpolation reads three or
+// four neighbours' EVs per pixel: as plane reads instead of conversions + table gathers).  Four pixels per thread.
+__global__ void diso_to20ev_kernel(const uint16_t *__restrict__ img, uint32_t *__restrict__ raw32, int *__restrict__ ev32, const PixParams P)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= P.w) return;
+    const size_t i = x4 + (size_t)y * P.w;
+    if (x4 + 3 < P.w && (i & 3) == 0) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(img + i);
+        uint4 r;
+        r.x = (uint32_t)to20_sample((uint16_t)(v.x & 0xFFFF), y, P); r.y = (uint32_t)to20_sample((uint16_t)(v.x >> 16), y, P);
+        r.z = (uint32_t)to20_sample((uint16_t)(v.y & 0xFFFF), y, P); r.w = (uint32_t)to20_sample((uint16_t)(v.y >> 16), y, P);
+        const int4 e = make_int4(__ldg(P.raw2ev + r.x), __ldg(P.raw2ev + r.y), __ldg(P.raw2ev + r.z), __ldg(P.raw2ev + r.w));
+        *reinterpret_cast<uint4 *>(raw32 + i) = r;
+        *reinterpret_cast<int4 *>(ev32 + i) = e;
+    } else {
+        for (int k = 0; k < 4 && x4 + k < P.w; k++) {
+            const uint32_t r = (uint32_t)to20_sample(img[i + k], y, P);
+            raw32[i + k] = r;
+            ev32[i + k] = __ldg(P.raw2ev + r);
+        }
+    }
+}
+
 __device__ __forceinline__ int mean2_ev(int a, int b, int white) { return (a >= white || b >= white) ? white : (a + b) / 2; }
 __device__ __forceinline__ int mean3_ev(int a, int b, int c, int white)
 {
@@ -281,17 +307,19 @@ __device__ __forceinline__ int mean3_ev(int a, int b, int c, int white)
 }
 
 // mean32_interpolate (or the edge-directed interpolation of amaze_interpolate, hdr.c:1182-1210) +
-// border_interpolate + fullres_reconstruction, one thread per pixel.  FROM14: the 20-bit samples are converted on
-// the fly from the 14-bit frame (the mean23 path reads at most four of them per pixel: no raw32 plane, no extra pass);
-// the AMaZE path keeps the plane, its demosaic stage needs it anyway.
+// border_interpolate + fullres_reconstruction, one thread per pixel, from the 20-bit plane.  FROM14 (the mean23 path):
+// the neighbours' EVs come from the plane diso_to20ev_kernel wrote next to it (raw32 / ev32 are converted and looked
+// up once per pixel; round 1 converted the three or four neighbours of every pixel on the fly: 286 instructions and
+// 4.5 table gathers per pixel).
 template <bool FROM14>
-__global__ void diso_interp_kernel(const uint16_t *__restrict__ img14, const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark,
+__global__ void diso_interp_kernel(const int *__restrict__ ev32, const uint32_t *__restrict__ raw32, uint32_t *__restrict__ dark,
                                    uint32_t *__restrict__ bright, uint32_t *__restrict__ fullres, const PixParams P)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     const int w = P.w, h = P.h;
     if (x >= w) return;
-#define R(xx, yy) (FROM14 ? to20_sample(img14[(xx) + (size_t)(yy) * w], (yy), P) : (int)raw32[(xx) + (size_t)(yy) * w])
+#define R(xx, yy) ((int)raw32[(xx) + (size_t)(yy) * w])
+#define EVP(xx, yy) (ev32[(xx) + (size_t)(yy) * w])                    // raw2ev[R(xx, yy)], from diso_to20ev_kernel
     const int br = P.is_bright[y % 4];
     uint32_t native, interp;
     // precedence = order of the loops in border_interpolate (hdr.c:1312-1352), later loops win
@@ -316,16 +344,17 @@ __global__ void diso_interp_kernel(const uint16_t *__restrict__ img14, const uin
         const int xe = x & ~1;
         int ev;
         if ((y & 1) == 0) {
-            if (x == xe) ev = mean2_ev(__ldg(P.raw2ev + R(x, y - 2)), __ldg(P.raw2ev + R(x, y + 2)), wev);
-            else ev = mean3_ev(__ldg(P.raw2ev + R(xe + 2, y + s)), __ldg(P.raw2ev + R(xe, y + s)), __ldg(P.raw2ev + R(xe + 1, y - 2 * s)), wev);
+            if (x == xe) ev = mean2_ev(EVP(x, y - 2), EVP(x, y + 2), wev);
+            else ev = mean3_ev(EVP(xe + 2, y + s), EVP(xe, y + s), EVP(xe + 1, y - 2 * s), wev);
         } else {
-            if (x == xe) ev = mean3_ev(__ldg(P.raw2ev + R(xe + 1, y + s)), __ldg(P.raw2ev + R(xe - 1, y + s)), __ldg(P.raw2ev + R(xe, y - 2 * s)), wev);
-            else ev = mean2_ev(__ldg(P.raw2ev + R(x, y - 2)), __ldg(P.raw2ev + R(x, y + 2)), wev);
+            if (x == xe) ev = mean3_ev(EVP(xe + 1, y + s), EVP(xe - 1, y + s), EVP(xe, y - 2 * s), wev);
+            else ev = mean2_ev(EVP(x, y - 2), EVP(x, y + 2), wev);
         }
         interp = (uint32_t)__ldg(P.ev2raw + ev);
         native = R(x, y);
     }
 #undef R
+#undef EVP
     const size_t i = x + (size_t)y * w;
     const uint32_t d = br ? interp : native, b = br ? native : interp;
     dark[i] = d;
@@ -347,10 +376,11 @@ __device__ __forceinline__ double fullres_curve_at(int i, int black)         // 
 
 // the two blending curves as tables over the 20-bit bright sample, like the reference's own mix_curve /
 // fullres_curve arrays: fullres_curve depends on black only, mix_curve on this frame's exposure match
-__device__ __forceinline__ void curve_limits(int i, double v, int *__restrict__ lim)
+__device__ __forceinline__ void curve_limits(int i, double v, int *__restrict__ lim, bool valid = true)
 {
     // block-aggregated (256 threads): at most one atomic per block and limit, none where it cannot change the limit
     int a0 = v != 0.0 ? i : N20, a1 = v != 1.0 ? i + 1 : 0, a2 = v > FULLRES_THR ? i : N20, a3 = !(v > FULLRES_THR) ? i + 1 : 0;
+    if (!valid) { a0 = N20; a1 = 0; a2 = N20; a3 = 0; }
     for (int o = 16; o; o >>= 1) {
         a0 = min(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, o)); a1 = max(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, o));
         a2 = min(a2, __shfl_xor_sync(0xFFFFFFFFu, a2, o)); a3 = max(a3, __shfl_xor_sync(0xFFFFFFFFu, a3, o));
@@ -375,15 +405,22 @@ __global__ void diso_fullres_curve_kernel(double *__restrict__ curve, int *__res
     curve[i] = v;
     curve_limits(i, v, lim);
 }
+// Only [i0, i1) is evaluated: the host derives from the curve's formula where it is flat (exactly 0.0 up to
+// ev = max_ev - overlap, exactly 1.0 from ev = max_ev on) and pads that by two sample units; entries outside are never
+// read (the readers clamp the index into [lim[0], lim[1]), and both limits lie inside the evaluated range).
 __global__ void diso_mix_curve_kernel(double *__restrict__ curve, int *__restrict__ lim, int black, double corr_ev, double max_ev,
-                                      double overlap)
+                                      double overlap, int i0, int i1)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // grid covers N20 exactly
-    const double ev = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0)) + corr_ev;
-    const double c = -cos(fmax(fmin(ev - (max_ev - overlap), overlap), 0.0) * M_PI / overlap);
-    const double k = fmax(fmin((c + 1.0) / 2.0, 1.0), 0.0);
-    curve[i] = k;
-    curve_limits(i, k, lim);
+    const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < i1;
+    double k = 0.0;
+    if (in) {
+        const double ev = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0)) + corr_ev;
+        const double c = -cos(fmax(fmin(ev - (max_ev - overlap), overlap), 0.0) * M_PI / overlap);
+        k = fmax(fmin((c + 1.0) / 2.0, 1.0), 0.0);
+        curve[i] = k;
+    }
+    curve_limits(i, k, lim, in);
 }
 // table value with the flat ends answered from the limits (exactly 0.0 below lim[0], exactly 1.0 from lim[1] on)
 __device__ __forceinline__ double curve_at(const double *__restrict__ curve, const int *__restrict__ lim, int i)
@@ -1045,7 +1082,19 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
     P.mix_curve = D.mix_curve;
     P.mix_lim = D.mix_lim;
     diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(D.mix_lim);
-    diso_mix_curve_kernel<<<N20 / 256, 256, 0, st>>>(D.mix_curve, D.mix_lim, black, P.corr_ev, P.max_ev, P.overlap);
+    {
+        // where the mixing curve is not flat (hdr.c:1562-1571): signal x = i / 64 - black / 64 between 2^(max_ev - overlap -
+        // corr_ev) and 2^(max_ev - corr_ev); below one sample unit of signal the curve is constant (x is clamped to 1)
+        const double x_lo = exp2(P.max_ev - P.overlap - P.corr_ev), x_hi = exp2(P.max_ev - P.corr_ev);
+        long long i0 = x_lo > 1.0 ? (long long)floor(black + 64.0 * x_lo) - 128 : 0;
+        long long i1 = (long long)ceil(black + 64.0 * std::max(x_hi, 1.0)) + 128;
+        i0 = std::min<long long>(std::max<long long>(i0, 0), N20);
+        i1 = std::min<long long>(std::max<long long>(i1, i0), N20);
+        if (!(x_lo == x_lo) || !(x_hi == x_hi)) { i0 = 0; i1 = N20; }   // NaN parameters: evaluate everything
+        if (i1 > i0)
+            diso_mix_curve_kernel<<<ceil_div(i1 - i0, 256), 256, 0, st>>>(D.mix_curve, D.mix_lim, black, P.corr_ev, P.max_ev, P.overlap,
+                                                                         (int)i0, (int)i1);
+    }
     ctx->launches += 2;
 
     // ---------------- phase D: per-pixel pipeline
@@ -1067,8 +1116,14 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
         P.amz.red = A.red; P.amz.green = A.green; P.amz.blue = A.blue; P.amz.squeezed = A.squeezed; P.amz.edir = A.edir;
         P.amz.ws = w + 16;
     }
-    if (P.method == 0) diso_interp_kernel<false><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
-    else diso_interp_kernel<true><<<g2, 256, 0, st>>>(d_img, D.raw32, D.dark, D.bright, D.fullres, P);
+    if (P.method == 0) diso_interp_kernel<false><<<g2, 256, 0, st>>>(nullptr, D.raw32, D.dark, D.bright, D.fullres, P);
+    else {
+        // the EV plane lives in the half-resolution plane's memory, which the mix kernel below writes after the last read
+        int *ev32 = reinterpret_cast<int *>(D.halfres);
+        diso_to20ev_kernel<<<dim3(ceil_div(ceil_div(w, 4), 128), h), 128, 0, st>>>(d_img, D.raw32, ev32, P);
+        diso_interp_kernel<true><<<g2, 256, 0, st>>>(ev32, D.raw32, D.dark, D.bright, D.fullres, P);
+        ctx->launches += 1;
+    }
     diso_mix_kernel<<<ceil_div((np + 1) / 2, 256), 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
     ctx->launches += 2;
     const uint32_t *frs = D.fullres, *hrs = D.halfres;
