@@ -211,25 +211,40 @@ __global__ void diso_highlights_kernel(const int2 *__restrict__ pairs, unsigned 
     if (k < cap) sel[k] = p;
 }
 
-// one CTA per candidate slope (hdr.c:751-772)
+// SCORE_CAND candidate slopes per CTA (hdr.c:751-772): a selected pair is loaded and converted once for all of them
+constexpr int SCORE_CAND = 4;
 __global__ void diso_score_kernel(const int2 *__restrict__ sel, const unsigned *__restrict__ nsel, unsigned cap,
-                                  const double *__restrict__ test_a, int dmed, int bmed, unsigned *__restrict__ scores)
+                                  const double *__restrict__ test_a, unsigned ncand, int dmed, int bmed, unsigned *__restrict__ scores)
 {
-    const double ta = test_a[blockIdx.x], tb = (double)dmed - (double)bmed * ta;
+    double ta[SCORE_CAND], tb[SCORE_CAND];
+    unsigned s[SCORE_CAND];
+#pragma unroll
+    for (int c = 0; c < SCORE_CAND; c++) {
+        const unsigned k = min(blockIdx.x * SCORE_CAND + c, ncand - 1);
+        ta[c] = test_a[k]; tb[c] = (double)dmed - (double)bmed * ta[c];
+        s[c] = 0;
+    }
     const unsigned n = min(*nsel, cap);
-    unsigned s = 0;
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
         const int2 p = sel[i];
         // abs((int)v) < 50 <=> |v| < 50 for the truncating conversion (|v| is far below 2^31 here): no F2I.F64,
         // and the int -> double conversions on the add pipe (common.cuh)
-        const double v = i2d(p.y) - (i2d(p.x) * ta + tb);
-        s += (fabs(v) < 50.0);
+        const double px = i2d(p.x), py = i2d(p.y);
+#pragma unroll
+        for (int c = 0; c < SCORE_CAND; c++) s[c] += (fabs(py - (px * ta[c] + tb[c])) < 50.0);
     }
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-    __shared__ unsigned sw[8];
-    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+    __shared__ unsigned sw[SCORE_CAND][8];
+#pragma unroll
+    for (int c = 0; c < SCORE_CAND; c++) {
+        for (int o = 16; o; o >>= 1) s[c] += __shfl_xor_sync(0xFFFFFFFFu, s[c], o);
+        if ((threadIdx.x & 31) == 0) sw[c][threadIdx.x >> 5] = s[c];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { unsigned t = 0; for (unsigned i = 0; i < blockDim.x / 32; i++) t += sw[i]; scores[blockIdx.x] = t; }
+    if (threadIdx.x < SCORE_CAND && blockIdx.x * SCORE_CAND + threadIdx.x < ncand) {
+        unsigned t = 0;
+        for (unsigned i = 0; i < blockDim.x / 32; i++) t += sw[threadIdx.x][i];
+        scores[blockIdx.x * SCORE_CAND + threadIdx.x] = t;
+    }
 }
 
 // ------------------------------------------------------------------ phase D: per-pixel pipeline
@@ -580,18 +595,46 @@ __global__ void diso_alias34_kernel(const uint16_t *__restrict__ aux, const uint
 
 // 3x3 "blur" of the overexposure flags (hdr.c:1636-1655): in -> out.  The flags are 0 / 100 and final_blend only
 // uses min(blurred / 200, 1): both planes are bytes, the blurred value saturates at 200.
+// Four pixels per thread when the rows are word aligned (w % 4 == 0): per row one 32-bit load and the two bytes next
+// to it instead of twelve byte loads, one 32-bit store.
 __global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const size_t i = x + (size_t)y * w;
-    int v = in[i];
-    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
-#define O(dx, dy) ((int)in[(x + (dx)) + (size_t)(y + (dy)) * w])
-        v = O(0, 0) + (O(0, -1) + O(-1, 0) + O(1, 0) + O(0, 1)) * 820 / 1024 + (O(-1, -1) + O(1, -1) + O(-1, 1) + O(1, 1)) * 657 / 1024;
-#undef O
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x0 >= w) return;
+    const size_t i0 = x0 + (size_t)y * w;
+    const bool rows_in = y >= 3 && y < h - 3;
+    if ((w & 3) == 0 && rows_in && x0 >= 4 && x0 + 8 <= w) {
+        int r[3][6];                                                      // rows y-1 .. y+1, columns x0-1 .. x0+4
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const uint8_t *p = in + i0 + (ptrdiff_t)(j - 1) * w;
+            const uint32_t m = *reinterpret_cast<const uint32_t *>(p);
+            r[j][0] = p[-1]; r[j][5] = p[4];
+            r[j][1] = m & 0xFF; r[j][2] = (m >> 8) & 0xFF; r[j][3] = (m >> 16) & 0xFF; r[j][4] = m >> 24;
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int v = r[1][k + 1];
+            if (x0 + k < w - 3)                                           // x0 + k >= 3 holds (x0 >= 4)
+                v = r[1][k + 1] + (r[0][k + 1] + r[1][k] + r[1][k + 2] + r[2][k + 1]) * 820 / 1024 +
+                    (r[0][k] + r[0][k + 2] + r[2][k] + r[2][k + 2]) * 657 / 1024;
+            o |= (uint32_t)min(v, 200) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(out + i0) = o;
+        return;
     }
-    out[i] = (uint8_t)min(v, 200);
+    for (int k = 0; k < 4 && x0 + k < w; k++) {
+        const int x = x0 + k;
+        const size_t i = i0 + k;
+        int v = in[i];
+        if (x >= 3 && x < w - 3 && rows_in) {
+#define O(dx, dy) ((int)in[(x + (dx)) + (size_t)(y + (dy)) * w])
+            v = O(0, 0) + (O(0, -1) + O(-1, 0) + O(1, 0) + O(0, 1)) * 820 / 1024 + (O(-1, -1) + O(1, -1) + O(-1, 1) + O(1, 1)) * 657 / 1024;
+#undef O
+        }
+        out[i] = (uint8_t)min(v, 200);
+    }
 }
 
 // final_blend (hdr.c:1691-1752) + convert_20_to_16bit (hdr.c:1760-1772)
@@ -1011,7 +1054,7 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
     MLVB_CUDA_OK(cudaMemsetAsync(D.nsel, 0, sizeof(unsigned), st));
     const unsigned ncand = (unsigned)T->test_a.size();
     if (ngrid) diso_highlights_kernel<<<ceil_div(ngrid, 256), 256, 0, st>>>(D.pairs, ngrid, b_lo, b_hi, D.sel, D.nsel, ngrid);
-    diso_score_kernel<<<ncand, 256, 0, st>>>(D.sel, D.nsel, ngrid, T->d_test_a, dmed, bmed, D.scores);
+    diso_score_kernel<<<ceil_div(ncand, SCORE_CAND), 256, 0, st>>>(D.sel, D.nsel, ngrid, T->d_test_a, ncand, dmed, bmed, D.scores);
     ctx->launches += 2;
     if (ncand > 4095) return MLVB_ERR_ARG;
     MLVB_CUDA_OK(cudaMemcpyAsync(scores, D.scores, ncand * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -1148,7 +1191,7 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
         diso_alias34_kernel<<<dim3(ceil_div((w + 1) / 2, 128), (h + 1) / 2), 128, 0, st>>>(D.aux, D.skip, D.amap, w, h);
         ctx->launches += 3;
     }
-    diso_over_blur_kernel<<<g2, 256, 0, st>>>(D.over, D.over2, w, h);
+    diso_over_blur_kernel<<<dim3(ceil_div(ceil_div(w, 4), 128), h), 128, 0, st>>>(D.over, D.over2, w, h);
     diso_final_kernel<<<dim3(ceil_div(w, 256), (h + 1) / 2), 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
     ctx->launches += 2;
     MLVB_CUDA_OK(cudaGetLastError());
