@@ -52,12 +52,12 @@ WORKLOADS = {
                cli=["--cs3x3", "--bad-pix", "--stripes"]),
     "C3": dict(w=3840, h=1536, opts=dict(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5),
                variant=dict(dual_iso=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
-               desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=8, e2e_chunk=8,
+               desc="C3: 3840x1536 14-bit dual-ISO MLV, --dual-iso --mean23 --cs5x5 (alias map on)", frames=16, e2e_chunk=16,
                kernel="dual-ISO stage (statistics + mean23 + 2x cs5x5 on 20-bit planes + alias map + blend)",
                cli=["--dual-iso", "--mean23", "--cs5x5"]),
     "C4": dict(w=5760, h=3240, opts=dict(dual_iso=2, hdr_interpolation_method=0, fix_bad_pixels=2),
                variant=dict(dual_iso=True, hot_cold=True), codec="raw", chain_bpp=7.25, stage="dualiso", stage_bpp=7.25,
-               desc="C4: 5760x3240 14-bit dual-ISO MLV, --dual-iso --amaze-edge --alias-map --really-bad-pix", frames=4, e2e_chunk=4,
+               desc="C4: 5760x3240 14-bit dual-ISO MLV, --dual-iso --amaze-edge --alias-map --really-bad-pix", frames=8, e2e_chunk=8,
                kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)",
                cli=["--dual-iso", "--amaze-edge", "--alias-map", "--really-bad-pix"]),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,

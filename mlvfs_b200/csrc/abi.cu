@@ -13,6 +13,16 @@
 
 namespace {
 
+// clip + the options that shape the per-clip state: frames of a key whose first frame has been through are independent
+// of each other (ctx->async_clips, under ctx->job_mu)
+static std::string clip_option_key(const char *mlv_filename, const mlvb_options *opts)
+{
+    char tag[64];
+    snprintf(tag, sizeof(tag), "|%d.%d.%d.%d.%d.%d", opts->fix_bad_pixels, opts->fix_stripes, opts->chroma_smooth,
+             opts->hdr_interpolation_method, opts->hdr_no_fullres, opts->hdr_no_alias_map);
+    return std::string(mlv_filename ? mlv_filename : "") + tag;
+}
+
 int round_up(size_t v, size_t a, size_t *out) { *out = (v + a - 1) / a * a; return 0; }
 
 // Pinned host memory handed out by mlvb_host_alloc: a process-wide pool.  Freed blocks are kept (up to
@@ -218,13 +228,29 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
             return run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, 1, r == 1, s);
         };
         StageTimer t(ctx, ST_DUALISO, st);
-        // frame 0 first, on the caller's stream: it creates the per-clip state (bad-pixel map, EV tables, stripes)
-        rc = one_frame(0, d_aux, st);
-        if (rc || nframes == 1) return rc;
-        // the other frames are independent: a few host threads, each with its own stream and scratch, so that one
+        // The batch's first frame goes first, on the caller's stream, when the clip's per-clip state (bad-pixel map, EV
+        // tables, stripes) may not exist yet: it creates it.  Once a frame of this clip + option set has been through
+        // (the same key the submit path keeps), every frame of the batch is independent.
+        const std::string clip_key = clip_option_key(mlv_filename, &opts);
+        bool primed;
+        { std::lock_guard<std::mutex> lk(ctx->job_mu); primed = ctx->async_clips.count(clip_key) != 0; }
+        const int first = primed ? 0 : 1;
+        if (!primed) {
+            rc = one_frame(0, d_aux, st);
+            if (rc) return rc;
+            { std::lock_guard<std::mutex> lk(ctx->job_mu); ctx->async_clips.insert(clip_key); }
+            if (nframes == 1) return rc;
+        } else if (nframes == 1) return one_frame(0, d_aux, st);
+        // the frames are independent: a few host threads, each with its own stream and scratch, so that one
         // frame's statistics read-backs and scalar epilogues overlap the kernels of the others
-        const int nlanes = std::min(nframes - 1, ctx->batch_lane_count);
+        // the lanes (streams, scratch, fork event) belong to the context: concurrent host batches (mlvb_process_frames
+        // has three slots) take turns here, while their copies and single-stream stages still overlap
+        std::lock_guard<std::mutex> lanes_lock(ctx->lanes_mu);
         const size_t need = aux_bytes_for(g, opts);
+        // measured on B200: frames with small scratch (C3: 5.9 MP mean23) gain up to 16 in flight, the AMaZE frames
+        // (C4: 2.7 GB of tile workspaces each) are best at 8
+        const int lane_cap = ctx->batch_lane_count > 0 ? ctx->batch_lane_count : (need > ((size_t)1 << 30) ? 8 : 16);
+        const int nlanes = std::min(nframes - first, lane_cap);
         if (!ctx->batch_fork) MLVB_CUDA_OK(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
         while ((int)ctx->batch_lanes.size() < nlanes) {
             mlvb_context::BatchLane l;
@@ -248,7 +274,7 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
                     lane_rc[l] = MLVB_ERR_CUDA;
                     return;
                 }
-                for (int f = 1 + l; f < nframes && lane_rc[l] == MLVB_OK; f += nlanes) lane_rc[l] = one_frame(f, L.d_aux, L.stream);
+                for (int f = first + l; f < nframes && lane_rc[l] == MLVB_OK; f += nlanes) lane_rc[l] = one_frame(f, L.d_aux, L.stream);
                 if (cudaEventRecord(L.done, L.stream) != cudaSuccess) lane_rc[l] = MLVB_ERR_CUDA;
             });
         for (auto &th : workers) th.join();
@@ -672,10 +698,7 @@ static mlvb_ticket submit_frame(mlvb_context *ctx, const struct frame_headers *h
     const bool blocking = opts->dual_iso == 2 && !ctx->profiling && !ctx->sync_submit;
     std::string key;
     if (blocking) {
-        char tag[64];
-        snprintf(tag, sizeof(tag), "|%d.%d.%d.%d.%d.%d", opts->fix_bad_pixels, opts->fix_stripes, opts->chroma_smooth,
-                 opts->hdr_interpolation_method, opts->hdr_no_fullres, opts->hdr_no_alias_map);
-        key = std::string(mlv_filename ? mlv_filename : "") + tag;
+        key = clip_option_key(mlv_filename, opts);
         std::unique_lock<std::mutex> lk(ctx->job_mu);
         if (ctx->async_clips.count(key)) {
             if (ctx->submit_workers.empty())

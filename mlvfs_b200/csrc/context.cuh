@@ -159,6 +159,7 @@ struct mlvb_context {
     struct BatchLane { cudaStream_t stream = nullptr; cudaEvent_t done = nullptr; void *d_aux = nullptr; size_t aux_cap = 0; };
     std::vector<BatchLane> batch_lanes;
     cudaEvent_t batch_fork = nullptr;
+    std::mutex lanes_mu;                   // one device batch at a time owns the lanes (host batches run concurrently)
 
     // host batches (mlvb_process_frames)
     std::mutex hb_mu;
@@ -166,7 +167,7 @@ struct mlvb_context {
     std::vector<BatchSlot> host_batches;
     bool blocking_sync = true;             // waits sleep on the event instead of spinning ($MLVB_BLOCKING_SYNC=0: spin)
     bool sync_submit = false, no_wide = false, wide_segments = false;   // $MLVB_SYNC_SUBMIT, $MLVB_NO_WIDE, $MLVB_WIDE_SEGMENTS (read once)
-    int batch_lane_count = 8;              // dual-ISO frames of a device batch in flight at once ($MLVB_BATCH_LANES)
+    int batch_lane_count = 0;              // dual-ISO frames of a device batch in flight at once ($MLVB_BATCH_LANES; 0: by scratch size)
     int spin_us = 150;                     // stream_wait polls this long before it sleeps ($MLVB_SPIN_US)
 
     std::atomic<uint64_t> launches{0};
