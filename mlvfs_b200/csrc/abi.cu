@@ -13,6 +13,16 @@
 
 namespace {
 
+// $MLVB_TRACE: timestamps of the host-batch phases on stderr (debugging aid: who waits for whom)
+static void trace_point(const char *what)
+{
+    static const bool on = getenv("MLVB_TRACE") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[mlvb %9.3f ms] thread %zx: %s\n", ms, std::hash<std::thread::id>()(std::this_thread::get_id()) & 0xFFFF, what);
+}
+
 // clip + the options that shape the per-clip state: frames of a key whose first frame has been through are independent
 // of each other (ctx->async_clips, under ctx->job_mu)
 static std::string clip_option_key(const char *mlv_filename, const mlvb_options *opts)
@@ -245,7 +255,9 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
         // frame's statistics read-backs and scalar epilogues overlap the kernels of the others
         // the lanes (streams, scratch, fork event) belong to the context: concurrent host batches (mlvb_process_frames
         // has three slots) take turns here, while their copies and single-stream stages still overlap
+        trace_point("dual ISO batch: waiting for the lanes");
         std::lock_guard<std::mutex> lanes_lock(ctx->lanes_mu);
+        trace_point("dual ISO batch: lanes acquired");
         const size_t need = aux_bytes_for(g, opts);
         // measured on B200: frames with small scratch (C3: 5.9 MP mean23) gain up to 16 in flight, the AMaZE frames
         // (C4: 2.7 GB of tile workspaces each) are best at 8
@@ -278,6 +290,7 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
                 if (cudaEventRecord(L.done, L.stream) != cudaSuccess) lane_rc[l] = MLVB_ERR_CUDA;
             });
         for (auto &th : workers) th.join();
+        trace_point("dual ISO batch: lane threads joined");
         ctx->profiling = was_profiling;
         for (int l = 0; l < nlanes; l++) {
             MLVB_CUDA_OK(cudaStreamWaitEvent(st, ctx->batch_lanes[l].done, 0));
@@ -845,6 +858,7 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
     const size_t stride = (max_bytes + (coded ? 1024 : 0) + 255) / 256 * 256;
     const size_t frame_px = (g.npix + 127) / 128 * 128;                       // 256-byte aligned frames
 
+    trace_point("process_frames: enter");
     BatchSlot *b = acquire_batch_slot(ctx);
     cudaStream_t st = b->stream;
     bool per_frame_status = false;                       // results[] already tell which frames failed
@@ -870,6 +884,7 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
             if (coded && payload_bytes[f] < stride)                           // a stale tail must not look like stream data
                 MLVB_CUDA_OK(cudaMemsetAsync(b->d_in + f * stride + payload_bytes[f], 0, stride - payload_bytes[f], st));
         }
+        trace_point("process_frames: H2D enqueued");
         mlvb_frame_result res0;
         r = run_pipeline(ctx, &hdrs[0], *opts, mlv_filename, b->d_in, stride, coded ? stride : max_bytes, b->d_work, b->d_out, frame_px,
                          nframes, b->d_status, b->d_aux, b->aux_cap, st, &res0);
@@ -878,7 +893,9 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
         for (int f = 0; f < nframes; f++)
             MLVB_CUDA_OK(cudaMemcpyAsync(dsts[f], b->d_out + f * frame_px, g.npix * 2, cudaMemcpyDeviceToHost, st));
         MLVB_CUDA_OK(cudaEventRecord(b->done, st));
+        trace_point("process_frames: D2H enqueued");
         MLVB_CUDA_OK(cudaEventSynchronize(b->done));
+        trace_point("process_frames: done");
         int rr = MLVB_OK;
         for (int f = 0; f < nframes; f++) {
             int s = MLVB_OK;
