@@ -167,8 +167,10 @@ int decode_payload(mlvb_context *ctx, const struct frame_headers *hdr, const Fra
 int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_options &opts, const char *mlv_filename,
                  const void *d_payload, size_t payload_stride, size_t payload_bytes, uint16_t *d_work, uint16_t *d_out,
                  size_t frame_stride, int nframes, int *d_status, void *d_aux, size_t aux_cap, cudaStream_t st,
-                 mlvb_frame_result *res)
+                 mlvb_frame_result *res, mlvb_frame_result *per_frame = nullptr)
 {
+    // res: what frame 0 reports; per_frame (optional, nframes entries, pre-filled by the caller): the fields that can
+    // differ between the frames of a batch -- whether the frame was converted and the levels that follow from it
     const FrameGeom g = geom_from_headers(hdr);
     if (g.w <= 0 || g.h <= 0) return MLVB_ERR_ARG;
     res->is_dual_iso = 0;
@@ -234,6 +236,7 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
             FrameGeom gf = g;
             if (r == 1) { gf.black *= 4; gf.white *= 4; }                          // hdr.c:1951-1952
             if (f == 0) { res->is_dual_iso = r; res->black_level = gf.black; res->white_level = gf.white; }
+            if (per_frame) { per_frame[f].is_dual_iso = r; per_frame[f].black_level = gf.black; per_frame[f].white_level = gf.white; }
             // converted: only stripes remain; not converted: the usual chain minus chroma smoothing (main.c:975)
             return run_single_iso_chain(ctx, hdr, gf, opts, mlv_filename, fa, fo, frame_stride, 1, 1, r == 1, s);
         };
@@ -819,7 +822,9 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
 
     // One device batch needs frame-independent results and one shape; anything else is pipelined frame by frame
     // over the context's slots (still one call for the host).
-    bool batch = nframes >= 2 && opts->dual_iso == 0 && opts->deflicker == 0 &&
+    // (full dual-ISO frames included: a device batch runs them on the context's lanes, all at once when the clip is
+    // primed; the preview conversion dual_iso == 1 stays per frame)
+    bool batch = nframes >= 2 && opts->dual_iso != 1 && opts->deflicker == 0 &&
                  !(hdrs[0].file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LZMA);
     for (int f = 1; f < nframes && batch; f++) batch = same_batch_shape(hdrs[0], hdrs[f]);
     if (!batch) {
@@ -886,8 +891,17 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
         }
         trace_point("process_frames: H2D enqueued");
         mlvb_frame_result res0;
+        std::vector<mlvb_frame_result> per_frame;
+        if (opts->dual_iso == 2) {                                            // frames of one clip may differ in "looks like dual ISO"
+            mlvb_frame_result init = mlvb_frame_result();
+            const FrameGeom g0 = geom_from_headers(&hdrs[0]);
+            init.black_level = g0.black; init.white_level = g0.white;
+            init.exposure_bias[0] = hdrs[0].rawi_hdr.raw_info.exposure_bias[0];
+            init.exposure_bias[1] = hdrs[0].rawi_hdr.raw_info.exposure_bias[1];
+            per_frame.assign(nframes, init);
+        }
         r = run_pipeline(ctx, &hdrs[0], *opts, mlv_filename, b->d_in, stride, coded ? stride : max_bytes, b->d_work, b->d_out, frame_px,
-                         nframes, b->d_status, b->d_aux, b->aux_cap, st, &res0);
+                         nframes, b->d_status, b->d_aux, b->aux_cap, st, &res0, per_frame.empty() ? nullptr : per_frame.data());
         if (r) return r;
         if (coded) MLVB_CUDA_OK(cudaMemcpyAsync(b->h_status, b->d_status, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
         for (int f = 0; f < nframes; f++)
@@ -903,7 +917,7 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
                 fprintf(stderr, "libmlvfs_b200: LJ92: frame %d of the batch failed (%d)\n", f, b->h_status[f]);    // main.c:671-679
                 s = rr = MLVB_ERR_ARG;
             }
-            if (results) { results[f] = res0; results[f].status = s; }
+            if (results) { results[f] = per_frame.empty() ? res0 : per_frame[f]; results[f].status = s; }
         }
         per_frame_status = true;
         return rr;
