@@ -824,7 +824,8 @@ int mlvb_process_frames(mlvb_context *ctx, int nframes, const struct frame_heade
     // over the context's slots (still one call for the host).
     // (full dual-ISO frames included: a device batch runs them on the context's lanes, all at once when the clip is
     // primed; the preview conversion dual_iso == 1 stays per frame)
-    bool batch = nframes >= 2 && opts->dual_iso != 1 && opts->deflicker == 0 &&
+    static const bool diso_batches = getenv("MLVB_DISO_HOST_BATCH") != nullptr;     // measured slower end to end (below)
+    bool batch = nframes >= 2 && (opts->dual_iso == 0 || (opts->dual_iso == 2 && diso_batches)) && opts->deflicker == 0 &&
                  !(hdrs[0].file_hdr.videoClass & MLVB_VIDEO_CLASS_FLAG_LZMA);
     for (int f = 1; f < nframes && batch; f++) batch = same_batch_shape(hdrs[0], hdrs[f]);
     if (!batch) {

@@ -65,6 +65,29 @@ struct CudaCtx {
     __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }
 };
 
+// squeezed[y]: the half-height row later stages index with (0 for dropped rows, like the reference's zero-initialised
+// array); sq_dst[y]: the row actually written (-1: none).  The reference walks the rows of one exposure in order and
+// gives them consecutive rows yh starting at the exposure's first row (dark) or h / 4 * 2 + its first row (bright),
+// stopping at yh >= h (hdr.c:977-1026): with the period-4 row pattern that is a closed form in y.
+__global__ void amz_row_maps_kernel(int *__restrict__ squeezed, int *__restrict__ sq_dst, int h, int b0, int b1, int b2, int b3)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    const int isb[4] = {b0, b1, b2, b3};
+    const int p = isb[y & 3];
+    int per = 0, before = 0, first = -1;
+    for (int k = 0; k < 4; k++) {
+        if (isb[k] != p) continue;
+        if (first < 0) first = k;
+        per++;
+        if (k < (y & 3)) before++;
+    }
+    const int yh = (p ? h / 4 * 2 + first : first) + (y >> 2) * per + before;
+    const bool ok = yh < h;
+    squeezed[y] = ok ? yh : 0;
+    sq_dst[y] = ok ? yh : -1;
+}
+
 __global__ void amz_squeeze_kernel(const uint32_t *__restrict__ raw32, float *__restrict__ rawf, const int *__restrict__ sq_dst,
                                    int w, int h, int ws, int black)
 {
@@ -199,25 +222,8 @@ int launch_amaze_stage(const uint32_t *d_raw32, int w, int h, int black, int whi
         return MLVB_ERR_UNSUPPORTED;
     }
     const int ws = w + 16;
-    // row maps of the squeeze (hdr.c:977-1026): squeezed[y] is what later stages index with (0 for dropped
-    // rows, like the reference's zero-initialised array), sq_dst[y] the row actually written (-1: none)
-    std::vector<int> sq(2 * (size_t)h, 0);
-    int *squeezed = sq.data(), *dst = sq.data() + h;
-    for (int y = 0; y < h; y++) dst[y] = -1;
-    for (int pass = 0; pass < 2; pass++) {
-        int yh = -1;
-        for (int y = 0; y < h; y++) {
-            if (is_bright[y % 4] != pass) continue;
-            if (yh < 0) yh = pass ? h / 4 * 2 + y : y;
-            if (yh >= h) break;                                          // cannot happen for the dark pass; guards the write
-            squeezed[y] = yh; dst[y] = yh;
-            yh++;
-            if (pass && yh >= h) break;
-        }
-    }
-    MLVB_CUDA_OK(cudaMemcpyAsync(A.squeezed, squeezed, (size_t)h * 4, cudaMemcpyHostToDevice, st));
-    MLVB_CUDA_OK(cudaMemcpyAsync(A.sq_dst, dst, (size_t)h * 4, cudaMemcpyHostToDevice, st));
-    MLVB_CUDA_OK(cudaStreamSynchronize(st));                              // `sq` is pageable and dies with this scope
+    // row maps of the squeeze (hdr.c:977-1026), computed on the device (no host copy, no synchronisation per frame)
+    amz_row_maps_kernel<<<ceil_div(h, 256), 256, 0, st>>>(A.squeezed, A.sq_dst, h, is_bright[0], is_bright[1], is_bright[2], is_bright[3]);
     MLVB_CUDA_OK(cudaMemsetAsync(A.rawf, 0, (size_t)ws * h * 4, st));
     MLVB_CUDA_OK(cudaMemsetAsync(A.counter, 0, sizeof(unsigned), st));
     const dim3 g2(ceil_div(w, 256), h);
