@@ -13,9 +13,10 @@
 // matching), each a histogram / selection kernel plus a tiny scalar epilogue on the host (the same
 // integer logic as the reference, O(bins)); everything per-pixel runs on the GPU.  Statistics are
 // exact integers; the per-pixel blends use IEEE fp64 without FMA contraction (-fmad=false) like the
-// reference's SSE2 code; log2/cos/pow inside the mixing curves come from CUDA's fp64 library
-// (<= 2 ulp from glibc), which can move a blend by one EV-LUT step (1/32768 EV) at most: the stage
-// is a tolerance stage (<= 1 DN on the 16-bit output) as the north star states.
+// reference's SSE2 code.  The 20-bit EV tables and fullres_curve (a function of black only) are built on the host with
+// glibc, so they are the reference's own values; only the per-frame mix_curve is evaluated with CUDA's fp64 log2 / cos
+// (<= 2 ulp from glibc), which can move a half-resolution blend by one EV-LUT step (1/32768 EV) at most: the stage is
+// a tolerance stage (<= 1 DN on the 16-bit output) as the north star states; every test so far measures 0 DN.
 #include <math.h>
 #include <string.h>
 
@@ -382,13 +383,6 @@ __global__ void diso_interp_kernel(const int *__restrict__ ev32, const uint32_t 
     fullres[i] = f;
 }
 
-__device__ __forceinline__ double fullres_curve_at(int i, int black)         // hdr.c:904-909
-{
-    const double ev2 = log2(fmax((double)i / 64.0 - (double)black / 64.0, 1.0));
-    const double c2 = -cos(fmax(fmin(ev2 - 4.0, 4.0), 0.0) * M_PI / 4.0);
-    return (c2 + 1.0) / 2.0;
-}
-
 // the two blending curves as tables over the 20-bit bright sample, like the reference's own mix_curve /
 // fullres_curve arrays: fullres_curve depends on black only, mix_curve on this frame's exposure match
 __device__ __forceinline__ void curve_limits(int i, double v, int *__restrict__ lim, bool valid = true)
@@ -413,13 +407,6 @@ __device__ __forceinline__ void curve_limits(int i, double v, int *__restrict__ 
 }
 __global__ void diso_curve_lim_init_kernel(int *__restrict__ lim) { lim[0] = N20; lim[1] = 0; lim[2] = N20; lim[3] = 0; }
 
-__global__ void diso_fullres_curve_kernel(double *__restrict__ curve, int *__restrict__ lim, int black)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // grid covers N20 exactly
-    const double v = fullres_curve_at(i, black);
-    curve[i] = v;
-    curve_limits(i, v, lim);
-}
 // Only [i0, i1) is evaluated: the host derives from the curve's formula where it is flat (exactly 0.0 up to
 // ev = max_ev - overlap, exactly 1.0 from ev = max_ev on) and pads that by two sample units; entries outside are never
 // read (the readers clamp the index into [lim[0], lim[1]), and both limits lie inside the evaluated range).
@@ -437,14 +424,8 @@ __global__ void diso_mix_curve_kernel(double *__restrict__ curve, int *__restric
     }
     curve_limits(i, k, lim, in);
 }
-// table value with the flat ends answered from the limits (exactly 0.0 below lim[0], exactly 1.0 from lim[1] on)
-__device__ __forceinline__ double curve_at(const double *__restrict__ curve, const int *__restrict__ lim, int i)
-{
-    if (i < __ldg(lim)) return 0.0;
-    if (i >= __ldg(lim + 1)) return 1.0;
-    return __ldg(curve + i);
-}
-// The same value without a branch: the fetch always happens, from an index clamped into the non-flat range (a neighbour
+// Table value with the flat ends answered from the limits (exactly 0.0 below lo = lim[0], exactly 1.0 from hi = lim[1] on).
+// No branch: the fetch always happens, from an index clamped into the non-flat range (a neighbour
 // of what the other lanes fetch), and the flat ends are selected afterwards.  Lets the compiler issue the gathers of
 // several pixels of one thread back to back.
 __device__ __forceinline__ double curve_at_nb(const double *__restrict__ curve, int lo, int hi, int i)
@@ -452,12 +433,6 @@ __device__ __forceinline__ double curve_at_nb(const double *__restrict__ curve, 
     const int j = hi > lo ? min(max(i, lo), hi - 1) : 0;
     const double v = __ldg(curve + j);
     return i < lo ? 0.0 : (i >= hi ? 1.0 : v);
-}
-__device__ __forceinline__ bool fullres_above_thr(const double *__restrict__ curve, const int *__restrict__ lim, int i)
-{
-    const int lo = __ldg(lim + 2), hi = __ldg(lim + 3);
-    if (lo == hi) return i >= lo;
-    return __ldg(curve + i) > FULLRES_THR;
 }
 
 // half-res blend (hdr.c:1562-1611) + overexposure flags (hdr.c:1627-1633) + alias-map skip mask
@@ -1130,10 +1105,24 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
             MLVB_CUDA_OK(cudaMemcpy(S->d_ev2raw_0, e2r.data(), 24 * EVR * sizeof(int), cudaMemcpyHostToDevice));
             MLVB_CUDA_OK(cudaMalloc(&S->d_fullres_curve, (size_t)N20 * sizeof(double)));
             MLVB_CUDA_OK(cudaMalloc(&S->d_fullres_lim, 4 * sizeof(int)));
-            diso_curve_lim_init_kernel<<<1, 1, 0, st>>>(S->d_fullres_lim);
-            diso_fullres_curve_kernel<<<N20 / 256, 256, 0, st>>>(S->d_fullres_curve, S->d_fullres_lim, black);
-            MLVB_CUDA_OK(stream_wait(ctx, st));                            // complete before the set is published to other streams
-            ctx->launches += 1;
+            {
+                // fullres_curve depends on black only (hdr.c:890-913): built once per black level on the HOST with glibc's
+                // log2 / cos, so every entry is the reference's own value (the per-frame mix_curve stays device-built)
+                std::vector<double> fc((size_t)N20);
+                int lim[4] = {N20, 0, N20, 0};
+                for (int i = 0; i < N20; i++) {
+                    const double ev2 = log2(std::max((double)i / 64.0 - (double)black / 64.0, 1.0));
+                    const double c2 = -cos(std::min(std::max(ev2 - 4.0, 0.0), 4.0) * M_PI / 4.0);
+                    const double f = (c2 + 1.0) / 2.0;
+                    fc[i] = f;
+                    if (f != 0.0 && i < lim[0]) lim[0] = i;
+                    if (f != 1.0) lim[1] = i + 1;
+                    if (f > FULLRES_THR && i < lim[2]) lim[2] = i;
+                    if (!(f > FULLRES_THR)) lim[3] = i + 1;
+                }
+                MLVB_CUDA_OK(cudaMemcpy(S->d_fullres_curve, fc.data(), (size_t)N20 * sizeof(double), cudaMemcpyHostToDevice));
+                MLVB_CUDA_OK(cudaMemcpy(S->d_fullres_lim, lim, sizeof(lim), cudaMemcpyHostToDevice));
+            }
             S->black = black; S->white = white;
             if (T->current) T->retired.push_back(std::move(T->current));
             T->current = S;
