@@ -96,6 +96,11 @@ struct CsParams {
     int stripes;                  // fused stripes epilogue (uint16 only)
     int black16, white16;
     int coef[8];
+    // Optional (dual-ISO planes): where the consumer provably never reads the smoothed sample: pixel i is dead iff
+    // (dead_flags[i] & dead_mask) == dead_mask (dualiso.cu: final blend).  A quad whose R and B sites are both dead skips
+    // its medians and table lookups (its samples pass through).
+    const uint8_t *dead_flags;
+    int dead_mask;
 };
 
 template <typename T, int METHOD>
@@ -113,6 +118,29 @@ chroma_smooth_kernel(const T *__restrict__ in_base, T *__restrict__ out_base, co
     const bool even_w = (w & 1) == 0;
     const int qx0 = blockIdx.x * CS_TQX - G::R, qy0 = blockIdx.y * CS_TQY - G::R;
 
+    auto quad_dead = [&](int x, int y) {                       // R at (x, y), B at (x + 1, y + 1)
+        if (x + 1 >= w || y + 1 >= h) return false;
+        const int m = P.dead_mask;
+        return (P.dead_flags[x + (size_t)y * w] & m) == m && (P.dead_flags[x + 1 + (size_t)(y + 1) * w] & m) == m;
+    };
+    unsigned dead_bits = 0;                                     // bit k: this thread's k-th quad of pass 2 is dead
+    if (P.dead_mask) {                                          // whole tile dead: copy through, no gathers, no medians
+        int live = 0, k = 0;
+        for (int i = threadIdx.x; i < CS_TQX * CS_TQY; i += CS_THREADS, k++) {
+            const int ty = i / CS_TQX, tx = i - ty * CS_TQX;
+            const int x = 2 * (blockIdx.x * CS_TQX + tx), y = 2 * (blockIdx.y * CS_TQY + ty);
+            if (x < w && y < h) { if (quad_dead(x, y)) dead_bits |= 1u << k; else live = 1; }
+        }
+        if (!__syncthreads_or(live)) {
+            for (int i = threadIdx.x; i < CS_TQX * CS_TQY; i += CS_THREADS) {
+                const int ty = i / CS_TQX, tx = i - ty * CS_TQX;
+                const int x = 2 * (blockIdx.x * CS_TQX + tx), y = 2 * (blockIdx.y * CS_TQY + ty);
+                if (x < w && y < h) store_quad(out, w, h, x, y, even_w, load_quad(in, w, h, x, y, even_w));
+            }
+            return;
+        }
+    }
+
     // pass 1: EV triplets for tile + halo
     for (int i = threadIdx.x; i < G::PW * G::PH; i += CS_THREADS) {
         const int ly = i / G::PW, lx = i - ly * G::PW;
@@ -129,13 +157,13 @@ chroma_smooth_kernel(const T *__restrict__ in_base, T *__restrict__ out_base, co
     __syncthreads();
 
     // pass 2: medians + rewrite
-    for (int i = threadIdx.x; i < CS_TQX * CS_TQY; i += CS_THREADS) {
+    for (int i = threadIdx.x, k2 = 0; i < CS_TQX * CS_TQY; i += CS_THREADS, k2++) {
         const int ty = i / CS_TQX, tx = i - ty * CS_TQX;
         const int x = 2 * (blockIdx.x * CS_TQX + tx), y = 2 * (blockIdx.y * CS_TQY + ty);
         if (x >= w || y >= h) continue;
         Quad<T> q = load_quad(in, w, h, x, y, even_w);
         // chroma_smooth.c:26-28 loop bounds
-        if (y >= 4 && y < h - 5 && x >= 4 && x < w - 4) {
+        if (y >= 4 && y < h - 5 && x >= 4 && x < w - 4 && !(dead_bits >> k2 & 1)) {
             const int ly = ty + G::R, lx = tx + G::R;
             const int ge = s_ge[ly][lx];
             if (ge >= 2 * MLVB_EV_RES) {
@@ -361,10 +389,11 @@ int launch_chroma_smooth_u16(const uint16_t *d_in, uint16_t *d_out, int w, int h
 }
 
 int launch_chroma_smooth_u32(const uint32_t *d_in, uint32_t *d_out, int w, int h, int method, const int *d_raw2ev,
-                             const int *d_ev2raw, cudaStream_t st)
+                             const int *d_ev2raw, cudaStream_t st, const uint8_t *d_dead_flags, int dead_mask)
 {
     CsParams P = {};
     P.w = w; P.h = h; P.black = 0;
+    P.dead_flags = d_dead_flags; P.dead_mask = d_dead_flags ? dead_mask : 0;
     P.raw2ev = d_raw2ev; P.ev2raw_i32 = d_ev2raw; P.ev2raw_u16 = nullptr;
     P.frame_stride = (size_t)w * h;
     switch (method) {

@@ -446,6 +446,7 @@ __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_
     if (t >= half) return;
     const int mlo = __ldg(P.mix_lim), mhi = __ldg(P.mix_lim + 1);
     const int tlo = __ldg(P.fullres_lim + 2), thi = __ldg(P.fullres_lim + 3);
+    const int fhi1 = max(__ldg(P.fullres_lim + 1), tlo);                 // f == 1.0 from here on (and above the alias threshold)
     size_t i[K];
     bool ok[K];
     int b[K], d[K];
@@ -483,7 +484,13 @@ __global__ void diso_mix_kernel(const uint32_t *__restrict__ dark, const uint32_
         if (!ok[k]) continue;
         halfres[i[k]] = hr[k];
         over[i[k]] = (b[k] >= P.white_darkened || d[k] >= P.white) ? 100 : 0;
-        skip[i[k]] = tlo == thi ? ((b[k] & 0xFFFFF) >= tlo) : (fc[k] > FULLRES_THR);
+        const bool sk = tlo == thi ? ((b[k] & 0xFFFFF) >= tlo) : (fc[k] > FULLRES_THR);
+        // 3: besides, the final blend takes its full-resolution weight f as exactly 1 here (fullres_curve == 1.0 from
+        // fullres_lim[1] on, and the dark-area limit (sig - black) / (4 DARK_NOISE) does not cut it): it never reads the
+        // smoothed half-resolution sample, and the smoothed full-resolution one only where the blurred overexposure
+        // flag is set -- the chroma smoothing skips such sites (chroma.cu: dead_mode)
+        const bool full = (b[k] & 0xFFFFF) >= fhi1 && (int)(((uint32_t)d[k] + (uint32_t)b[k]) / 2) - P.black >= 4 * DARK_NOISE;
+        skip[i[k]] = sk ? (full ? 3 : 1) : 0;
     }
 }
 
@@ -572,7 +579,9 @@ __global__ void diso_alias34_kernel(const uint16_t *__restrict__ aux, const uint
 // uses min(blurred / 200, 1): both planes are bytes, the blurred value saturates at 200.
 // Four pixels per thread when the rows are word aligned (w % 4 == 0): per row one 32-bit load and the two bytes next
 // to it instead of twelve byte loads, one 32-bit store.
-__global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h)
+// Also folds "the blurred flag is 0" into the site flags of the mix kernel: flags 3 -> 7 (chroma smoothing of the
+// full-resolution plane skips sites with all three bits, of the half-resolution plane those with the low two).
+__global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint8_t *__restrict__ flags, int w, int h)
 {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x0 >= w) return;
@@ -597,6 +606,11 @@ __global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *_
             o |= (uint32_t)min(v, 200) << (8 * k);
         }
         *reinterpret_cast<uint32_t *>(out + i0) = o;
+        uint32_t f = *reinterpret_cast<const uint32_t *>(flags + i0), g = f;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (((f >> (8 * k)) & 3u) == 3u && ((o >> (8 * k)) & 0xFFu) == 0u) g |= 4u << (8 * k);
+        if (g != f) *reinterpret_cast<uint32_t *>(flags + i0) = g;
         return;
     }
     for (int k = 0; k < 4 && x0 + k < w; k++) {
@@ -609,6 +623,7 @@ __global__ void diso_over_blur_kernel(const uint8_t *__restrict__ in, uint8_t *_
 #undef O
         }
         out[i] = (uint8_t)min(v, 200);
+        if ((flags[i] & 3) == 3 && min(v, 200) == 0) flags[i] |= 4;
     }
 }
 
@@ -1180,16 +1195,18 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
     }
     diso_mix_kernel<<<ceil_div((np + 1) / 2, 256), 256, 0, st>>>(D.dark, D.bright, D.halfres, D.over, D.skip, P);
     ctx->launches += 2;
+    // the blurred overexposure flags first: they tell the chroma smoothing where the final blend reads its output
+    diso_over_blur_kernel<<<dim3(ceil_div(ceil_div(w, 4), 128), h), 128, 0, st>>>(D.over, D.over2, D.skip, w, h);
     const uint32_t *frs = D.fullres, *hrs = D.halfres;
     if (cs_method == 2 || cs_method == 3 || cs_method == 5) {
         int rc;
         if (use_fullres) {
-            rc = launch_chroma_smooth_u32(D.fullres, D.frs, w, h, cs_method, P.raw2ev, P.ev2raw, st);
+            rc = launch_chroma_smooth_u32(D.fullres, D.frs, w, h, cs_method, P.raw2ev, P.ev2raw, st, D.skip, 7);
             if (rc) return rc;
             frs = D.frs;
             ctx->launches += 1;
         }
-        rc = launch_chroma_smooth_u32(D.halfres, D.hrs, w, h, cs_method, P.raw2ev, P.ev2raw, st);
+        rc = launch_chroma_smooth_u32(D.halfres, D.hrs, w, h, cs_method, P.raw2ev, P.ev2raw, st, D.skip, 3);
         if (rc) return rc;
         hrs = D.hrs;
         ctx->launches += 1;
@@ -1202,7 +1219,6 @@ static int hdr_interpolate_impl(mlvb_context *ctx, uint16_t *d_img, int w, int h
         diso_alias34_kernel<<<dim3(ceil_div((w + 1) / 2, 128), (h + 1) / 2), 128, 0, st>>>(D.aux, D.skip, D.amap, w, h);
         ctx->launches += 3;
     }
-    diso_over_blur_kernel<<<dim3(ceil_div(ceil_div(w, 4), 128), h), 128, 0, st>>>(D.over, D.over2, w, h);
     diso_final_kernel<<<dim3(ceil_div(w, 256), (h + 1) / 2), 256, 0, st>>>(D.dark, D.bright, D.fullres, frs, hrs, D.over2, D.amap, d_img, P);
     ctx->launches += 2;
     MLVB_CUDA_OK(cudaGetLastError());

@@ -23,7 +23,7 @@ int launch_chroma_smooth_u16(const uint16_t *d_in, uint16_t *d_out, int w, int h
                              int black, int method, const EvLuts &luts, const StripeCoef *stripes, int white,
                              cudaStream_t st);
 int launch_chroma_smooth_u32(const uint32_t *d_in, uint32_t *d_out, int w, int h, int method, const int *d_raw2ev,
-                             const int *d_ev2raw, cudaStream_t st);
+                             const int *d_ev2raw, cudaStream_t st, const uint8_t *d_dead_flags = nullptr, int dead_mask = 0);
 int launch_stripes_apply(uint16_t *d_img, int w, size_t npix, size_t frame_stride, int nframes, int black, int white,
                          const StripeCoef *sc, cudaStream_t st);
 
