@@ -135,6 +135,22 @@ AMZ_HD float bound_cd(float cd, float c0, float n1, float n2, float sgn)
 }
 AMZ_HD float var3(float a, float b, float c) { return 3.0f * (sq(a) + sq(b) + sq(c)) - sq(a + b + c); }
 
+// (row, column) of the flat index idx = tid, tid + nthr, ... over rows of n cells: one division per loop instead of one
+// per iteration (the passes below are loops of ~90 iterations per thread)
+struct Strider {
+    int row, col, q, r, n;
+    AMZ_HD Strider(int tid, int nthr, int n_) : n(n_ > 0 ? n_ : 1)
+    {
+        row = tid / n; col = tid - row * n;
+        q = nthr / n; r = nthr - q * n;
+    }
+    AMZ_HD void step()
+    {
+        col += r; row += q;
+        if (col >= n) { col -= n; row++; }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------------
 template <class Ctx>
 AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float *__restrict__ raw, float *__restrict__ red,
@@ -171,8 +187,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- load + mirrored borders (:378-469); the bottom border may run past row 159 like the reference's ----
     {
         const int rrend = G.rrmax < rr1 ? G.rrmax + 16 : rr1;
-        for (int idx = tid; idx < rrend * cc1; idx += nthr) {
-            const int rr = idx / cc1, cc = idx - rr * cc1;
+        Strider sd0(tid, nthr, cc1);
+        for (int idx = tid; idx < rrend * cc1; idx += nthr, sd0.step()) {
+            const int rr = sd0.row, cc = sd0.col;
             const bool tb = rr < G.rrmin, bb = rr >= G.rrmax, lb = cc < G.ccmin, rb = cc >= G.ccmax;
             const int rl = rr - G.rrmax, cl = cc - G.ccmax;              // local indices inside the bottom / right border
             int sr, sc, fr = rr, fcc = cc;
@@ -198,8 +215,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- gradients, directional weights (:553-567) and diagonal gradients (:581-606) ----
     {
         const int cw = cdiv(cc1, 4) * 4, nrow = rr1 - 4;
-        for (int idx = tid; idx < nrow * cw; idx += nthr) {
-            const int rr = 2 + idx / cw, cc = idx % cw, i = rr * TS + cc;
+        Strider sd1(tid, nthr, cw);
+        for (int idx = tid; idx < nrow * cw; idx += nthr, sd1.step()) {
+            const int rr = 2 + sd1.row, cc = sd1.col, i = rr * TS + cc;
             pf(cfa, i + V2 + pfd);
             const float delh = ab(cfa[i + 1] - cfa[i - 1]), delv = ab(cfa[i + V1] - cfa[i - V1]);
             W.dirwts1[i] = AMZ_EPS + ab(cfa[i + 2] - cfa[i]) + ab(cfa[i] - cfa[i - 2]) + delh;
@@ -207,8 +225,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             W.delhvsqsum[i] = delh * delh + delv * delv;
         }
         const int np = 4 * cdiv(cc1 - 12, 8), nrow6 = rr1 - 12;
-        for (int idx = tid; idx < nrow6 * np; idx += nthr) {
-            const int rr = 6 + idx / np, cc = 6 + 2 * (idx % np), i = rr * TS + cc;
+        Strider sd2(tid, nthr, np);
+        for (int idx = tid; idx < nrow6 * np; idx += nthr, sd2.step()) {
+            const int rr = 6 + sd2.row, cc = 6 + 2 * sd2.col, i = rr * TS + cc;
             const int o = (fc(rr, 2) & 1) ? 0 : 1, g = i + o, c = i + (1 - o);
             const float t = cfa[g];
             W.delp[i >> 1] = ab(cfa[c + P1] - cfa[c - P1]);
@@ -223,8 +242,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- H/V colour differences (:633-689) and the diagonal R/B estimates (:1115-1180) ----
     {
         const int nc = 4 * cdiv(cc1 - 11, 4), nrow = rr1 - 8;
-        for (int idx = tid; idx < nrow * nc; idx += nthr) {
-            const int rr = 4 + idx / nc, cc = 4 + idx % nc, i = rr * TS + cc;
+        Strider sd3(tid, nthr, nc);
+        for (int idx = tid; idx < nrow * nc; idx += nthr, sd3.step()) {
+            const int rr = 4 + sd3.row, cc = 4 + sd3.col, i = rr * TS + cc;
             const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;
             const float *d0 = W.dirwts0, *d1 = W.dirwts1;
             pf(cfa, i + V2 + pfd); pf(d0, i + V2 + pfd); pf(d1, i + pfd);
@@ -254,8 +274,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         const int nrow8 = rr1 - 16;
         for (int par = 0; par < 2; par++) {                               // rows of one parity share a site count
             const int ns = 4 * cdiv(cc1 - 16 - par, 8), nr = (nrow8 + 1 - par) / 2;      // rows 8+par, 10+par, ...
-            for (int idx = tid; idx < nr * ns; idx += nthr) {
-                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+            Strider sd4(tid, nthr, ns);
+            for (int idx = tid; idx < nr * ns; idx += nthr, sd4.step()) {
+                const int rr = 8 + par + 2 * (sd4.row), cc = 8 + par + 2 * sd4.col, i = rr * TS + cc, i1 = i >> 1;
                 pf(cfa, i + M2 + 2 * pfd); pfh(W.delm, i + M2 + 2 * pfd); pfh(W.delp, i + M2 + 2 * pfd);
                 pfh(W.Dgrbsq1m, i + V2 + 2 * pfd); pfh(W.Dgrbsq1p, i + V2 + 2 * pfd);
                 const float c0 = cfa[i];
@@ -326,8 +347,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             const float h = (havar < var3(hm2, h0, horig[i + 2])) ? ha : h0;
             return bound_cd(h, cfa[i], cfa[i - 1], cfa[i + 1], sgn);
         };
-        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * ncol; idx += nthr) {
-            const int rr = 4 + idx / ncol, t = idx % ncol, cc = 4 + t, i = rr * TS + cc;
+        Strider sd5(tid, nthr, ncol);
+        for (int idx = tid; idx < (nrow > 0 ? nrow : 0) * ncol; idx += nthr, sd5.step()) {
+            const int rr = 4 + sd5.row, t = sd5.col, cc = 4 + t, i = rr * TS + cc;
             const float sgn = ((rr + cc) & 1) ? -1.0f : 1.0f;             // the same for column cc - 2
             pf(horig, i + pfd); pf(W.hcdalt, i + pfd); pf(cfa, i + pfd);
             float hm2 = horig[i - 2];
@@ -374,8 +396,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- H/V weight (:876-920) and Nyquist texture test (:967-996) ----
     for (int par = 0; par < 2; par++) {
         const int ns = 4 * cdiv(cc1 - 12 - par, 8), nr = (rr1 - 12 + 1 - par) / 2;
-        for (int idx = tid; idx < nr * ns; idx += nthr) {
-            const int rr = 6 + par + 2 * (idx / ns), cc = 6 + par + 2 * (idx % ns), i = rr * TS + cc;
+        Strider sd6(tid, nthr, ns);
+        for (int idx = tid; idx < nr * ns; idx += nthr, sd6.step()) {
+            const int rr = 6 + par + 2 * (sd6.row), cc = 6 + par + 2 * sd6.col, i = rr * TS + cc;
             const float *vcd = W.vcd, *hcd = W.hcd, *d0 = W.dirwts0, *d1 = W.dirwts1;
             pf(vcd, i + V3 + 2 * pfd); pf(hcd, i + 2 * pfd); pf(d0, i + V1 + 2 * pfd); pf(d1, i + 2 * pfd);
             pf(W.dgintv, i + V2 + 2 * pfd); pf(W.dginth, i + 2 * pfd);
@@ -400,8 +423,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             hvwt[i >> 1] = dec ? varwt : diffwt;
         }
         const int nq = cdiv(cc1 - 12 - par, 2);
-        for (int idx = tid; idx < nr * nq; idx += nthr) {
-            const int rr = 6 + par + 2 * (idx / nq), cc = 6 + par + 2 * (idx % nq), i = rr * TS + cc;
+        Strider sd7(tid, nthr, nq);
+        for (int idx = tid; idx < nr * nq; idx += nthr, sd7.step()) {
+            const int rr = 6 + par + 2 * (sd7.row), cc = 6 + par + 2 * sd7.col, i = rr * TS + cc;
             const float *q = W.cddiffsq, *d = W.delhvsqsum;
             pf(q, i + V2 + 2 * pfd); pf(d, i + V2 + 2 * pfd);
             float nyqtest = (gaussodd[0] * q[i] + gaussodd[1] * (q[i - M1] + q[i + P1] + q[i - P1] + q[i + M1]) +
@@ -496,8 +520,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         // ---- area interpolation inside Nyquist regions (:1016-1045) ----
         for (int par = 0; par < 2; par++) {
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
-            for (int idx = tid; idx < nr * ns; idx += nthr) {
-                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+            Strider sd8(tid, nthr, ns);
+            for (int idx = tid; idx < nr * ns; idx += nthr, sd8.step()) {
+                const int rr = 8 + par + 2 * (sd8.row), cc = 8 + par + 2 * sd8.col, i = rr * TS + cc;
                 pf(cfa, i + 7 * TS + 2 * pfd);
                 if (!nyquist[i >> 1]) continue;
                 float sumh = 0, sumv = 0, sumsqh = 0, sumsqv = 0, areawt = 0;
@@ -592,8 +617,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
         // ---- G at R/B sites with the final hvwt (:1063-1074) ----
         for (int par = 0; par < 2; par++) {
             const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
-            for (int idx = tid; idx < nr * ns; idx += nthr) {
-                const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+            Strider sd9(tid, nthr, ns);
+            for (int idx = tid; idx < nr * ns; idx += nthr, sd9.step()) {
+                const int rr = 8 + par + 2 * (sd9.row), cc = 8 + par + 2 * sd9.col, i = rr * TS + cc, i1 = i >> 1;
                 pf(W.hcd, i + 2 * pfd); pf(W.vcd, i + 2 * pfd); pfh(hvwt, i + 2 * pfd); pf(cfa, i + 2 * pfd); pf(rgbgreen, i + V1 + 2 * pfd);
                 const float d = W.hcd[i] * (1.0f - hvwt[i1]) + W.vcd[i] * hvwt[i1];
                 W.Dgrb0[i1] = d;
@@ -614,8 +640,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
 #define AMZ_D2V(k) W.Dgrb2[2 * ((k) >> 1) + 1]
             for (int par = 0; par < 2; par++) {
                 const int ns = cdiv(cc1 - 16 - par, 2), nr = (rr1 - 16 + 1 - par) / 2;
-                for (int idx = tid; idx < nr * ns; idx += nthr) {
-                    const int rr = 8 + par + 2 * (idx / ns), cc = 8 + par + 2 * (idx % ns), i = rr * TS + cc;
+                Strider sd10(tid, nthr, ns);
+                for (int idx = tid; idx < nr * ns; idx += nthr, sd10.step()) {
+                    const int rr = 8 + par + 2 * (sd10.row), cc = 8 + par + 2 * sd10.col, i = rr * TS + cc;
                     pf(W.Dgrb2, i + V2 + 2 * pfd);
                     if (!nyquist[i >> 1]) continue;
                     const float gvarh = AMZ_EPSSQ + (gquinc[0] * AMZ_D2H(i) + gquinc[1] * (AMZ_D2H(i - M1) + AMZ_D2H(i + P1) + AMZ_D2H(i - P1) + AMZ_D2H(i + M1)) +
@@ -639,8 +666,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- where the diagonal estimate discriminates better, redo G from R+B (:1287-1352) ----
     for (int par = 0; par < 2; par++) {
         const int ns = cdiv(cc1 - 24 - par, 2), nr = (rr1 - 24 + 1 - par) / 2;
-        for (int idx = tid; idx < nr * ns; idx += nthr) {
-            const int rr = 12 + par + 2 * (idx / ns), cc = 12 + par + 2 * (idx % ns), i = rr * TS + cc, i1 = i >> 1;
+        Strider sd11(tid, nthr, ns);
+        for (int idx = tid; idx < nr * ns; idx += nthr, sd11.step()) {
+            const int rr = 12 + par + 2 * (sd11.row), cc = 12 + par + 2 * sd11.col, i = rr * TS + cc, i1 = i >> 1;
             pfh(pmwt, i + 2 * pfd); pfh(hvwt, i + 2 * pfd); pfh(W.rbint, i + V1 + 2 * pfd); pf(cfa, i + V1 + 2 * pfd);
             pf(W.dirwts0, i + V1 + 2 * pfd); pf(W.dirwts1, i + 2 * pfd);
             if (ab(0.5f - pmwt[i1]) < ab(0.5f - hvwt[i1])) continue;
@@ -685,8 +713,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- split G-B out of the G-R plane at the B sites (:1358-1362) ----
     {
         const int nr = cdiv(rr1 - 12 - 13, 2), ns = cdiv(cc1 - 12 - 13, 2);
-        for (int idx = tid; idx < nr * ns; idx += nthr) {
-            const int rr = 13 + 2 * (idx / ns), cc = 13 + 2 * (idx % ns), i1 = (rr * TS + cc) >> 1;
+        Strider sd12(tid, nthr, ns);
+        for (int idx = tid; idx < nr * ns; idx += nthr, sd12.step()) {
+            const int rr = 13 + 2 * (sd12.row), cc = 13 + 2 * sd12.col, i1 = (rr * TS + cc) >> 1;
             W.Dgrb1[i1] = W.Dgrb0[i1];
             W.Dgrb0[i1] = 0.0f;
         }
@@ -698,8 +727,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     for (int par = 0; par < 2; par++) {
         const int ns = 4 * cdiv(cc1 - 28 - par, 8), nr = (rr1 - 28 + 1 - par) / 2;
         float *const D = par ? W.Dgrb0 : W.Dgrb1;                          // c = 1 - FC/2: R rows fill G-B, B rows fill G-R
-        for (int idx = tid; idx < nr * ns; idx += nthr) {
-            const int rr = 14 + par + 2 * (idx / ns), cc = 14 + par + 2 * (idx % ns), i = rr * TS + cc;
+        Strider sd13(tid, nthr, ns);
+        for (int idx = tid; idx < nr * ns; idx += nthr, sd13.step()) {
+            const int rr = 14 + par + 2 * (sd13.row), cc = 14 + par + 2 * sd13.col, i = rr * TS + cc;
 #define AMZ_G(o) D[(i + (o)) >> 1]
             pfh(D, i + M3 + 2 * pfd);
             const float wtnw = 1.0f / (AMZ_EPS + ab(AMZ_G(-M1) - AMZ_G(M1)) + ab(AMZ_G(-M1) - AMZ_G(-M3)) + ab(AMZ_G(M1) - AMZ_G(-M3)));
@@ -720,8 +750,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
     // ---- write red, blue (:1400-1445) and green (:1451-1455) ----
     {
         const int nc = cc1 - 32, nrow = rr1 - 32;
-        for (int idx = tid; idx < nrow * nc; idx += nthr) {
-            const int rr = 16 + idx / nc, cc = 16 + idx % nc, i = rr * TS + cc;
+        Strider sd14(tid, nthr, nc);
+        for (int idx = tid; idx < nrow * nc; idx += nthr, sd14.step()) {
+            const int rr = 16 + sd14.row, cc = 16 + sd14.col, i = rr * TS + cc;
             const size_t o = (size_t)(rr + top) * stride + cc + left;
             const bool is_green = ((rr + cc) & 1) != 0;
             pf(rgbgreen, i + pfd); pfh(hvwt, i + V1 + pfd); pfh(W.Dgrb0, i + V1 + pfd); pfh(W.Dgrb1, i + V1 + pfd);
@@ -737,8 +768,9 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             }
         }
         const int ng = 4 * cdiv(cc1 - 35, 4);
-        for (int idx = tid; idx < nrow * ng; idx += nthr) {
-            const int rr = 16 + idx / ng, cc = 16 + idx % ng;
+        Strider sd15(tid, nthr, ng);
+        for (int idx = tid; idx < nrow * ng; idx += nthr, sd15.step()) {
+            const int rr = 16 + sd15.row, cc = 16 + sd15.col;
             green[(size_t)(rr + top) * stride + cc + left] = rgbgreen[rr * TS + cc] * 65535.0f;
         }
     }
