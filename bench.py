@@ -43,11 +43,11 @@ sys.path.insert(0, ROOT)
 # pixel of the whole chain and of the dominant stage
 WORKLOADS = {
     "C1": dict(w=1920, h=1080, opts={}, variant={}, codec="raw", chain_bpp=3.75, stage="unpack", stage_bpp=3.75,
-               desc="C1: 1920x1080 14-bit uncompressed MLV, plain unpack -> DNG", frames=256, e2e_chunk=16,
+               desc="C1: 1920x1080 14-bit uncompressed MLV, plain unpack -> DNG", frames=256, e2e_chunk=8,
                kernel="unpack_groups_kernel<14>", cli=[]),
     "C2": dict(w=1920, h=1080, opts=dict(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=1),
                variant=dict(hot_cold=True, stripes=True), codec="raw", chain_bpp=3.75, stage="chroma", stage_bpp=3.75,
-               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256, e2e_chunk=16,
+               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256, e2e_chunk=8,
                kernel="fused3_wide_kernel (unpack + bad-pixel patches + 3x3 median chroma smoothing + stripes, one pass; persistent, EV tables in shared memory)",
                cli=["--cs3x3", "--bad-pix", "--stripes"]),
     "C3": dict(w=3840, h=1536, opts=dict(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5),
@@ -362,7 +362,7 @@ class Rig:
 
 
 def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s=1.0, e2e_s=1.5, sample_clocks=False,
-            e2e_threads=4, e2e_chunk=0, quick=False):
+            e2e_threads=3, e2e_chunk=0, quick=False):
     """One workload on this rank's GPU: device-resident steps (timed + sustained), per-stage times, e2e."""
     torch = rig.torch
     w, h = wl["w"], wl["h"]
@@ -609,7 +609,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-path", action="store_true")
     ap.add_argument("--quick", action="store_true", help="warm-up + timed steps of the headline workload only (for ncu runs)")
-    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--e2e-threads", type=int, default=3)       # measured: 8-frame chunks x 3 threads 10.85 k, 16 x 4 10.46 k (C2, same box)
     ap.add_argument("--e2e-chunk", type=int, default=0)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
