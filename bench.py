@@ -373,7 +373,10 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     distinct = min(B, distinct_frames(wl))
     base, sizes = distinct_payloads(wl)
     stride = base.shape[1]
-    packed = np.ascontiguousarray(base[np.arange(B) % distinct])
+    # this rank's shard of a clip of B * world frames (frame n -> rank n mod world), primed with the clip's frame 0
+    from mlvfs_b200 import sharding
+    own = np.array(sharding.frames_for_rank(B * rig.world, rig.rank, rig.world))
+    packed = np.ascontiguousarray(base[own % distinct])
     in_bytes = float(np.mean(sizes))
     ctx = M.Context(device=rig.local, slots=slots)
     d_in = torch.from_numpy(packed).cuda()
@@ -384,6 +387,9 @@ def measure(rig, M, name, wl, steps, warmup, slots, frames_per_step=0, sustain_s
     def step():
         ctx.process_batch_device(hdr, opts, clip, d_in.data_ptr(), stride, stride, d_out.data_ptr(), npix, B, stream.cuda_stream)
 
+    d_prime = torch.from_numpy(np.ascontiguousarray(base[np.array(sharding.prime_frames(rig.rank, rig.world)) % distinct])).cuda()
+    ctx.process_batch_device(hdr, opts, clip, d_prime.data_ptr(), stride, stride, d_out.data_ptr(), npix, d_prime.shape[0],
+                             stream.cuda_stream)                 # per-clip state from frame 0 on every rank
     W_ = max(warmup, 3)
     for _ in range(W_):
         step()

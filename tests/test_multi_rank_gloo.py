@@ -41,3 +41,22 @@ def test_frame_sharding_world_size_2(tmp_path):
         [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
          "--master-port", "29531", str(script)], env=env, text=True, stderr=subprocess.STDOUT, timeout=240)
     assert "OK" in out, out
+
+
+def test_in_process_chunk_dealing_matches_the_host_layer():
+    """sharding.gpu_for_frame mirrors host/frame_builder.c (context_for_frame: (frame / chunk) % contexts): every frame on
+    exactly one GPU, a look-ahead chunk never split, and every shard primed with the clip's frame 0."""
+    import re
+    from mlvfs_b200 import sharding
+    src = open(os.path.join(ROOT, "mlvfs_b200", "host", "frame_builder.c")).read()
+    assert re.search(r"g_ctx\[\(frame / g_chunk\) % g_nctx\]", src), "the C dealing changed: update mlvfs_b200/sharding.py"
+    for nframes, chunk, g in [(37, 4, 8), (256, 8, 8), (5, 16, 2), (64, 1, 3)]:
+        seen = [0] * nframes
+        for gpu in range(g):
+            for a, b in sharding.chunks_for_gpu(nframes, gpu, chunk, g):
+                assert a % chunk == 0 and b - a <= chunk
+                for n in range(a, b):
+                    assert sharding.gpu_for_frame(n, chunk, g) == gpu
+                    seen[n] += 1
+        assert seen == [1] * nframes
+    assert sharding.prime_frames(3, 8) == [0]
