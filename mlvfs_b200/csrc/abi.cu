@@ -264,7 +264,9 @@ int run_pipeline(mlvb_context *ctx, const struct frame_headers *hdr, const mlvb_
         const size_t need = aux_bytes_for(g, opts);
         // measured on B200: frames with small scratch (C3: 5.9 MP mean23) gain up to 16 in flight, the AMaZE frames
         // (C4: 2.7 GB of tile workspaces each) are best at 8
-        const int lane_cap = ctx->batch_lane_count > 0 ? ctx->batch_lane_count : (need > ((size_t)1 << 30) ? 8 : 16);
+        // (each lane is a host thread that polls: with fewer than 8 host cores per GPU -- eight ranks on a 32-core box -- 8)
+        const int lane_cap = ctx->batch_lane_count > 0 ? ctx->batch_lane_count
+                                                       : ((need > ((size_t)1 << 30) || ctx->spin_us < 1000) ? 8 : 16);
         const int nlanes = std::min(nframes - first, lane_cap);
         if (!ctx->batch_fork) MLVB_CUDA_OK(cudaEventCreateWithFlags(&ctx->batch_fork, cudaEventDisableTiming));
         while ((int)ctx->batch_lanes.size() < nlanes) {
