@@ -261,10 +261,15 @@ void free_focus_pixel_maps(void)
 {
     mlvb_context *ctx = mlvb_default_context();
     if (!ctx) return;
-    std::lock_guard<std::mutex> lk(ctx->clip_mu);
-    ctx->focus_maps.clear();
-    for (auto &m : ctx->bad_maps) m = BadPixelMap();
-    ctx->bad_map_cursor = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->clip_mu);
+        ctx->focus_maps.clear();
+        for (auto &m : ctx->bad_maps) m = BadPixelMap();
+        ctx->bad_map_cursor = 0;
+    }
+    // no clip is "primed" any more: the next frame of every clip goes first, alone, and recreates the maps
+    std::lock_guard<std::mutex> jl(ctx->job_mu);
+    ctx->async_clips.clear();
 }
 
 // ---------------------------------------------------------------- stripes.c
