@@ -47,7 +47,7 @@ WORKLOADS = {
                kernel="unpack_groups_kernel<14>", cli=[]),
     "C2": dict(w=1920, h=1080, opts=dict(chroma_smooth=3, fix_bad_pixels=1, fix_stripes=1),
                variant=dict(hot_cold=True, stripes=True), codec="raw", chain_bpp=3.75, stage="chroma", stage_bpp=3.75,
-               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=256, e2e_chunk=8,
+               desc="C2: 1920x1080 14-bit uncompressed MLV, --stripes --bad-pix --cs3x3", frames=512, e2e_chunk=8,
                kernel="fused3_wide_kernel (unpack + bad-pixel patches + 3x3 median chroma smoothing + stripes, one pass; persistent, EV tables in shared memory)",
                cli=["--cs3x3", "--bad-pix", "--stripes"]),
     "C3": dict(w=3840, h=1536, opts=dict(dual_iso=2, hdr_interpolation_method=1, chroma_smooth=5),
