@@ -61,7 +61,7 @@ WORKLOADS = {
                kernel="dual-ISO stage (statistics + AMaZE + edge-directed interpolation + alias map + blend)",
                cli=["--dual-iso", "--amaze-edge", "--alias-map", "--really-bad-pix"]),
     "C5": dict(w=3840, h=2160, opts={}, variant={}, codec="lj92", chain_bpp=2.9, stage="lj92", stage_bpp=2.9,
-               desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=128, e2e_chunk=16,
+               desc="C5: 3840x2160 LJ92-compressed MLV, plain decode -> DNG", frames=256, e2e_chunk=16,
                kernel="LJ92 stage (unstuff + self-synchronising parallel Huffman decode + separated predictor-6 scans + untile)",
                cli=[]),
 }
