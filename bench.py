@@ -577,6 +577,8 @@ def run_ours(args, wl):
     hp = None
     if not args.only and not args.no_host_path:
         # the frame-request path in ONE process over all of this job's GPUs; the other ranks wait at the barrier
+        rig.torch.cuda.empty_cache()
+        M.lib().mlvb_host_pool_trim()            # the frame server is another process: hand back this one's pinned pool first
         if rig.rank == 0:
             hp = {args.workload: host_path(wl, rig.world, 256)}
             if rig.world > 1:
