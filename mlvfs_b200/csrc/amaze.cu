@@ -60,6 +60,13 @@ struct CudaCtx {
 #else
     __device__ __forceinline__ void prefetch(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #endif
+#if defined(AMZ_NO_STREAM)
+    __device__ __forceinline__ float ld_stream(const float *p) { return *p; }
+    __device__ __forceinline__ void st_stream(float *p, float v) { *p = v; }
+#else
+    __device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+    __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
+#endif
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
     __device__ __forceinline__ void atomic_add(int *p, int v) { atomicAdd(p, v); }

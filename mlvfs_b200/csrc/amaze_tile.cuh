@@ -204,7 +204,7 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             else if (rb)       { sr = rr + top;         sc = width - cl - 2;                        vec = false; fcc = cl; } // :426-433
             else               { sr = rr + top;         sc = cc + left;                             vec = true; }            // :381-387
             if (AMZ_PF_ROWS && sr + AMZ_PF_ROWS < height) C.prefetch(raw + (size_t)(sr + AMZ_PF_ROWS) * stride + sc);
-            const float v = raw[(size_t)sr * stride + sc] / 65535.0f;
+            const float v = C.ld_stream(raw + (size_t)sr * stride + sc) / 65535.0f;   // read 1.56 times per frame, never again
             cfa[rr * TS + cc] = v;
             if (vec || fc(fr, fcc) == 1) rgbgreen[rr * TS + cc] = v;
         }
@@ -760,18 +760,19 @@ AMZ_HD void tile_body(Ctx &C, const Ws &W, const Geom &G, Shared &S, const float
             if (is_green) {
                 const float wu = hvwt[(i - V1) >> 1], wr = 1.0f - hvwt[(i + 1) >> 1], wl = 1.0f - hvwt[(i - 1) >> 1], wd = hvwt[(i + V1) >> 1];
                 const float temp = 1.0f / (wu + wr + wl + wd);
-                red[o] = 65535.0f * (g - (wu * W.Dgrb0[(i - V1) >> 1] + wr * W.Dgrb0[(i + 1) >> 1] + wl * W.Dgrb0[(i - 1) >> 1] + wd * W.Dgrb0[(i + V1) >> 1]) * temp);
-                blue[o] = 65535.0f * (g - (wu * W.Dgrb1[(i - V1) >> 1] + wr * W.Dgrb1[(i + 1) >> 1] + wl * W.Dgrb1[(i - 1) >> 1] + wd * W.Dgrb1[(i + V1) >> 1]) * temp);
+                // the finished planes are streamed out (evict-first): they must not push workspace lines out of the L2
+                C.st_stream(red + o, 65535.0f * (g - (wu * W.Dgrb0[(i - V1) >> 1] + wr * W.Dgrb0[(i + 1) >> 1] + wl * W.Dgrb0[(i - 1) >> 1] + wd * W.Dgrb0[(i + V1) >> 1]) * temp));
+                C.st_stream(blue + o, 65535.0f * (g - (wu * W.Dgrb1[(i - V1) >> 1] + wr * W.Dgrb1[(i + 1) >> 1] + wl * W.Dgrb1[(i - 1) >> 1] + wd * W.Dgrb1[(i + V1) >> 1]) * temp));
             } else {
-                red[o] = 65535.0f * (g - W.Dgrb0[i >> 1]);
-                blue[o] = 65535.0f * (g - W.Dgrb1[i >> 1]);
+                C.st_stream(red + o, 65535.0f * (g - W.Dgrb0[i >> 1]));
+                C.st_stream(blue + o, 65535.0f * (g - W.Dgrb1[i >> 1]));
             }
         }
         const int ng = 4 * cdiv(cc1 - 35, 4);
         Strider sd15(tid, nthr, ng);
         for (int idx = tid; idx < nrow * ng; idx += nthr, sd15.step()) {
             const int rr = 16 + sd15.row, cc = 16 + sd15.col;
-            green[(size_t)(rr + top) * stride + cc + left] = rgbgreen[rr * TS + cc] * 65535.0f;
+            C.st_stream(green + (size_t)(rr + top) * stride + cc + left, rgbgreen[rr * TS + cc] * 65535.0f);
         }
     }
 }

@@ -21,6 +21,8 @@ struct HostCtx {
     void syncwarp() { wbar->arrive_and_wait(); }
     void mark(int) {}
     void prefetch(const void *) {}
+    float ld_stream(const float *p) { return *p; }
+    void st_stream(float *p, float v) { *p = v; }
     void atomic_add(int *p, int v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 };
 }  // namespace
