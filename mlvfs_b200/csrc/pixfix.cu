@@ -195,7 +195,10 @@ fix_row_runs_kernel(const FixArgs A, const unsigned *__restrict__ seg_start, uns
 constexpr int LONG_WARPS_MAX = 16;
 constexpr int LONG_CHUNK = 256;            // list entries staged per warp at a time
 constexpr int LONG_WIN = 4096;             // pixels of a row staged per warp at a time
-constexpr int LONG_WARM = 128;             // warm-up steps of a speculative piece of a dense run (walk_dense_warp)
+#ifndef LONG_WARM_CFG
+#define LONG_WARM_CFG 128
+#endif
+constexpr int LONG_WARM = LONG_WARM_CFG;    // warm-up steps of a speculative piece of a dense run (walk_dense_warp)
 constexpr int LONG_DENSE_MIN = 192;        // shortest stretch of consecutive entries handed to walk_dense_warp
 constexpr size_t LONG_WARP_BYTES = (LONG_WIN + 8 + LONG_CHUNK) * sizeof(uint16_t);   // window, entry columns
 
